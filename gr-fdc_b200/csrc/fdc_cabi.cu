@@ -1,0 +1,505 @@
+/* fdc_cabi.cu -- C ABI (include/fdc_cabi.h): library entry points, the fused throughput channelizer context and
+ * the copy/multiply/FFT block replacements.  The activity-gated blocks live in fdc_cabi_act.cu. */
+#include "fdc_cabi_internal.h"
+#include <algorithm>
+#include <cstring>
+#include <map>
+
+using namespace fdc;
+
+/* ---- error plumbing ---------------------------------------------------------------------------- */
+static thread_local std::string g_err;
+namespace fdc {
+void set_error(const std::string& s) { g_err = s; }
+int fail(const std::string& s) { g_err = s; return -1; }
+int cuda_fail(cudaError_t e, const char* what)
+{
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return -1;
+}
+bool require_device()
+{
+    int n = 0;
+    const cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        g_err = std::string("fdc_b200: no usable CUDA device (") + (e != cudaSuccess ? cudaGetErrorString(e) : "count 0") +
+                "); this library has no CPU fallback";
+        cudaGetLastError();
+        return false;
+    }
+    return true;
+}
+}  // namespace fdc
+
+extern "C" {
+
+int fdc_api_version(void) { return FDC_API_VERSION; }
+const char* fdc_last_error(void) { return g_err.c_str(); }
+int fdc_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+int fdc_set_device(int device)
+{
+    if (!require_device()) return -1;
+    const cudaError_t e = cudaSetDevice(device);
+    return e == cudaSuccess ? 0 : cuda_fail(e, "cudaSetDevice");
+}
+void* fdc_host_alloc(size_t bytes)
+{
+    void* p = 0;
+    if (!require_device()) return 0;
+    const cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) { cuda_fail(e, "cudaHostAlloc"); return 0; }
+    return p;
+}
+void fdc_host_free(void* p) { if (p) cudaFreeHost(p); }
+unsigned long long fdc_launch_count(void) { return launch_count(); }
+
+int fdc_opt_channelparams(int blocksize, int relinvovl, double freq, double bw, int* f, int* l, int* lout, double* passband,
+                          double* stopband)
+{
+    try { opt_channelparams(blocksize, relinvovl, freq, bw, f, l, lout, passband, stopband); return 0; }
+    catch (const std::exception& e) { return fail(e.what()); }
+}
+int fdc_psw_build_tables(int blocklen, int numphasestates, float passbw, float stopbw, int windowtype, float* out)
+{
+    try {
+        if (blocklen <= 0 || numphasestates <= 0) return fail("blocklen and numphasestates must be > 0");
+        psw_check_args(passbw, stopbw);
+        std::vector<std::complex<float> > t;
+        psw_tables(blocklen, numphasestates, passbw, stopbw, windowtype, t);
+        memcpy(out, t.data(), sizeof(std::complex<float>) * t.size());
+        return 0;
+    } catch (const std::exception& e) { return fail(e.what()); }
+}
+
+}  // extern "C"
+
+/* ================================================================================================
+ * fused throughput channelizer
+ * ================================================================================================ */
+struct fdc_chan {
+    int dev, N, ovl, hop, nphase, nchan;
+    bool big; int N1, N2;
+    std::vector<ChanDev> chans;
+    std::vector<int> l;
+    std::vector<std::pair<int, std::pair<int, int> > > groups;    /* (l, (first index in sel, count)) */
+    long lout_total;
+    long blockcount;
+    long chunk_blocks;                 /* blocks per K1->K2 round trip: spectrum ring sized to stay in L2 */
+    DevBuf d_chans, d_sel, d_tables, d_hist, d_hist2, d_spec, d_mid;
+    const float2 *twlo, *twhi; int tws_log2;
+    cudaStream_t stream;
+    /* host path: NSLOT pipelined chunk slots */
+    enum { NSLOT = 3 };
+    cudaStream_t hs[NSLOT];
+    DevBuf h_in[NSLOT], h_out[NSLOT], h_spec[NSLOT], h_mid[NSLOT];
+    long host_chunk;
+    fdc_chan() : stream(0), host_chunk(0) { for (int i = 0; i < NSLOT; i++) hs[i] = 0; }
+};
+
+static long pick_chunk_blocks(int N)
+{
+    /* spectrum ring of about 32 MiB: with the (equally large) four-step intermediate it stays well inside the
+     * 126 MB L2, so the K1 -> K2 hand-over does not touch HBM; never fewer than one wave of CTAs. */
+    long c = (32L << 20) / ((long)N * 8);
+    if (c < 8) c = 8;
+    return c;
+}
+
+/* enqueue K1 + K2 for nb blocks whose input starts at d_in (history at d_hist) */
+static int chan_enqueue_chunk(fdc_chan* c, const float2* d_in, const float2* d_hist, long nb, float2* d_spec, float2* d_mid,
+                              float2* d_out, long call_blocks, long call_blk0, long glob_blk0, cudaStream_t s)
+{
+    cudaError_t e;
+    if (!c->big) {
+        FwdParams p; p.in = d_in; p.hist = d_hist; p.spec = d_spec; p.nblocks = nb; p.hop = c->hop; p.ovl = c->ovl; p.N = c->N;
+        p.scale = 1.0f / (float)c->N;
+        e = launch_fwd_small(p, s);
+    } else {
+        BigParams p; p.in = d_in; p.hist = d_hist; p.mid = d_mid; p.spec = d_spec; p.twlo = c->twlo; p.twhi = c->twhi;
+        p.tws_log2 = c->tws_log2; p.nblocks = nb; p.hop = c->hop; p.ovl = c->ovl; p.scale = 1.0f / (float)c->N;
+        e = launch_fwd_big(p, c->N, s);
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "forward FFT launch");
+    if (!d_out) return 0;
+    for (size_t g = 0; g < c->groups.size(); g++) {
+        ExtractParams q; q.spec = d_spec; q.spec_stride = c->N; q.tables = (const float2*)c->d_tables.p;
+        q.chans = (const ChanDev*)c->d_chans.p; q.sel = (const int*)c->d_sel.p + c->groups[g].second.first; q.out = d_out;
+        q.nb = nb; q.call_blocks = call_blocks; q.call_blk0 = call_blk0; q.glob_blk0 = glob_blk0; q.nphase = c->nphase;
+        e = launch_extract(q, c->groups[g].first, c->groups[g].second.second, s);
+        if (e != cudaSuccess) return cuda_fail(e, "channel extract launch");
+    }
+    return 0;
+}
+
+extern "C" {
+
+fdc_chan* fdc_chan_create(int N, int ovl, int nphase, int nchan, const fdc_chan_desc* ch)
+{
+    if (!require_device()) return 0;
+    if (N < 16 || (N & (N - 1))) { fail("fdc_chan_create: N must be a power of two >= 16"); return 0; }
+    if (ovl < 0 || ovl >= N) { fail("fdc_chan_create: need 0 <= ovl < N"); return 0; }
+    if (nphase < 1) { fail("fdc_chan_create: nphase must be >= 1"); return 0; }
+    if (nchan < 0 || (nchan > 0 && !ch)) { fail("fdc_chan_create: bad channel list"); return 0; }
+    fdc_chan* c = new fdc_chan;
+    cudaGetDevice(&c->dev);
+    c->N = N; c->ovl = ovl; c->hop = N - ovl; c->nphase = nphase; c->nchan = nchan; c->blockcount = 0;
+    c->big = false; c->N1 = c->N2 = 0; c->twlo = c->twhi = 0; c->tws_log2 = 0;
+    if (!fwd_small_supported(N)) {
+        if (!fwd_big_supported(N, &c->N1, &c->N2)) { fail("fdc_chan_create: unsupported FFT length"); delete c; return 0; }
+        c->big = true;
+        big_twiddle_tables(N, &c->twlo, &c->twhi, &c->tws_log2);
+    }
+    /* channels: validate, group by l, pack tables */
+    std::vector<float2> tables;
+    std::map<int, std::vector<int> > by_l;
+    long prefix = 0;
+    for (int i = 0; i < nchan; i++) {
+        const fdc_chan_desc& d = ch[i];
+        if (!tile_len_supported(d.l)) { fail("fdc_chan_create: channel slice length must be a power of two in [2, 16384]"); delete c; return 0; }
+        if (d.f < 0 || d.f + d.l > N) { fail("fdc_chan_create: channel slice [f, f+l) outside the spectrum"); delete c; return 0; }
+        if (d.lout < 1 || d.lout > d.l) { fail("fdc_chan_create: need 1 <= lout <= l"); delete c; return 0; }
+        if (!d.table) { fail("fdc_chan_create: channel table missing"); delete c; return 0; }
+        ChanDev cd; memset(&cd, 0, sizeof(cd));
+        cd.f = d.f; cd.lout = d.lout; cd.shift = ((d.shift % nphase) + nphase) % nphase;
+        cd.tab_off = (long)tables.size(); cd.lout_prefix = prefix; cd.gain = d.gain;
+        prefix += d.lout;
+        const float2* t = (const float2*)d.table;
+        tables.insert(tables.end(), t, t + (size_t)nphase * d.l);
+        c->chans.push_back(cd); c->l.push_back(d.l); by_l[d.l].push_back(i);
+    }
+    c->lout_total = prefix;
+    std::vector<int> sel;
+    for (std::map<int, std::vector<int> >::iterator it = by_l.begin(); it != by_l.end(); ++it) {
+        c->groups.push_back(std::make_pair(it->first, std::make_pair((int)sel.size(), (int)it->second.size())));
+        sel.insert(sel.end(), it->second.begin(), it->second.end());
+    }
+    c->chunk_blocks = pick_chunk_blocks(N);
+    bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && c->d_chans.upload(c->chans.data(), sizeof(ChanDev) * c->chans.size());
+    ok = ok && c->d_sel.upload(sel.data(), sizeof(int) * sel.size());
+    ok = ok && c->d_tables.upload(tables.data(), sizeof(float2) * tables.size());
+    ok = ok && c->d_hist.reserve(sizeof(float2) * (size_t)std::max(ovl, 1)) && c->d_hist2.reserve(sizeof(float2) * (size_t)std::max(ovl, 1));
+    ok = ok && cudaMemset(c->d_hist.p, 0, sizeof(float2) * (size_t)std::max(ovl, 1)) == cudaSuccess;
+    /* warm the twiddle caches so no allocation happens inside a timed region */
+    if (ok) {
+        if (c->big) { twiddle_table(c->N1); twiddle_table(c->N2); } else twiddle_table(N);
+        for (size_t g = 0; g < c->groups.size(); g++) twiddle_table(c->groups[g].first);
+    }
+    if (!ok) { cuda_fail(cudaGetLastError(), "fdc_chan_create: device allocation"); fdc_chan_destroy(c); return 0; }
+    return c;
+}
+
+void fdc_chan_destroy(fdc_chan* c)
+{
+    if (!c) return;
+    cudaDeviceSynchronize();
+    if (c->stream) cudaStreamDestroy(c->stream);
+    for (int i = 0; i < fdc_chan::NSLOT; i++) if (c->hs[i]) cudaStreamDestroy(c->hs[i]);
+    delete c;
+}
+int fdc_chan_hop(const fdc_chan* c) { return c ? c->hop : -1; }
+long fdc_chan_blockcount(const fdc_chan* c) { return c ? c->blockcount : -1; }
+int fdc_chan_reset(fdc_chan* c)
+{
+    if (!c) return fail("null context");
+    cudaDeviceSynchronize();
+    c->blockcount = 0;
+    const cudaError_t e = cudaMemset(c->d_hist.p, 0, sizeof(float2) * (size_t)std::max(c->ovl, 1));
+    return e == cudaSuccess ? 0 : cuda_fail(e, "fdc_chan_reset");
+}
+int fdc_chan_seek(fdc_chan* c, long first_block)
+{
+    if (!c || first_block < 0) return fail("fdc_chan_seek: bad arguments");
+    c->blockcount = first_block;
+    return 0;
+}
+int fdc_chan_set_history(fdc_chan* c, const void* host)
+{
+    if (!c || !host) return fail("fdc_chan_set_history: bad arguments");
+    if (c->ovl == 0) return 0;
+    cudaDeviceSynchronize();
+    const cudaError_t e = cudaMemcpy(c->d_hist.p, host, sizeof(float2) * (size_t)c->ovl, cudaMemcpyHostToDevice);
+    return e == cudaSuccess ? 0 : cuda_fail(e, "fdc_chan_set_history");
+}
+
+/* history for the next call = the last ovl samples of [old history | this call's input] */
+static int chan_save_history(fdc_chan* c, const float2* d_in, long nblocks, cudaStream_t s)
+{
+    if (c->ovl == 0 || nblocks == 0) return 0;
+    const long n_new = nblocks * c->hop;
+    cudaError_t e;
+    if (n_new >= c->ovl) {
+        e = cudaMemcpyAsync(c->d_hist.p, d_in + (n_new - c->ovl), sizeof(float2) * (size_t)c->ovl, cudaMemcpyDeviceToDevice, s);
+    } else {
+        float2* h = (float2*)c->d_hist.p; float2* h2 = (float2*)c->d_hist2.p;
+        e = cudaMemcpyAsync(h2, h + n_new, sizeof(float2) * (size_t)(c->ovl - n_new), cudaMemcpyDeviceToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h2 + (c->ovl - n_new), d_in, sizeof(float2) * (size_t)n_new, cudaMemcpyDeviceToDevice, s);
+        c->d_hist.swap(c->d_hist2);
+    }
+    return e == cudaSuccess ? 0 : cuda_fail(e, "history save");
+}
+
+int fdc_chan_work_device(fdc_chan* c, const void* d_in_v, long nblocks, void* d_out_v, void* d_spectrum_v, void* stream)
+{
+    if (!c) return fail("null context");
+    if (nblocks < 0) return fail("nblocks < 0");
+    if (nblocks == 0) return 0;
+    const float2* d_in = (const float2*)d_in_v; float2* d_out = (float2*)d_out_v; float2* d_spectrum = (float2*)d_spectrum_v;
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    const long chunk = d_spectrum ? nblocks : std::min(nblocks, c->chunk_blocks);
+    if (!d_spectrum && !c->d_spec.reserve(sizeof(float2) * (size_t)chunk * c->N)) return cuda_fail(cudaGetLastError(), "spectrum ring");
+    if (c->big && !c->d_mid.reserve(sizeof(float2) * (size_t)std::min(nblocks, c->chunk_blocks) * c->N)) return cuda_fail(cudaGetLastError(), "four-step intermediate");
+    const long step = c->big ? std::min(chunk, c->chunk_blocks) : chunk;
+    for (long b0 = 0; b0 < nblocks; b0 += step) {
+        const long nb = std::min(step, nblocks - b0);
+        const float2* in = d_in + b0 * c->hop;
+        const float2* hist = b0 == 0 ? (const float2*)c->d_hist.p : in - c->ovl;
+        float2* spec = d_spectrum ? d_spectrum + b0 * c->N : (float2*)c->d_spec.p;
+        if (chan_enqueue_chunk(c, in, hist, nb, spec, (float2*)c->d_mid.p, d_out, nblocks, b0, c->blockcount + b0, s)) return -1;
+    }
+    if (chan_save_history(c, d_in, nblocks, s)) return -1;
+    c->blockcount += nblocks;
+    return 0;
+}
+
+int fdc_chan_sync(fdc_chan* c)
+{
+    if (!c) return fail("null context");
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    for (int i = 0; i < fdc_chan::NSLOT && e == cudaSuccess; i++) if (c->hs[i]) e = cudaStreamSynchronize(c->hs[i]);
+    return e == cudaSuccess ? 0 : cuda_fail(e, "fdc_chan_sync");
+}
+
+/* Host buffers in, host buffers out: the call is cut into chunks that are pipelined over NSLOT streams
+ * (H2D of chunk i+1 and D2H of chunk i-1 overlap the kernels of chunk i).  Every chunk after the first uploads
+ * its own ovl-sample halo from the caller's buffer, so chunks are independent. */
+int fdc_chan_work_host(fdc_chan* c, const void* in_v, long nblocks, void* const* outs, void* spectrum_v)
+{
+    if (!c) return fail("null context");
+    if (nblocks < 0) return fail("nblocks < 0");
+    if (nblocks == 0) return 0;
+    const float2* in = (const float2*)in_v; float2* spectrum = (float2*)spectrum_v;
+    const long chunk = std::min(nblocks, c->chunk_blocks);
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < fdc_chan::NSLOT; i++) {
+        if (!c->hs[i] && (e = cudaStreamCreateWithFlags(&c->hs[i], cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "stream");
+        bool ok = c->h_in[i].reserve(sizeof(float2) * (size_t)(c->ovl + chunk * c->hop)) &&
+                  c->h_out[i].reserve(sizeof(float2) * (size_t)std::max(1L, chunk * c->lout_total)) &&
+                  c->h_spec[i].reserve(sizeof(float2) * (size_t)chunk * c->N) &&
+                  (!c->big || c->h_mid[i].reserve(sizeof(float2) * (size_t)chunk * c->N));
+        if (!ok) return cuda_fail(cudaGetLastError(), "host-path staging buffers");
+    }
+    /* uniform channel layout in the caller's memory -> one 2-D copy per chunk instead of one per channel */
+    bool uniform = c->nchan > 1 && outs;
+    if (uniform) {
+        for (int i = 0; i < c->nchan && uniform; i++) {
+            if (!outs[i] || c->chans[i].lout != c->chans[0].lout) uniform = false;
+            else if (i > 0 && (const char*)outs[i] - (const char*)outs[i - 1] != (ptrdiff_t)(sizeof(float2) * nblocks * c->chans[0].lout)) uniform = false;
+        }
+    }
+    int slot = 0;
+    for (long b0 = 0; b0 < nblocks; b0 += chunk, slot = (slot + 1) % fdc_chan::NSLOT) {
+        const long nb = std::min(chunk, nblocks - b0);
+        cudaStream_t s = c->hs[slot];
+        float2* d_in = (float2*)c->h_in[slot].p;
+        if (b0 == 0) {
+            if (c->ovl) e = cudaMemcpyAsync(d_in, c->d_hist.p, sizeof(float2) * (size_t)c->ovl, cudaMemcpyDeviceToDevice, s);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(d_in + c->ovl, in, sizeof(float2) * (size_t)(nb * c->hop), cudaMemcpyHostToDevice, s);
+        } else if (b0 * c->hop >= c->ovl) {
+            e = cudaMemcpyAsync(d_in, in + (b0 * c->hop - c->ovl), sizeof(float2) * (size_t)(c->ovl + nb * c->hop), cudaMemcpyHostToDevice, s);
+        } else {
+            /* halo straddles the saved history and this call's first samples (overlap > 50 % only) */
+            const long from_hist = c->ovl - b0 * c->hop;
+            e = cudaMemcpyAsync(d_in, (float2*)c->d_hist.p + (c->ovl - from_hist), sizeof(float2) * (size_t)from_hist, cudaMemcpyDeviceToDevice, s);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(d_in + from_hist, in, sizeof(float2) * (size_t)(b0 * c->hop + nb * c->hop), cudaMemcpyHostToDevice, s);
+        }
+        if (e != cudaSuccess) return cuda_fail(e, "H2D");
+        float2* d_out = (outs && c->nchan) ? (float2*)c->h_out[slot].p : 0;
+        if (chan_enqueue_chunk(c, d_in + c->ovl, d_in, nb, (float2*)c->h_spec[slot].p, (float2*)c->h_mid[slot].p, d_out, nb, 0,
+                               c->blockcount + b0, s)) return -1;
+        if (d_out) {
+            if (uniform) {
+                const size_t lo = (size_t)c->chans[0].lout;
+                e = cudaMemcpy2DAsync((float2*)outs[0] + b0 * lo, sizeof(float2) * nblocks * lo, d_out, sizeof(float2) * nb * lo,
+                                      sizeof(float2) * nb * lo, (size_t)c->nchan, cudaMemcpyDeviceToHost, s);
+            } else {
+                for (int i = 0; i < c->nchan && e == cudaSuccess; i++) {
+                    if (!outs[i]) continue;
+                    const long lo = c->chans[i].lout;
+                    e = cudaMemcpyAsync((float2*)outs[i] + b0 * lo, d_out + nb * c->chans[i].lout_prefix, sizeof(float2) * (size_t)(nb * lo),
+                                        cudaMemcpyDeviceToHost, s);
+                }
+            }
+            if (e != cudaSuccess) return cuda_fail(e, "D2H");
+        }
+        if (spectrum) {
+            e = cudaMemcpyAsync(spectrum + b0 * c->N, c->h_spec[slot].p, sizeof(float2) * (size_t)(nb * c->N), cudaMemcpyDeviceToHost, s);
+            if (e != cudaSuccess) return cuda_fail(e, "D2H spectrum");
+        }
+    }
+    for (int i = 0; i < fdc_chan::NSLOT; i++) if ((e = cudaStreamSynchronize(c->hs[i])) != cudaSuccess) return cuda_fail(e, "sync");
+    /* history for the next call straight from the caller's buffer */
+    if (c->ovl) {
+        const long n_new = nblocks * c->hop;
+        if (n_new >= c->ovl) e = cudaMemcpy(c->d_hist.p, in + (n_new - c->ovl), sizeof(float2) * (size_t)c->ovl, cudaMemcpyHostToDevice);
+        else {
+            float2* h = (float2*)c->d_hist.p; float2* h2 = (float2*)c->d_hist2.p;
+            e = cudaMemcpy(h2, h + n_new, sizeof(float2) * (size_t)(c->ovl - n_new), cudaMemcpyDeviceToDevice);
+            if (e == cudaSuccess) e = cudaMemcpy(h2 + (c->ovl - n_new), in, sizeof(float2) * (size_t)n_new, cudaMemcpyHostToDevice);
+            c->d_hist.swap(c->d_hist2);
+        }
+        if (e != cudaSuccess) return cuda_fail(e, "history save");
+    }
+    c->blockcount += nblocks;
+    return 0;
+}
+
+}  // extern "C"
+
+/* ================================================================================================
+ * copy / multiply / FFT block replacements (host buffers)
+ * ================================================================================================ */
+struct fdc_overlap_save { int itemsize, outputlen, overlaplen; DevBuf d_in, d_out, d_hist; cudaStream_t s; };
+struct fdc_vector_cut { int itemsize, veclen, offset, blocklen; DevBuf d_in, d_out; cudaStream_t s; };
+struct fdc_psw { int blocksize, relinvovl, counter, shift; std::vector<std::complex<float> > tables; DevBuf d_tab, d_in, d_out; cudaStream_t s; };
+struct fdc_fft { int n, forward, shift; DevBuf d_in, d_out; cudaStream_t s; };
+
+extern "C" {
+
+fdc_overlap_save* fdc_overlap_save_create(int itemsize, int outputlen, int overlaplen)
+{
+    if (!require_device()) return 0;
+    if (itemsize <= 0 || outputlen <= 0 || overlaplen < 0 || overlaplen >= outputlen) { fail("overlap_save: need itemsize > 0 and 0 <= overlaplen < outputlen"); return 0; }
+    fdc_overlap_save* b = new fdc_overlap_save;
+    b->itemsize = itemsize; b->outputlen = outputlen; b->overlaplen = overlaplen; b->s = 0;
+    const size_t hb = (size_t)itemsize * std::max(overlaplen, 1);
+    /* history starts as zeros, lib/overlap_save_impl.cc:52 */
+    if (cudaStreamCreateWithFlags(&b->s, cudaStreamNonBlocking) != cudaSuccess || !b->d_hist.reserve(hb) || cudaMemset(b->d_hist.p, 0, hb) != cudaSuccess) {
+        cuda_fail(cudaGetLastError(), "overlap_save create"); fdc_overlap_save_destroy(b); return 0;
+    }
+    return b;
+}
+int fdc_overlap_save_work(fdc_overlap_save* b, int n, const void* in, void* out)
+{
+    if (!b || n < 0) return fail("overlap_save work: bad arguments");
+    if (n == 0) return 0;
+    const long inplen = b->outputlen - b->overlaplen;
+    const size_t ib = (size_t)n * inplen * b->itemsize, ob = (size_t)n * b->outputlen * b->itemsize, hb = (size_t)b->overlaplen * b->itemsize;
+    if (!b->d_in.reserve(ib) || !b->d_out.reserve(ob)) return cuda_fail(cudaGetLastError(), "overlap_save buffers");
+    cudaError_t e = cudaMemcpyAsync(b->d_in.p, in, ib, cudaMemcpyHostToDevice, b->s);
+    if (e == cudaSuccess) e = launch_rowcopy(b->d_in.p, b->d_hist.p, (long)hb, b->d_out.p, n, (long)b->outputlen * b->itemsize, inplen * b->itemsize, -(long)hb, b->s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, b->d_out.p, ob, cudaMemcpyDeviceToHost, b->s);
+    /* save the last overlaplen input items (lib/overlap_save_impl.cc:78); defined for overlaplen <= inplen */
+    if (e == cudaSuccess && hb) {
+        if (ib >= hb) e = cudaMemcpyAsync(b->d_hist.p, (const char*)b->d_in.p + (ib - hb), hb, cudaMemcpyDeviceToDevice, b->s);
+        else {
+            /* more than 50 % overlap and a short call: slide the history (the reference reads out of bounds here) */
+            DevBuf tmp; if (!tmp.reserve(hb)) return cuda_fail(cudaGetLastError(), "overlap_save history");
+            e = cudaMemcpyAsync(tmp.p, (const char*)b->d_hist.p + ib, hb - ib, cudaMemcpyDeviceToDevice, b->s);
+            if (e == cudaSuccess) e = cudaMemcpyAsync((char*)tmp.p + (hb - ib), b->d_in.p, ib, cudaMemcpyDeviceToDevice, b->s);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(b->d_hist.p, tmp.p, hb, cudaMemcpyDeviceToDevice, b->s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(b->s);
+        }
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(b->s);
+    return e == cudaSuccess ? n : cuda_fail(e, "overlap_save work");
+}
+void fdc_overlap_save_destroy(fdc_overlap_save* b) { if (!b) return; if (b->s) { cudaStreamSynchronize(b->s); cudaStreamDestroy(b->s); } delete b; }
+
+fdc_vector_cut* fdc_vector_cut_create(int itemsize, int veclen, int offset, int blocklen)
+{
+    if (!require_device()) return 0;
+    /* the reference performs no checks in C++ (only GRC does, grc/FDC_vector_cut_vxx.xml:64-68); reading outside the
+     * input vector is undefined there and refused here */
+    if (itemsize <= 0 || veclen <= 0 || blocklen <= 0 || offset < 0 || offset + blocklen > veclen) { fail("vector_cut_vxx: need 0 <= offset and offset + blocklen <= veclen"); return 0; }
+    fdc_vector_cut* b = new fdc_vector_cut;
+    b->itemsize = itemsize; b->veclen = veclen; b->offset = offset; b->blocklen = blocklen; b->s = 0;
+    if (cudaStreamCreateWithFlags(&b->s, cudaStreamNonBlocking) != cudaSuccess) { cuda_fail(cudaGetLastError(), "vector_cut create"); delete b; return 0; }
+    return b;
+}
+int fdc_vector_cut_work(fdc_vector_cut* b, int n, const void* in, void* out)
+{
+    if (!b || n < 0) return fail("vector_cut work: bad arguments");
+    if (n == 0) return 0;
+    const size_t ib = (size_t)n * b->veclen * b->itemsize, ob = (size_t)n * b->blocklen * b->itemsize;
+    if (!b->d_in.reserve(ib) || !b->d_out.reserve(ob)) return cuda_fail(cudaGetLastError(), "vector_cut buffers");
+    cudaError_t e = cudaMemcpyAsync(b->d_in.p, in, ib, cudaMemcpyHostToDevice, b->s);
+    if (e == cudaSuccess) e = launch_rowcopy(b->d_in.p, b->d_in.p, 0, b->d_out.p, n, (long)b->blocklen * b->itemsize, (long)b->veclen * b->itemsize, (long)b->offset * b->itemsize, b->s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, b->d_out.p, ob, cudaMemcpyDeviceToHost, b->s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(b->s);
+    return e == cudaSuccess ? n : cuda_fail(e, "vector_cut work");
+}
+void fdc_vector_cut_destroy(fdc_vector_cut* b) { if (!b) return; if (b->s) { cudaStreamSynchronize(b->s); cudaStreamDestroy(b->s); } delete b; }
+
+fdc_psw* fdc_psw_create(int blocklen, int numphasestates, int shifts, float passbw, float stopbw, int windowtype)
+{
+    if (!require_device()) return 0;
+    fdc_psw* b = 0;
+    try {
+        psw_check_args(passbw, stopbw);
+        if (blocklen <= 0 || numphasestates <= 0) throw std::invalid_argument("blocklen and numphasestates must be > 0");
+        b = new fdc_psw; b->s = 0;
+        b->blocksize = blocklen; b->relinvovl = numphasestates; b->counter = 0;
+        b->shift = ((shifts % numphasestates) + numphasestates) % numphasestates;       /* prevent negative shift, :58 */
+        psw_tables(blocklen, numphasestates, passbw, stopbw, windowtype, b->tables);
+        if (cudaStreamCreateWithFlags(&b->s, cudaStreamNonBlocking) != cudaSuccess || !b->d_tab.upload(b->tables.data(), sizeof(float2) * b->tables.size()))
+            throw std::runtime_error(std::string("psw create: ") + cudaGetErrorString(cudaGetLastError()));
+        return b;
+    } catch (const std::exception& e) { fail(e.what()); fdc_psw_destroy(b); return 0; }
+}
+int fdc_psw_work(fdc_psw* b, int n, const void* in, void* out)
+{
+    if (!b || n < 0) return fail("psw work: bad arguments");
+    if (n == 0) return 0;
+    const size_t bytes = sizeof(float2) * (size_t)n * b->blocksize;
+    if (!b->d_in.reserve(bytes) || !b->d_out.reserve(bytes)) return cuda_fail(cudaGetLastError(), "psw buffers");
+    cudaError_t e = cudaMemcpyAsync(b->d_in.p, in, bytes, cudaMemcpyHostToDevice, b->s);
+    if (e == cudaSuccess) e = launch_psw((const float2*)b->d_in.p, (float2*)b->d_out.p, (const float2*)b->d_tab.p, n, b->blocksize, b->relinvovl, b->counter, b->shift, b->s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, b->d_out.p, bytes, cudaMemcpyDeviceToHost, b->s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(b->s);
+    if (e != cudaSuccess) return cuda_fail(e, "psw work");
+    b->counter = (int)((b->counter + (long)(n % b->relinvovl) * b->shift) % b->relinvovl);
+    return n;
+}
+int fdc_psw_state(const fdc_psw* b, int* blocksize, int* relinvovl, int* counter, int* shift)
+{
+    if (!b) return fail("null block");
+    *blocksize = b->blocksize; *relinvovl = b->relinvovl; *counter = b->counter; *shift = b->shift; return 0;
+}
+int fdc_psw_tables(const fdc_psw* b, float* out)
+{
+    if (!b) return fail("null block");
+    memcpy(out, b->tables.data(), sizeof(std::complex<float>) * b->tables.size()); return 0;
+}
+void fdc_psw_destroy(fdc_psw* b) { if (!b) return; if (b->s) { cudaStreamSynchronize(b->s); cudaStreamDestroy(b->s); } delete b; }
+
+fdc_fft* fdc_fft_create(int n, int forward, int shift)
+{
+    if (!require_device()) return 0;
+    if (!tile_len_supported(n)) { fail("fft: size must be a power of two in [2, 16384]"); return 0; }
+    fdc_fft* b = new fdc_fft; b->n = n; b->forward = forward != 0; b->shift = shift != 0; b->s = 0;
+    if (cudaStreamCreateWithFlags(&b->s, cudaStreamNonBlocking) != cudaSuccess) { cuda_fail(cudaGetLastError(), "fft create"); delete b; return 0; }
+    twiddle_table(n);
+    return b;
+}
+int fdc_fft_work(fdc_fft* b, long nvec, const void* in, void* out)
+{
+    if (!b || nvec < 0) return fail("fft work: bad arguments");
+    if (nvec == 0) return 0;
+    const size_t bytes = sizeof(float2) * (size_t)nvec * b->n;
+    if (!b->d_in.reserve(bytes) || !b->d_out.reserve(bytes)) return cuda_fail(cudaGetLastError(), "fft buffers");
+    cudaError_t e = cudaMemcpyAsync(b->d_in.p, in, bytes, cudaMemcpyHostToDevice, b->s);
+    PlainParams p; p.in = (const float2*)b->d_in.p; p.out = (float2*)b->d_out.p; p.nvec = nvec; p.shift = b->shift;
+    if (e == cudaSuccess) e = launch_plain_fft(p, b->n, b->forward, b->s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, b->d_out.p, bytes, cudaMemcpyDeviceToHost, b->s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(b->s);
+    return e == cudaSuccess ? 0 : cuda_fail(e, "fft work");
+}
+void fdc_fft_destroy(fdc_fft* b) { if (!b) return; if (b->s) { cudaStreamSynchronize(b->s); cudaStreamDestroy(b->s); } delete b; }
+
+}  // extern "C"

@@ -1,0 +1,224 @@
+/* fdc_k_misc.cu -- twiddle tables, the copy-type blocks (overlap_save, vector_cut_vxx), the stand-alone
+ * phase_shifting_windowing_vcc multiply, and K3: power / threshold / edge kernels of the activity-gated blocks. */
+#include "fdc_kcommon.cuh"
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <vector>
+#include <cmath>
+#include <cfloat>
+
+namespace fdc {
+
+static std::atomic<unsigned long long> g_launches(0);
+void count_launch(int n) { g_launches += (unsigned long long)n; }
+unsigned long long launch_count() { return g_launches.load(); }
+
+/* ---- twiddle tables (per device, per length) ------------------------------------------------ */
+static std::mutex g_tw_mutex;
+static std::map<std::pair<int, long>, float2*> g_tw;      /* (device, key) -> device pointer */
+
+static float2* upload_roots(long n, long N, long stride)   /* exp(-2 pi i m*stride / N), m < n */
+{
+    std::vector<float2> h((size_t)n);
+    for (long m = 0; m < n; m++) {
+        const long double a = -2.0L * 3.141592653589793238462643383279502884L * (long double)((m * stride) % N) / (long double)N;
+        h[(size_t)m] = make_float2((float)cosl(a), (float)sinl(a));
+    }
+    float2* d = 0;
+    if (cudaMalloc(&d, sizeof(float2) * (size_t)n) != cudaSuccess) return 0;
+    if (cudaMemcpy(d, h.data(), sizeof(float2) * (size_t)n, cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return 0; }
+    return d;
+}
+const float2* twiddle_table(int L)
+{
+    int dev = 0; cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> g(g_tw_mutex);
+    float2*& p = g_tw[std::make_pair(dev, (long)L)];
+    if (!p) p = upload_roots(L < 1 ? 1 : L, L < 1 ? 1 : L, 1);
+    return p;
+}
+void big_twiddle_tables(int N, const float2** lo, const float2** hi, int* tws_log2)
+{
+    int dev = 0; cudaGetDevice(&dev);
+    int lg = 0; while ((1 << lg) < N) lg++;
+    const int s = lg / 2;                       /* lo: 2^s entries, hi: N / 2^s entries */
+    std::lock_guard<std::mutex> g(g_tw_mutex);
+    float2*& a = g_tw[std::make_pair(dev, -(long)N)];
+    float2*& b = g_tw[std::make_pair(dev, -(long)N - (1L << 40))];
+    if (!a) a = upload_roots(1L << s, N, 1);
+    if (!b) b = upload_roots((long)N >> s, N, 1L << s);
+    *lo = a; *hi = b; *tws_log2 = s;
+}
+
+/* ---- row copy: overlap_save (lib/overlap_save_impl.cc:70-78) and vector_cut_vxx (lib/vector_cut_vxx_impl.cc:67-68)
+ * both are "row b of the output = a window of the input byte stream"; bytes before the start of the input come
+ * from the history saved by the previous call. */
+template <class U>
+__global__ void __launch_bounds__(256) k_rowcopy(const U* __restrict__ src, const U* __restrict__ hist, long hist_units,
+                                                 U* __restrict__ dst, long nrows, long row_units, long src_stride,
+                                                 long src_off)
+{
+    const long total = nrows * row_units;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long b = i / row_units, k = i - b * row_units;
+        const long g = b * src_stride + src_off + k;
+        dst[i] = g < 0 ? hist[hist_units + g] : src[g];
+    }
+}
+cudaError_t launch_rowcopy(const void* src, const void* hist, long hist_bytes, void* dst, long nrows, long row_bytes,
+                           long src_stride, long src_off, cudaStream_t s)
+{
+    if (nrows <= 0 || row_bytes <= 0) return cudaSuccess;
+    const uintptr_t al = (uintptr_t)src | (uintptr_t)hist | (uintptr_t)dst | (uintptr_t)hist_bytes | (uintptr_t)row_bytes |
+                         (uintptr_t)src_stride | (uintptr_t)(src_off < 0 ? -src_off : src_off);
+    const long total = nrows * row_bytes;
+    int unit = 1;
+    if ((al & 15) == 0) unit = 16; else if ((al & 7) == 0) unit = 8; else if ((al & 3) == 0) unit = 4; else if ((al & 1) == 0) unit = 2;
+    long blocks = (total / unit + 255) / 256; if (blocks > 148L * 16) blocks = 148L * 16; if (blocks < 1) blocks = 1;
+#define GO(TT) k_rowcopy<TT><<<(unsigned)blocks, 256, 0, s>>>((const TT*)src, (const TT*)hist, hist_bytes / unit, (TT*)dst, nrows, \
+                                                              row_bytes / unit, src_stride / unit, src_off / unit)
+    switch (unit) {
+    case 16: GO(uint4); break;
+    case 8: GO(uint2); break;
+    case 4: GO(unsigned); break;
+    case 2: GO(unsigned short); break;
+    default: GO(unsigned char); break;
+    }
+#undef GO
+    count_launch();
+    return cudaGetLastError();
+}
+
+/* ---- phase_shifting_windowing_vcc::work (lib/phase_shifting_windowing_vcc_impl.cc:72-86) ------- */
+__global__ void __launch_bounds__(256) k_psw(const float2* __restrict__ in, float2* __restrict__ out,
+                                             const float2* __restrict__ table, long nblocks, int l, int nphase, int counter,
+                                             int shift)
+{
+    const long total = nblocks * l;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long b = i / l; const int k = (int)(i - b * l);
+        const int ph = (int)((counter + (b % nphase) * shift) % nphase);
+        out[i] = cmul_exact(in[i], __ldg(table + (long)ph * l + k));
+    }
+}
+cudaError_t launch_psw(const float2* in, float2* out, const float2* table, long nblocks, int l, int nphase, int counter,
+                       int shift, cudaStream_t s)
+{
+    if (nblocks <= 0) return cudaSuccess;
+    long blocks = (nblocks * l + 255) / 256; if (blocks > 148L * 16) blocks = 148L * 16;
+    k_psw<<<(unsigned)blocks, 256, 0, s>>>(in, out, table, nblocks, l, nphase, counter, shift);
+    count_launch();
+    return cudaGetLastError();
+}
+
+/* ---- K3 ------------------------------------------------------------------------------------------ */
+/* one thread per (block, power bin): D sequential |x|^2 additions, the order of the generic VOLK accumulator.
+ * A warp covers 32 adjacent power bins = 32*D contiguous spectrum bins; the tile is staged through shared
+ * memory with coalesced loads so that HBM/L2 sees full lines. */
+__global__ void __launch_bounds__(256) k_group_power(const float2* __restrict__ spec, long spec_stride, int start, int D,
+                                                     int M, int mean, float* __restrict__ P)
+{
+    const long b = blockIdx.y;
+    const float2* row = spec + b * spec_stride + start;
+    const float norm = 1.0f / (float)D;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
+        const float2* x = row + (long)i * D;
+        float acc = 0.0f;
+        for (int k = 0; k < D; k++) {
+            const float2 v = __ldg(x + k);
+            acc = fdc_add(acc, fdc_add(fdc_mul(v.x, v.x), fdc_mul(v.y, v.y)));
+        }
+        P[b * M + i] = mean ? fdc_mul(acc, norm) : acc;
+    }
+}
+cudaError_t launch_group_power(const float2* spec, long spec_stride, long nblocks, int start, int D, int M, int mean,
+                               float* P, cudaStream_t s)
+{
+    if (nblocks <= 0 || M <= 0) return cudaSuccess;
+    for (long b0 = 0; b0 < nblocks; b0 += 65535) {
+        const long nb = nblocks - b0 < 65535 ? nblocks - b0 : 65535;
+        int gx = (M + 255) / 256; if (gx > 1024) gx = 1024;
+        k_group_power<<<dim3((unsigned)gx, (unsigned)nb), 256, 0, s>>>(spec + b0 * spec_stride, spec_stride, start, D, M, mean,
+                                                                      P + b0 * M);
+        count_launch();
+    }
+    return cudaGetLastError();
+}
+
+/* one CTA per block: ratios of adjacent power bins, threshold classification, ordered compaction of the two edge
+ * lists with warp ballots + a CTA-level running offset (ascending bin order is what the reference's deque holds
+ * before std::sort, lib/SegmentDetection_impl.cc:206-217). */
+__global__ void __launch_bounds__(256) k_edges(const float* __restrict__ P, int M, float T, float invT, int guard, int cap,
+                                               int* __restrict__ counts, float* __restrict__ rise_ratio,
+                                               int* __restrict__ rise_idx, int* __restrict__ fall_idx)
+{
+    __shared__ int s_warp[2][8];
+    __shared__ int s_base[2];
+    const long b = blockIdx.x;
+    const float* p = P + b * M;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 2) s_base[threadIdx.x] = 0;
+    __syncthreads();
+    const int n = M - 1;
+    for (int i0 = 0; i0 < n; i0 += 256) {
+        const int i = i0 + threadIdx.x;
+        bool rise = false, fall = false; float r = 0.0f;
+        if (i < n) {
+            float den = p[i];
+            if (guard && den == 0.0f) den = FLT_MIN;
+            r = fdc_div(p[i + 1], den);
+            rise = r > T;
+            fall = !rise && r < invT;
+        }
+        const unsigned mr = __ballot_sync(0xffffffffu, rise), mf = __ballot_sync(0xffffffffu, fall);
+        if (lane == 0) { s_warp[0][warp] = __popc(mr); s_warp[1][warp] = __popc(mf); }
+        __syncthreads();
+        int offr = s_base[0], offf = s_base[1];
+        for (int w = 0; w < warp; w++) { offr += s_warp[0][w]; offf += s_warp[1][w]; }
+        const unsigned lower = (1u << lane) - 1u;
+        if (rise) { const int o = offr + __popc(mr & lower); if (o < cap) { rise_ratio[b * cap + o] = r; rise_idx[b * cap + o] = i; } }
+        if (fall) { const int o = offf + __popc(mf & lower); if (o < cap) fall_idx[b * cap + o] = i; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tr = 0, tf = 0;
+            for (int w = 0; w < 8; w++) { tr += s_warp[0][w]; tf += s_warp[1][w]; }
+            s_base[0] += tr; s_base[1] += tf;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { counts[b * 2] = s_base[0]; counts[b * 2 + 1] = s_base[1]; }
+}
+cudaError_t launch_edges(const float* P, long nblocks, int M, float T, float invT, int guard, int cap, int* counts,
+                         float* rise_ratio, int* rise_idx, int* fall_idx, cudaStream_t s)
+{
+    if (nblocks <= 0) return cudaSuccess;
+    k_edges<<<(unsigned)nblocks, 256, 0, s>>>(P, M, T, invT, guard, cap, counts, rise_ratio, rise_idx, fall_idx);
+    count_launch();
+    return cudaGetLastError();
+}
+
+/* one thread per block: strictly sequential sum over the measurement band (lib/PowerActivationChannel_impl.cc:289-291).
+ * std::real(x * conj(x)) is a*a - b*(-b): two rounded products and one rounded sum. */
+__global__ void __launch_bounds__(128) k_band_power(const float2* __restrict__ spec, long spec_stride, long nblocks, int m0,
+                                                    int m1, float* __restrict__ pwr)
+{
+    const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblocks) return;
+    const float2* x = spec + b * spec_stride;
+    float acc = 0.0f;
+    for (int i = m0; i < m1; i++) {
+        const float2 v = __ldg(x + i);
+        acc = fdc_add(acc, fdc_sub(fdc_mul(v.x, v.x), fdc_mul(v.y, -v.y)));
+    }
+    pwr[b] = acc;
+}
+cudaError_t launch_band_power(const float2* spec, long spec_stride, long nblocks, int m0, int m1, float* pwr, cudaStream_t s)
+{
+    if (nblocks <= 0) return cudaSuccess;
+    k_band_power<<<(unsigned)((nblocks + 127) / 128), 128, 0, s>>>(spec, spec_stride, nblocks, m0, m1, pwr);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace fdc

@@ -1,0 +1,54 @@
+/* fdc_launch.h -- host-callable launchers of the sm_100a kernels (internal to libfdc_b200.so). */
+#ifndef FDC_LAUNCH_H
+#define FDC_LAUNCH_H
+#include <cuda_runtime.h>
+#include "fdc_functors.cuh"
+
+namespace fdc {
+
+/* every launcher counts its launches here (fdc_launch_count) */
+void count_launch(int n = 1);
+unsigned long long launch_count();
+
+/* forward root table exp(-2 pi i m / L), m in [0, L), on the current device (cached per device and L) */
+const float2* twiddle_table(int L);
+/* split table for W_N^m, N = N1*N2: lo has 2^tws_log2 entries, hi the rest */
+void big_twiddle_tables(int N, const float2** lo, const float2** hi, int* tws_log2);
+
+bool fwd_small_supported(int N);      /* N handled by one CTA (16 .. 16384) */
+bool fwd_big_supported(int N, int* N1, int* N2);
+bool tile_len_supported(int L);       /* inverse / plain tile lengths (2 .. 16384) */
+
+cudaError_t launch_fwd_small(const FwdParams& p, cudaStream_t s);
+cudaError_t launch_fwd_big(const BigParams& p, int N, cudaStream_t s);
+/* nsel channels sharing slice length l */
+cudaError_t launch_extract(const ExtractParams& p, int l, int nsel, cudaStream_t s);
+cudaError_t launch_jobs(const JobParams& p, int l, cudaStream_t s);
+cudaError_t launch_plain_fft(const PlainParams& p, int L, int forward, cudaStream_t s);
+
+/* out row b (row_bytes) <- src[b*src_stride + src_off ...); source bytes before 0 come from hist
+ * (hist holds hist_bytes bytes that logically precede src[0]).  overlap_save and vector_cut_vxx. */
+cudaError_t launch_rowcopy(const void* src, const void* hist, long hist_bytes, void* dst, long nrows,
+                           long row_bytes, long src_stride, long src_off, cudaStream_t s);
+/* out[b][k] = in[b][k] * table[(counter + b*shift) % nphase][k]  (VOLK-exact complex multiply) */
+cudaError_t launch_psw(const float2* in, float2* out, const float2* table, long nblocks, int l, int nphase,
+                       int counter, int shift, cudaStream_t s);
+
+/* ---- K3: power / threshold / edges ---------------------------------------------------------- */
+/* P[b*M + i] = sum_{k<D} |X_b[start + i*D + k]|^2, strictly sequential fp32 (generic VOLK order,
+ * lib/SegmentDetection_impl.cc:185-190); mean != 0 multiplies by 1/D afterwards
+ * (lib/activity_detection_channelizer_vcm_impl.cc:633-648). */
+cudaError_t launch_group_power(const float2* spec, long spec_stride, long nblocks, int start, int D, int M,
+                               int mean, float* P, cudaStream_t s);
+/* per block: rising edges (ratio > T) as (ratio, index i) and falling edges (ratio < 1/T) as index i, in
+ * ascending i, compacted with warp ballots.  guard != 0: a zero denominator is replaced by FLT_MIN
+ * (activity_detection_channelizer_vcm_impl.cc:703-704).  Layout per block: counts[b*2+{0,1}],
+ * rise_ratio[b*cap + n], rise_idx[b*cap + n], fall_idx[b*cap + n]. */
+cudaError_t launch_edges(const float* P, long nblocks, int M, float T, float invT, int guard, int cap,
+                         int* counts, float* rise_ratio, int* rise_idx, int* fall_idx, cudaStream_t s);
+/* pwr[b] = sum_{i in [m0, m1)} re(x * conj x), sequential (lib/PowerActivationChannel_impl.cc:289-291) */
+cudaError_t launch_band_power(const float2* spec, long spec_stride, long nblocks, int m0, int m1, float* pwr,
+                              cudaStream_t s);
+
+}  // namespace fdc
+#endif

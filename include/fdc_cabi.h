@@ -1,0 +1,195 @@
+/* fdc_cabi.h -- C ABI of the B200-native gr-FDC hot path (libfdc_b200.so).
+ *
+ * gr-FDC itself has no FFI: its blocks are C++ gr::sync_block subclasses created through
+ * `static sptr make(...)` (include/FDC/<block>.h:49 in the reference) whose work() bodies live in
+ * lib/<block>_impl.cc.  This header is the boundary a maintainer binds instead of those bodies:
+ * every entry point below names the reference interface it replaces.  Plain pointers and sizes
+ * only, no C++/torch types, no exceptions across the boundary: constructors return NULL and every
+ * other call a negative status on failure, with the text in fdc_last_error() (the block wrappers
+ * re-throw it as std::invalid_argument, which is what the reference constructors throw).
+ *
+ * All sample buffers are gr_complex = interleaved float32 (re, im), 8 bytes per item.
+ * "host" entry points take ordinary (preferably pinned, see fdc_host_alloc) host memory and
+ * include the host<->device copies; "device" entry points take CUDA device pointers and a
+ * cudaStream_t passed as void* (NULL = the context's own stream) and only enqueue work.
+ * A context is used by one caller thread at a time (GNU Radio never re-enters work() of one
+ * block); different contexts may be used concurrently.  There is NO CPU fallback: without a
+ * usable CUDA device every constructor fails. */
+#ifndef FDC_CABI_H
+#define FDC_CABI_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define FDC_API_VERSION 1
+
+/* window types, lib/windows.h:29-33 */
+enum { FDC_WIN_RECTANGULAR = 0, FDC_WIN_HANN = 1, FDC_WIN_RAMP = 2 };
+
+/* ---- library / device -------------------------------------------------------------------- */
+int fdc_api_version(void);
+const char* fdc_last_error(void);                 /* thread local, never NULL */
+int fdc_device_count(void);                        /* number of CUDA devices, <= 0 if none */
+int fdc_set_device(int device);                    /* device used by contexts created afterwards on this thread */
+void* fdc_host_alloc(size_t bytes);                /* pinned host memory for the *_host entry points */
+void fdc_host_free(void* p);
+/* number of kernel launches this library has enqueued so far (all contexts, this process) */
+unsigned long long fdc_launch_count(void);
+
+/* ---- geometry and window tables (host side, bit exact restatements) ----------------------- */
+/* FrequencyDomainChannelizer.get_opt_channelparams, python/FrequencyDomainChannelizer.py:322-345
+ * (freq and bw already converted with get_freq/get_bw, i.e. DC at 0.5). */
+int fdc_opt_channelparams(int blocksize, int relinvovl, double freq, double bw,
+                          int* f, int* l, int* lout, double* passband, double* stopband);
+/* cr_win(wintype, blocksize, passbw, stopbw, w, relinvovl, 1, false), lib/windows.h:41-78, as called by
+ * phase_shifting_windowing_vcc_impl (lib/phase_shifting_windowing_vcc_impl.cc:62).
+ * out: relinvovl * blocksize complex floats. */
+int fdc_psw_build_tables(int blocklen, int numphasestates, float passbw, float stopbw, int windowtype, float* out);
+
+/* ---- the fused throughput channelizer ------------------------------------------------------
+ * Replaces the chain the hier block wires (python/FrequencyDomainChannelizer.py:201-231, 284-315):
+ *   stream_to_vector -> FDC.overlap_save -> fft_vcc(N, fwd, shift) -> multiply_const(1/N)
+ *   -> per channel: vector_cut_vxx(f,l) -> phase_shifting_windowing_vcc -> fft_vcc(l, inverse, shift)
+ *                   -> vector_cut_vxx(l-lout, lout) -> vector_to_stream -> multiply_const(l)
+ * One forward-FFT kernel (overlap staging, fft-shift and 1/N fused) and one batched channel-extract
+ * kernel per distinct l. */
+typedef struct fdc_chan fdc_chan;
+typedef struct {
+    int f;               /* first bin of the slice in the fft-shifted spectrum (vector_cut offset) */
+    int l;               /* slice / inverse FFT length, power of two */
+    int lout;            /* samples kept per block: the last lout of the l IFFT outputs */
+    int shift;           /* phase table advance per block (phase_shifting_windowing_vcc `shifts`) */
+    float gain;          /* output scale (multiply_const_cc, the hier block uses l) */
+    const float* table;  /* nphase * l complex floats: table[p][k] multiplies bin f+k on blocks with phase p */
+} fdc_chan_desc;
+
+/* N: forward FFT length (power of two), ovl: samples re-used from the previous block (0 <= ovl < N;
+ * the reference's overlap_save is only defined for ovl <= N/2, lib/overlap_save_impl.cc:74-78),
+ * nphase: number of phase states of every table. */
+fdc_chan* fdc_chan_create(int N, int ovl, int nphase, int nchan, const fdc_chan_desc* ch);
+void fdc_chan_destroy(fdc_chan* c);
+int fdc_chan_hop(const fdc_chan* c);              /* N - ovl new samples per block */
+long fdc_chan_blockcount(const fdc_chan* c);      /* blocks consumed so far (phase counter origin) */
+int fdc_chan_reset(fdc_chan* c);                  /* zero history, block counter 0 */
+/* Position a fresh/reset context in the middle of a stream (time sharding): the next block is
+ * global block `first_block`; history is NOT touched (feed the halo with fdc_chan_set_history). */
+int fdc_chan_seek(fdc_chan* c, long first_block);
+int fdc_chan_set_history(fdc_chan* c, const void* host_last_ovl_samples);
+/* in: nblocks*hop new samples.  outs[i]: nblocks*lout_i samples for channel i (NULL entries are skipped).
+ * spectrum: optional nblocks*N normalised fft-shifted spectrum (the hier block's debug port). */
+int fdc_chan_work_host(fdc_chan* c, const void* in, long nblocks, void* const* outs, void* spectrum);
+/* Device-resident variant.  d_out: one buffer, channel i starts at item offset
+ * sum_{j<i} nblocks*lout_j ("channel-major slabs").  d_spectrum may be NULL (an internal L2-sized
+ * ring is used then).  Only enqueues on `stream`; history/counters are advanced. */
+int fdc_chan_work_device(fdc_chan* c, const void* d_in, long nblocks, void* d_out, void* d_spectrum, void* stream);
+int fdc_chan_sync(fdc_chan* c);
+
+/* ---- individual block replacements (host buffers in, host buffers out) ---------------------- */
+/* FDC.overlap_save, include/FDC/overlap_save.h:49, lib/overlap_save_impl.cc:62-81 */
+typedef struct fdc_overlap_save fdc_overlap_save;
+fdc_overlap_save* fdc_overlap_save_create(int itemsize, int outputlen, int overlaplen);
+int fdc_overlap_save_work(fdc_overlap_save* b, int noutput_items, const void* in, void* out);
+void fdc_overlap_save_destroy(fdc_overlap_save* b);
+
+/* FDC.vector_cut_vxx, include/FDC/vector_cut_vxx.h:49, lib/vector_cut_vxx_impl.cc:59-72 */
+typedef struct fdc_vector_cut fdc_vector_cut;
+fdc_vector_cut* fdc_vector_cut_create(int itemsize, int veclen, int offset, int blocklen);
+int fdc_vector_cut_work(fdc_vector_cut* b, int noutput_items, const void* in, void* out);
+void fdc_vector_cut_destroy(fdc_vector_cut* b);
+
+/* FDC.phase_shifting_windowing_vcc, include/FDC/phase_shifting_windowing_vcc.h:49,
+ * lib/phase_shifting_windowing_vcc_impl.cc:41-86 */
+typedef struct fdc_psw fdc_psw;
+fdc_psw* fdc_psw_create(int blocklen, int numphasestates, int shifts, float passbw, float stopbw, int windowtype);
+int fdc_psw_work(fdc_psw* b, int noutput_items, const void* in, void* out);
+int fdc_psw_state(const fdc_psw* b, int* blocksize, int* relinvovl, int* counter, int* shift);
+int fdc_psw_tables(const fdc_psw* b, float* out);   /* relinvovl*blocklen complex floats */
+void fdc_psw_destroy(fdc_psw* b);
+
+/* gr::fft::fft_vcc(n, forward, rectangular window, shift) as the hier block uses it
+ * (python/FrequencyDomainChannelizer.py:206, 228); third-party stage, provided so that a flowgraph
+ * can stay on the GPU library end to end. */
+typedef struct fdc_fft fdc_fft;
+fdc_fft* fdc_fft_create(int n, int forward, int shift);
+int fdc_fft_work(fdc_fft* b, long nvec, const void* in, void* out);
+void fdc_fft_destroy(fdc_fft* b);
+
+/* ---- activity-gated channels: PDUs ---------------------------------------------------------- */
+/* One published message: the pmt dict of lib/SegmentDetection_impl.cc:446-460,502-515 /
+ * lib/PowerActivationChannel_impl.cc:222-232 plus the c32vector payload. */
+typedef struct {
+    char id[160];          /* "<time>.PowActChan.<ID>.<n>.fin|.part" or "<time>.DETECTED.<seg>.<chan>" */
+    int finalized;
+    long part;             /* -1: key absent */
+    double rel_cfreq, rel_bw;
+    long blockstart, blockend;
+    long vectorstart, vectorend;   /* -1: key absent (PowerActivationChannel) */
+    long nsamples;
+    const float* data;     /* nsamples complex floats, owned by the block until the next msg_clear/destroy */
+} fdc_msg;
+
+/* FDC.PowerActivationChannel, include/FDC/PowerActivationChannel.h:49, lib/PowerActivationChannel_impl.cc */
+typedef struct fdc_pac fdc_pac;
+fdc_pac* fdc_pac_create(int blocklen, float cfreq, float bw, int relinvovl, float thresh, int maxblocks,
+                        int deactivation_delay, int msg, int fileoutput, const char* path, int verbose, int ID);
+int fdc_pac_work_host(fdc_pac* b, int noutput_items, const void* in);
+int fdc_pac_work_device(fdc_pac* b, int noutput_items, const void* d_in, void* stream);
+/* geo[12]: extract_start, extract_stop, extract_width, measure_start, measure_stop, deltaphase, output_len,
+ * output_ovl_offset, active, count, phase, blockcount; f[2]: thresh (linear), lastpower */
+int fdc_pac_state(const fdc_pac* b, int* geo, float* f);
+int fdc_pac_tables(const fdc_pac* b, float* out);    /* relinvovl * blocklen complex floats */
+int fdc_pac_msg_count(const fdc_pac* b);
+int fdc_pac_msg_get(const fdc_pac* b, int i, fdc_msg* out);
+void fdc_pac_msg_clear(fdc_pac* b);
+void fdc_pac_destroy(fdc_pac* b);
+
+/* FDC.SegmentDetection, include/FDC/SegmentDetection.h:49, lib/SegmentDetection_impl.cc */
+typedef struct fdc_segdet fdc_segdet;
+fdc_segdet* fdc_segdet_create(int ID, int blocklen, int relinvovl, float seg_start, float seg_stop, float thresh,
+                              float minchandist, float window_flank_puffer, int maxblocks_to_emit,
+                              int channel_deactivation_delay, int messageoutput, int fileoutput, const char* path,
+                              int threads, int verbose);
+int fdc_segdet_work_host(fdc_segdet* b, int noutput_items, const void* in);
+int fdc_segdet_work_device(fdc_segdet* b, int noutput_items, const void* d_in, void* stream);
+/* geo[8]: d_start, d_stop, d_width, D, M, blockcount, n_active, active_channels_counter; f[1]: thresh */
+int fdc_segdet_state(const fdc_segdet* b, long* geo, float* f);
+int fdc_segdet_window(const fdc_segdet* b, int log2w, int phase, float* out);
+int fdc_segdet_power(const fdc_segdet* b, float* out);          /* decimated power of the last block, M floats */
+/* active channel i, out[14]: ID, detect_start, detect_stop, extract_start, extract_stop, extract_width, ovlskip,
+ * outputsamples, count, phase, phaseincrement, inactive, part, buffered blocks */
+int fdc_segdet_active(const fdc_segdet* b, int i, int* out);
+int fdc_segdet_msg_count(const fdc_segdet* b);
+int fdc_segdet_msg_get(const fdc_segdet* b, int i, fdc_msg* out);
+void fdc_segdet_msg_clear(fdc_segdet* b);
+void fdc_segdet_destroy(fdc_segdet* b);
+
+/* FDC.activity_detection_channelizer_vcm, include/FDC/activity_detection_channelizer_vcm.h:49,
+ * lib/activity_detection_channelizer_vcm_impl.cc.  segments: nsegs pairs (start, stop). */
+typedef struct fdc_actdet fdc_actdet;
+fdc_actdet* fdc_actdet_create(int blocklen, const float* segments, int nsegs, float thresh, int relinvovl,
+                              int maxblocks, int message, int fileoutput, const char* path, int threads,
+                              float minchandist, int channel_deactivation_delay, double window_flank_puffer,
+                              int verbose);
+int fdc_actdet_work_host(fdc_actdet* b, int noutput_items, const void* in);
+int fdc_actdet_work_device(fdc_actdet* b, int noutput_items, const void* d_in, void* stream);
+int fdc_actdet_nsegments(const fdc_actdet* b);
+/* out[7]: ID, start, stop, width, D, M, n_active */
+int fdc_actdet_segment(const fdc_actdet* b, int i, int* out);
+int fdc_actdet_power(const fdc_actdet* b, int seg, float* out);
+int fdc_actdet_msg_count(const fdc_actdet* b);
+int fdc_actdet_msg_get(const fdc_actdet* b, int i, fdc_msg* out);
+void fdc_actdet_msg_clear(fdc_actdet* b);
+void fdc_actdet_destroy(fdc_actdet* b);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif

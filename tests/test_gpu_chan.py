@@ -1,0 +1,119 @@
+"""GPU parity: the CUDA throughput channelizer and block replacements against the oracle (the unmodified
+reference blocks + restated third-party stages), through the C ABI.  Tolerance: channel samples and spectra
+rel-L2 <= 1e-5 (BASELINE.json north_star); byte-copy blocks and tables bit exact."""
+import numpy as np
+import pytest
+
+import workloads
+from helpers import rel_l2, make_ref_chain, make_gpu_chain
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def FDC():
+    import FDC as m
+    return m
+
+
+@pytest.mark.parametrize("n", [2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384])
+@pytest.mark.parametrize("forward,shift", [(True, True), (False, True), (True, False), (False, False)])
+def test_fft_vcc_stage(FDC, ref, n, forward, shift):
+    rng = np.random.default_rng(n + 7 * forward + 3 * shift)
+    nvec = max(3, 9000 // n)
+    x = (rng.standard_normal(nvec * n) + 1j * rng.standard_normal(nvec * n)).astype(np.complex64)
+    want = ref.fft_vcc(x, n, forward, shift)
+    got = FDC.fft_vcc(n, forward, None, shift, 1).process(x)
+    assert rel_l2(got, want) < 2e-6
+
+
+def test_overlap_save_bit_exact(FDC, ref):
+    # Appendix B.4 plus cfp32 geometry, chunked calls
+    x = np.arange(1, 61, dtype=np.float32)
+    a = ref.overlap_save(4, 8, 2); b = FDC.overlap_save(4, 8, 2)
+    want = np.concatenate([a.work(x[:30]).view(np.float32), a.work(x[30:]).view(np.float32)])
+    got = np.concatenate([b.process(x[:6]), b.process(x[6:18]), b.process(x[18:])])
+    assert np.array_equal(got, want)
+    assert list(got[:16]) == [0, 0, 1, 2, 3, 4, 5, 6, 5, 6, 7, 8, 9, 10, 11, 12]
+    rng = np.random.default_rng(5)
+    y = (rng.standard_normal(3072 * 7) + 1j * rng.standard_normal(3072 * 7)).astype(np.complex64)
+    a = ref.overlap_save(8, 4096, 1024); b = FDC.overlap_save(8, 4096, 1024)
+    want = a.work(y).view(np.complex64)
+    got = np.concatenate([b.process(y[:3072 * 2]), b.process(y[3072 * 2:])])
+    assert np.array_equal(got.view(np.uint8), want.view(np.uint8))
+
+
+def test_vector_cut_bit_exact(FDC, ref):
+    x = np.array([0, 1, 2, 3, 10, 11, 12, 13], dtype=np.float32)
+    assert list(FDC.vector_cut_vxx(4, 4, 1, 2).process(x)) == [1, 2, 11, 12]          # Appendix B.5
+    rng = np.random.default_rng(6)
+    y = (rng.standard_normal(4096 * 5) + 1j * rng.standard_normal(4096 * 5)).astype(np.complex64)
+    want = ref.vector_cut_vxx(8, 4096, 963, 1024).work(y).view(np.complex64)
+    got = FDC.vector_cut_vxx(8, 4096, 963, 1024).process(y)
+    assert np.array_equal(got.view(np.uint8), want.view(np.uint8))
+    with pytest.raises(FDC.FDCError):
+        FDC.vector_cut_vxx(8, 16, 10, 8)
+
+
+@pytest.mark.parametrize("args", [(200, 4, 3, 0.5, 0.75, 2), (256, 4, 5, 0.55, 0.8, 1), (64, 2, 7, 0.88, 1.0, 0),
+                                  (512, 8, -3, 0.3, 0.9, 1)])
+def test_psw_block_bit_exact(FDC, ref, args):
+    a = ref.phase_shifting_windowing_vcc(*args); b = FDC.phase_shifting_windowing_vcc(*args)
+    assert np.array_equal(a.tables().view(np.uint8), b.tables().view(np.uint8))
+    rng = np.random.default_rng(args[0])
+    x = (rng.standard_normal(args[0] * 11) + 1j * rng.standard_normal(args[0] * 11)).astype(np.complex64)
+    want = np.concatenate([a.work(x[:args[0] * 2]).view(np.complex64), a.work(x[args[0] * 2:]).view(np.complex64)])
+    got = np.concatenate([b.process(x[:args[0] * 5]), b.process(x[args[0] * 5:])])
+    assert np.array_equal(got.view(np.uint8), want.view(np.uint8))
+    assert a.state() == b.state()
+
+
+CASES = {
+    "cfg1": (workloads.cfg1, 40),
+    "example4096_rect": (lambda: workloads.cfg_example(4096, 4, workloads.RECTANGULAR), 12),
+    "example4096_hann": (lambda: workloads.cfg_example(4096, 4, workloads.HANN), 12),
+    "example2048_r2_ramp": (lambda: workloads.cfg_example(2048, 2, workloads.RAMP), 12),
+    "example16384_r8": (lambda: workloads.cfg_example(16384, 8, workloads.HANN), 6),
+    "cfg2": (workloads.cfg2, 6),
+    "example32768": (lambda: workloads.cfg_example(32768, 4, workloads.HANN), 5),
+    "cfg4": (workloads.cfg4, 4),
+}
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_chain_matches_reference(FDC, ref, case):
+    mk, nblocks = CASES[case]
+    cfg = mk()
+    x = workloads.tones_input(cfg, nblocks * cfg.hop, seed=11) + workloads.noise_input(nblocks * cfg.hop, 12) * np.float32(0.05)
+    want, wspec = make_ref_chain(ref, cfg).run(x, nthreads=8, want_spectrum=True)
+    g = make_gpu_chain(FDC, cfg)
+    # two calls with different sizes: history and phase counters must carry over
+    n1 = nblocks // 3
+    o1, s1 = g.work_host(x[:n1 * cfg.hop], want_spectrum=True)
+    o2, s2 = g.work_host(x[n1 * cfg.hop:], want_spectrum=True)
+    spec = np.concatenate([s1, s2])
+    assert rel_l2(spec, wspec) < TOL
+    worst = 0.0
+    for i in range(cfg.nchan):
+        got = np.concatenate([o1[i], o2[i]])
+        assert got.size == want[i].size == nblocks * cfg.params[i][2]
+        worst = max(worst, rel_l2(got, want[i]))
+    assert worst < TOL, worst
+    assert g.blockcount == nblocks
+
+
+def test_device_path_equals_host_path(FDC):
+    import torch
+    cfg = workloads.cfg2()
+    nblocks = 700                                   # more than one L2 chunk (512 blocks)
+    x = workloads.noise_input(nblocks * cfg.hop, 3)
+    g1 = make_gpu_chain(FDC, cfg); g2 = make_gpu_chain(FDC, cfg)
+    outs, _ = g1.work_host(x)
+    d_in = torch.from_numpy(x.view(np.float32)).cuda()
+    d_out = torch.empty(nblocks * cfg.out_per_block * 2, dtype=torch.float32, device="cuda")
+    g2.work_device(d_in.data_ptr(), nblocks, d_out.data_ptr(), 0, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy().view(np.complex64)
+    for i, (off, ln) in enumerate(g2.out_slices(nblocks)):
+        assert np.array_equal(got[off:off + ln].view(np.uint8), outs[i].view(np.uint8))
