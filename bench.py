@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py -- input Msamples/s (cfp32) of the frequency-domain channelizer hot path and % of the HBM roofline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg4|cfg2|cfg1|cfg4_ovl75|cfg5] [--impl reference]
+
+One "step" = one pass of the hot path (overlap-save staging -> forward FFT -> all channels: bin cut, filter/phase table,
+inverse FFT, overlap discard) over one batch of `blocks_per_step` overlap-save blocks of synthetic input.
+  value : whole-job input samples/s with the batch resident in HBM (device pointers through the C ABI)
+  e2e   : the same through fdc_chan_work_host: pinned HOST input and output buffers, H2D/D2H inside the timed region
+  roofline : dominant kernel, algorithmic bytes per launch / its CUDA-event time, against MEASURED_PEAKS.json
+  cpu_baseline : the reference's own blocks (oracle/_ref, compiled from the unmodified sources) on the host cores
+N > 1: one process per GPU (torchrun); the stream is time-sharded into contiguous runs of blocks, every rank recomputes
+its own halo, no collective on the data path ("weak" scaling: per-GPU batch fixed).  The NCCL gather of the channel
+outputs to rank 0 is measured separately and reported under "gather".
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "gr-fdc_b200", "python"), os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+import workloads  # noqa: E402
+
+WORKLOADS = {
+    "cfg1": workloads.cfg1, "cfg2": workloads.cfg2, "cfg4": workloads.cfg4,
+    "cfg4_ovl75": lambda: workloads.cfg4(True), "cfg5": workloads.cfg5_fixed,
+}
+METRIC = "input Msamples/s (cfp32)"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return json.load(fh), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons during the timed region (NVML, ~5 ms period)."""
+
+    def __init__(self, index):
+        threading.Thread.__init__(self); self.daemon = True
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz, self.ok = index, False, [], set(), None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit(); self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def result(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def blocks_per_step(cfg):
+    """batch whose input alone (>= 256 MiB) exceeds the 126 MB L2, so consecutive steps cannot hit in cache"""
+    return max(64, int(np.ceil((256 << 20) / (8.0 * cfg.hop))))
+
+
+def cpu_reference_run(cfg, seconds_target=12.0):
+    """The reference's CPU implementation of the path: the unmodified gr-FDC blocks (oracle/_ref) in the hier block's
+    topology with the fp32 FFT stand-in, all host cores.  Bounded sample sized from a short calibration run."""
+    from oracle import fdc_ref
+    from helpers import make_ref_chain
+    if cfg.ovl != cfg.N // cfg.R:
+        return None
+    cores = os.cpu_count() or 1
+    fdc_ref.set_fft_mode(1)
+    chain = make_ref_chain(fdc_ref, cfg)
+    nb = max(cores, 8)
+    x = workloads.noise_input(nb * cfg.hop, 99)
+    t = time.perf_counter(); chain.run(x, nthreads=cores); dt = time.perf_counter() - t
+    nb2 = int(min(max(nb, nb * seconds_target / max(dt, 1e-3)), 4096, (1 << 31) // (8 * cfg.N)))
+    x = workloads.noise_input(nb2 * cfg.hop, 98)
+    t = time.perf_counter(); chain.run(x, nthreads=cores); dt = time.perf_counter() - t
+    fdc_ref.set_fft_mode(0)
+    return {"value": nb2 * cfg.hop / dt / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "reference",
+            "sample": "%d blocks (%d samples) of %s, unmodified gr-FDC blocks + fp32 FFT/VOLK stand-ins, %.1f s" %
+                      (nb2, nb2 * cfg.hop, cfg.name, dt)}
+
+
+def run_reference(args, cfg, rank, world):
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    from oracle import fdc_ref
+    from helpers import make_ref_chain
+    fdc_ref.set_fft_mode(1)
+    chain = make_ref_chain(fdc_ref, cfg)
+    nb = max(2 * cores, 16)                                   # bounded sample per step
+    x = workloads.noise_input(nb * cfg.hop, 97)
+    for _ in range(args.warmup):
+        chain.run(x, nthreads=cores)
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        chain.run(x, nthreads=cores)
+    dt = time.perf_counter() - t
+    v = args.steps * nb * cfg.hop / dt / 1e6
+    sample = "%d blocks (%d samples) of %s per step, unmodified gr-FDC blocks (oracle/_ref) + fp32 FFT/VOLK stand-ins" % (nb, nb * cfg.hop, cfg.name)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg.name, "fft": cfg.N, "overlap": cfg.ovl, "channels": cfg.nchan, "blocks_per_step": nb},
+            "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": cores, "kind": "reference", "sample": sample},
+            "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
+    ap.add_argument("--blocks", type=int, default=0, help="blocks per step per GPU (default: input >= 256 MiB)")
+    ap.add_argument("--chunk", type=int, default=0, help="override blocks per K1->K2 round trip")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = WORKLOADS[args.workload]()
+    if args.impl == "reference":
+        return run_reference(args, cfg, rank, world)
+    W = max(args.warmup, 3); K = max(args.steps, 1)
+
+    import torch
+    import torch.distributed as dist
+    import FDC
+    from helpers import make_gpu_chain
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    FDC._cabi.check(FDC._cabi.lib().fdc_set_device(local))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    L = FDC._cabi.lib()
+
+    nb = args.blocks or blocks_per_step(cfg)
+    chan = make_gpu_chain(FDC, cfg)
+    if args.chunk:
+        chan.chunk_blocks = args.chunk
+    # time sharding: rank r owns global blocks [r*K'*nb, ...) -- contiguous run, own halo (zeros here: synthetic stream)
+    chan.seek(rank * (W + K) * nb)
+    gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
+    d_in = torch.randn(nb * cfg.hop * 2, dtype=torch.float32, device=dev, generator=gen)
+    d_out = torch.empty(nb * cfg.out_per_block * 2, dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        chan.work_device(d_in.data_ptr(), nb, d_out.data_ptr(), 0, stream)
+
+    def bracket():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W):
+        step()
+    bracket()
+    sampler = ClockSampler(local); sampler.start()
+    l0 = L.fdc_launch_count()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        step()
+    e1.record()
+    bracket()
+    ms = e0.elapsed_time(e1)
+    launches = int(L.fdc_launch_count() - l0)
+    if len(sampler.samples) < 5:              # very short timed region: keep the same load running for the clock record
+        t_end = time.time() + 0.5
+        while time.time() < t_end:
+            step(); torch.cuda.synchronize()
+        clock_window = "timed region + 0.5 s of the same steps"
+    else:
+        clock_window = "timed region"
+    sampler.stop_flag = True; sampler.join()
+    clocks = sampler.result(); clocks["window"] = clock_window
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * K * nb * cfg.hop / (ms * 1e-3) / 1e6
+
+    # ---- per-kernel roofline (separate pass with events around each kernel) ----
+    peaks, peak_src = measured_peaks()
+    chan.set_profiling(True)
+    PK = max(3, min(K, 10))
+    for _ in range(PK):
+        step()
+    ms_fwd, ms_ext, chunks = chan.get_profile()
+    chan.set_profiling(False)
+    in_bytes = 8.0 * nb * cfg.hop * PK
+    out_bytes = 8.0 * nb * cfg.out_per_block * PK
+    spec_bytes = 8.0 * nb * cfg.N * PK
+    kern = {"forward_fft": {"ms": ms_fwd, "algorithmic_GB": in_bytes / 1e9, "GBps_algorithmic": in_bytes / ms_fwd / 1e6,
+                            "GBps_incl_spectrum_write": (in_bytes + spec_bytes) / ms_fwd / 1e6},
+            "channel_extract": {"ms": ms_ext, "algorithmic_GB": out_bytes / 1e9, "GBps_algorithmic": out_bytes / ms_ext / 1e6}}
+    dom = "forward_fft" if ms_fwd >= ms_ext else "channel_extract"
+    ach = kern[dom]["GBps_algorithmic"]
+    path_gbs = value * 1e6 / world * cfg.bytes_per_sample() / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                "launches_per_step": launches / K, "kernels": kern,
+                "path": {"bytes_per_sample": cfg.bytes_per_sample(), "achieved": path_gbs, "frac": path_gbs / peaks["hbm_gbs"],
+                         "frac_of_8TBps_nominal": path_gbs / 8000.0,
+                         "flop_per_sample": cfg.flops_per_sample(), "tflops_fp32": value * 1e6 / world * cfg.flops_per_sample() / 1e12}}
+
+    # ---- e2e: host buffers through the C ABI ----
+    e2e = None
+    if not args.no_e2e:
+        nb_e = min(nb, max(64, int((64 << 20) / (8.0 * cfg.hop))))            # 64 MiB of input per step
+        nbytes_in = 8 * nb_e * cfg.hop; nbytes_out = 8 * nb_e * cfg.out_per_block
+        import ctypes
+        h_in = L.fdc_host_alloc(nbytes_in); h_out = L.fdc_host_alloc(nbytes_out)
+        if not h_in or not h_out:
+            raise SystemExit("pinned allocation failed: " + FDC._cabi.last_error())
+        xin = np.ctypeslib.as_array(ctypes.cast(h_in, ctypes.POINTER(ctypes.c_float)), shape=(nb_e * cfg.hop * 2,))
+        xin[:] = np.random.default_rng(5 + rank).standard_normal(xin.size, dtype=np.float32)
+        outs = []
+        off = 0
+        for lo in chan.lout:
+            outs.append(h_out + off); off += 8 * nb_e * lo
+        ptrs = (ctypes.c_void_p * len(outs))(*outs)
+        EK = max(3, min(K, 10))
+        for _ in range(2):
+            FDC._cabi.check(L.fdc_chan_work_host(chan._h, ctypes.c_void_p(h_in), nb_e, ctypes.cast(ptrs, ctypes.c_void_p), None))
+        bracket()
+        t0 = time.perf_counter()
+        for _ in range(EK):
+            FDC._cabi.check(L.fdc_chan_work_host(chan._h, ctypes.c_void_p(h_in), nb_e, ctypes.cast(ptrs, ctypes.c_void_p), None))
+        bracket()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * EK * nb_e * cfg.hop / float(tt.item()) / 1e6, "unit": "Msamples/s",
+               "h2d_bytes_per_step": nbytes_in, "d2h_bytes_per_step": nbytes_out, "steps": EK, "blocks_per_step": nb_e,
+               "api": "fdc_chan_work_host (pinned host in/out, 3-slot H2D/compute/D2H pipeline)"}
+        L.fdc_host_free(h_in); L.fdc_host_free(h_out)
+
+    # ---- optional: NCCL gather of the channel outputs to the sink rank ----
+    gather = None
+    if world > 1:
+        bufs = [torch.empty_like(d_out) for _ in range(world)] if rank == 0 else None
+        for _ in range(2):
+            dist.gather(d_out, bufs, dst=0)
+        bracket()
+        g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
+        g0.record()
+        GK = 5
+        for _ in range(GK):
+            step(); dist.gather(d_out, bufs, dst=0)
+        g1.record(); bracket()
+        tg = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        gather = {"value": world * GK * nb * cfg.hop / (float(tg.item()) * 1e-3) / 1e6, "unit": "Msamples/s",
+                  "note": "compute + NCCL gather of every rank's output slab to rank 0 (sink ingest bound)"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_reference_run(cfg)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": cfg.name, "fft": cfg.N, "overlap": cfg.ovl, "hop": cfg.hop, "channels": cfg.nchan,
+                           "slice_len": cfg.params[0][1], "out_per_block": cfg.out_per_block, "blocks_per_step_per_gpu": nb,
+                           "chunk_blocks": chan.chunk_blocks, "sharding": "time (contiguous runs of blocks per rank, halo recomputed)",
+                           "l2_policy": "inputs larger than L2 (%.0f MB in, %.0f MB out per step)" %
+                                        (8e-6 * nb * cfg.hop, 8e-6 * nb * cfg.out_per_block)},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
+        if gather:
+            line["gather"] = gather
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

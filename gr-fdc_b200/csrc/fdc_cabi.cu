@@ -98,7 +98,19 @@ struct fdc_chan {
     cudaStream_t hs[NSLOT];
     DevBuf h_in[NSLOT], h_out[NSLOT], h_spec[NSLOT], h_mid[NSLOT];
     long host_chunk;
-    fdc_chan() : stream(0), host_chunk(0) { for (int i = 0; i < NSLOT; i++) hs[i] = 0; }
+    /* optional per-kernel timing (fdc_chan_set_profiling): events around K1 and K2 of every chunk */
+    bool prof;
+    std::vector<cudaEvent_t> prof_ev;      /* triples: before K1, after K1, after K2 */
+    std::vector<cudaEvent_t> prof_pool;
+    fdc_chan() : stream(0), host_chunk(0), prof(false) { for (int i = 0; i < NSLOT; i++) hs[i] = 0; }
+    cudaEvent_t ev()
+    {
+        cudaEvent_t e = 0;
+        if (!prof_pool.empty()) { e = prof_pool.back(); prof_pool.pop_back(); }
+        else cudaEventCreate(&e);
+        prof_ev.push_back(e);
+        return e;
+    }
 };
 
 static long pick_chunk_blocks(int N)
@@ -115,6 +127,7 @@ static int chan_enqueue_chunk(fdc_chan* c, const float2* d_in, const float2* d_h
                               float2* d_out, long call_blocks, long call_blk0, long glob_blk0, cudaStream_t s)
 {
     cudaError_t e;
+    if (c->prof) cudaEventRecord(c->ev(), s);
     if (!c->big) {
         FwdParams p; p.in = d_in; p.hist = d_hist; p.spec = d_spec; p.nblocks = nb; p.hop = c->hop; p.ovl = c->ovl; p.N = c->N;
         p.scale = 1.0f / (float)c->N;
@@ -125,7 +138,8 @@ static int chan_enqueue_chunk(fdc_chan* c, const float2* d_in, const float2* d_h
         e = launch_fwd_big(p, c->N, s);
     }
     if (e != cudaSuccess) return cuda_fail(e, "forward FFT launch");
-    if (!d_out) return 0;
+    if (c->prof) cudaEventRecord(c->ev(), s);
+    if (!d_out) { if (c->prof) cudaEventRecord(c->ev(), s); return 0; }
     for (size_t g = 0; g < c->groups.size(); g++) {
         ExtractParams q; q.spec = d_spec; q.spec_stride = c->N; q.tables = (const float2*)c->d_tables.p;
         q.chans = (const ChanDev*)c->d_chans.p; q.sel = (const int*)c->d_sel.p + c->groups[g].second.first; q.out = d_out;
@@ -133,6 +147,7 @@ static int chan_enqueue_chunk(fdc_chan* c, const float2* d_in, const float2* d_h
         e = launch_extract(q, c->groups[g].first, c->groups[g].second.second, s);
         if (e != cudaSuccess) return cuda_fail(e, "channel extract launch");
     }
+    if (c->prof) cudaEventRecord(c->ev(), s);
     return 0;
 }
 
@@ -199,6 +214,8 @@ void fdc_chan_destroy(fdc_chan* c)
     if (!c) return;
     cudaDeviceSynchronize();
     if (c->stream) cudaStreamDestroy(c->stream);
+    for (size_t i = 0; i < c->prof_ev.size(); i++) cudaEventDestroy(c->prof_ev[i]);
+    for (size_t i = 0; i < c->prof_pool.size(); i++) cudaEventDestroy(c->prof_pool[i]);
     for (int i = 0; i < fdc_chan::NSLOT; i++) if (c->hs[i]) cudaStreamDestroy(c->hs[i]);
     delete c;
 }
@@ -264,6 +281,43 @@ int fdc_chan_work_device(fdc_chan* c, const void* d_in_v, long nblocks, void* d_
     }
     if (chan_save_history(c, d_in, nblocks, s)) return -1;
     c->blockcount += nblocks;
+    return 0;
+}
+
+int fdc_chan_set_profiling(fdc_chan* c, int enable)
+{
+    if (!c) return fail("null context");
+    cudaDeviceSynchronize();
+    c->prof = enable != 0;
+    c->prof_pool.insert(c->prof_pool.end(), c->prof_ev.begin(), c->prof_ev.end());
+    c->prof_ev.clear();
+    return 0;
+}
+int fdc_chan_get_profile(fdc_chan* c, double* ms_fwd, double* ms_extract, long* chunks)
+{
+    if (!c) return fail("null context");
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return cuda_fail(e, "fdc_chan_get_profile");
+    double a = 0, b = 0; long n = 0;
+    for (size_t i = 0; i + 2 < c->prof_ev.size(); i += 3) {
+        float t1 = 0, t2 = 0;
+        cudaEventElapsedTime(&t1, c->prof_ev[i], c->prof_ev[i + 1]);
+        cudaEventElapsedTime(&t2, c->prof_ev[i + 1], c->prof_ev[i + 2]);
+        a += t1; b += t2; n++;
+    }
+    c->prof_pool.insert(c->prof_pool.end(), c->prof_ev.begin(), c->prof_ev.end());
+    c->prof_ev.clear();
+    if (ms_fwd) *ms_fwd = a;
+    if (ms_extract) *ms_extract = b;
+    if (chunks) *chunks = n;
+    return 0;
+}
+int fdc_chan_chunk_blocks(const fdc_chan* c) { return c ? (int)c->chunk_blocks : -1; }
+int fdc_chan_set_chunk_blocks(fdc_chan* c, int blocks)
+{
+    if (!c || blocks < 1) return fail("fdc_chan_set_chunk_blocks: bad arguments");
+    cudaDeviceSynchronize();
+    c->chunk_blocks = blocks;
     return 0;
 }
 

@@ -49,6 +49,10 @@ SIGNATURES = {
     "fdc_chan_work_host": (_i, [_vp, _vp, _l, _vp, _vp]),
     "fdc_chan_work_device": (_i, [_vp, _vp, _l, _vp, _vp, _vp]),
     "fdc_chan_sync": (_i, [_vp]),
+    "fdc_chan_set_profiling": (_i, [_vp, _i]),
+    "fdc_chan_get_profile": (_i, [_vp, _dp, _dp, C.POINTER(C.c_long)]),
+    "fdc_chan_chunk_blocks": (_i, [_vp]),
+    "fdc_chan_set_chunk_blocks": (_i, [_vp, _i]),
     "fdc_overlap_save_create": (_vp, [_i, _i, _i]),
     "fdc_overlap_save_work": (_i, [_vp, _i, _vp, _vp]),
     "fdc_overlap_save_destroy": (None, [_vp]),
@@ -105,7 +109,9 @@ def lib():
                            "or `make -C gr-fdc_b200/csrc`; there is no CPU fallback" % LIB_PATH)
         L = C.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
-            fn = getattr(L, name)
+            fn = getattr(L, name, None)
+            if fn is None:
+                raise FDCError("libfdc_b200.so does not export %s (stale build?)" % name)
             fn.restype = res
             fn.argtypes = args
         _lib = L

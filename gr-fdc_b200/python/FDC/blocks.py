@@ -229,6 +229,23 @@ class Channelizer(object):
     def sync(self):
         check(lib().fdc_chan_sync(self._h))
 
+    def set_profiling(self, enable):
+        check(lib().fdc_chan_set_profiling(self._h, int(bool(enable))))
+
+    def get_profile(self):
+        """(ms in forward-FFT kernels, ms in extract kernels, chunks) since the last call; synchronises."""
+        a, b, n = C.c_double(), C.c_double(), C.c_long()
+        check(lib().fdc_chan_get_profile(self._h, C.byref(a), C.byref(b), C.byref(n)))
+        return a.value, b.value, n.value
+
+    @property
+    def chunk_blocks(self):
+        return lib().fdc_chan_chunk_blocks(self._h)
+
+    @chunk_blocks.setter
+    def chunk_blocks(self, v):
+        check(lib().fdc_chan_set_chunk_blocks(self._h, int(v)))
+
     def out_slices(self, nblocks):
         """(offset, length) in items of every channel inside the device slab of a call with nblocks blocks."""
         return [(int(self.lout_prefix[i]) * nblocks, self.lout[i] * nblocks) for i in range(self.nchan)]

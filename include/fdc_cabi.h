@@ -88,6 +88,13 @@ int fdc_chan_work_host(fdc_chan* c, const void* in, long nblocks, void* const* o
  * ring is used then).  Only enqueues on `stream`; history/counters are advanced. */
 int fdc_chan_work_device(fdc_chan* c, const void* d_in, long nblocks, void* d_out, void* d_spectrum, void* stream);
 int fdc_chan_sync(fdc_chan* c);
+/* Measurement hooks.  Profiling records CUDA events around the forward-FFT and the channel-extract kernels of every
+ * chunk; get_profile synchronises and returns the summed kernel times (ms) since the last call.  chunk_blocks is
+ * the number of blocks per K1 -> K2 round trip (the spectrum ring that is meant to stay resident in L2). */
+int fdc_chan_set_profiling(fdc_chan* c, int enable);
+int fdc_chan_get_profile(fdc_chan* c, double* ms_fwd, double* ms_extract, long* chunks);
+int fdc_chan_chunk_blocks(const fdc_chan* c);
+int fdc_chan_set_chunk_blocks(fdc_chan* c, int blocks);
 
 /* ---- individual block replacements (host buffers in, host buffers out) ---------------------- */
 /* FDC.overlap_save, include/FDC/overlap_save.h:49, lib/overlap_save_impl.cc:62-81 */
