@@ -184,7 +184,12 @@ def main():
     gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
     d_in = torch.randn(nb * cfg.hop * 2, dtype=torch.float32, device=dev, generator=gen)
     d_out = torch.empty(nb * cfg.out_per_block * 2, dtype=torch.float32, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
+    # a dedicated (non-default) torch stream: the kernels are enqueued on it through the C ABI and the CUDA events
+    # that time them are recorded on the same stream
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
 
     def step():
         chan.work_device(d_in.data_ptr(), nb, d_out.data_ptr(), 0, stream)

@@ -143,7 +143,7 @@ static int chan_enqueue_chunk(fdc_chan* c, const float2* d_in, const float2* d_h
     for (size_t g = 0; g < c->groups.size(); g++) {
         ExtractParams q; q.spec = d_spec; q.spec_stride = c->N; q.tables = (const float2*)c->d_tables.p;
         q.chans = (const ChanDev*)c->d_chans.p; q.sel = (const int*)c->d_sel.p + c->groups[g].second.first; q.out = d_out;
-        q.nb = nb; q.call_blocks = call_blocks; q.call_blk0 = call_blk0; q.glob_blk0 = glob_blk0; q.nphase = c->nphase;
+        q.nb = nb; q.call_blocks = call_blocks; q.call_blk0 = call_blk0; q.glob_phase0 = (int)(glob_blk0 % c->nphase); q.nphase = c->nphase;
         e = launch_extract(q, c->groups[g].first, c->groups[g].second.second, s);
         if (e != cudaSuccess) return cuda_fail(e, "channel extract launch");
     }

@@ -1,6 +1,10 @@
 /* fdc_functors.cuh -- the global-memory sides of the tile FFT: what each kernel fuses into its
  * first-pass loads and last-pass stores.  Host/device code (see fdc_hd.h).
  *
+ * Every functor has   Ctx begin(batch)   -- per-signal addressing (block / channel / job lookup, phase selection,
+ *                                            row pointers), evaluated once per butterfly, and
+ *                     get(ctx, n) / put(ctx, k, v)  -- the per-element access, index arithmetic only.
+ *
  * HBM layout
  *   input stream  : contiguous cfp32 samples of this call, preceded logically by `hist`
  *                   (the last ovl samples of the previous call, zeros at stream start --
@@ -15,6 +19,24 @@
 
 namespace fdc {
 
+/* overlap-save window of one block: element n is in[blk*hop - ovl + n]; the first `nhist` elements of the very
+ * first blocks of a launch come from the saved history instead (lib/overlap_save_impl.cc:70-78) */
+struct OvlCtx { const float2* base; const float2* hbase; int nhist; };
+FDC_HD OvlCtx ovl_ctx(const float2* in, const float2* hist, long blk, int hop, int ovl, bool valid)
+{
+    OvlCtx c;
+    const long start = blk * hop - ovl;                 /* may be negative for the first blocks */
+    c.base = in + start; c.hbase = hist + blk * hop;
+    c.nhist = start < 0 ? (int)(-start) : 0;
+    if (!valid) { c.base = 0; c.nhist = -1; }
+    return c;
+}
+FDC_HD float2 ovl_get(const OvlCtx& c, long n)
+{
+    if (c.nhist < 0) return make_float2(0.f, 0.f);
+    return n < c.nhist ? fdc_ldg(c.hbase + n) : fdc_ldg(c.base + n);
+}
+
 /* ------------------------------------------------------------------ K1: forward FFT, N in one CTA */
 struct FwdParams {
     const float2* in;      /* new samples of this launch: block b starts at in[b*hop - ovl] */
@@ -25,23 +47,27 @@ struct FwdParams {
     float scale;           /* 1/N (a power of two: exact) */
 };
 template <int N, int B> struct FwdLoader {
+    typedef OvlCtx Ctx;
     const FwdParams& p; int tile;
-    FDC_HD float2 operator()(int batch, int n) const
+    FDC_HD Ctx begin(int batch) const
     {
         const long blk = (long)tile * B + batch;
-        if (blk >= p.nblocks) return make_float2(0.f, 0.f);
-        const long g = blk * p.hop + n - p.ovl;
-        return g < 0 ? fdc_ldg(p.hist + (p.ovl + g)) : fdc_ldg(p.in + g);
+        return ovl_ctx(p.in, p.hist, blk, p.hop, p.ovl, blk < p.nblocks);
     }
+    FDC_HD float2 get(const Ctx& c, int n) const { return ovl_get(c, n); }
 };
 template <int N, int B> struct FwdStorer {
+    typedef float2* Ctx;
     const FwdParams& p; int tile;
-    FDC_HD void operator()(int batch, int k, float2 v) const
+    FDC_HD Ctx begin(int batch) const
     {
         const long blk = (long)tile * B + batch;
-        if (blk >= p.nblocks) return;
+        return blk < p.nblocks ? p.spec + blk * N : (float2*)0;
+    }
+    FDC_HD void put(const Ctx& row, int k, float2 v) const
+    {
         /* fft_vcc shift=True for a forward transform: out[0:N/2] = Y[N/2:N], out[N/2:N] = Y[0:N/2] */
-        p.spec[blk * N + (k ^ (N / 2))] = make_float2(v.x * p.scale, v.y * p.scale);
+        if (row) row[k ^ (N / 2)] = make_float2(v.x * p.scale, v.y * p.scale);
     }
 };
 
@@ -61,39 +87,48 @@ struct BigParams {
     float scale;
 };
 template <int N1, int N2, int B> struct ColLoader {     /* signal = column n2, element index = n1 */
+    struct Ctx { OvlCtx o; int n2; };
     const BigParams& p; int tile; long blk;
-    FDC_HD float2 operator()(int batch, int n1) const
+    FDC_HD Ctx begin(int batch) const
     {
-        const int n2 = tile * B + batch;
-        const long g = blk * p.hop + (long)N2 * n1 + n2 - p.ovl;
-        return g < 0 ? fdc_ldg(p.hist + (p.ovl + g)) : fdc_ldg(p.in + g);
+        Ctx c; c.n2 = tile * B + batch; c.o = ovl_ctx(p.in, p.hist, blk, p.hop, p.ovl, true);
+        return c;
     }
+    FDC_HD float2 get(const Ctx& c, int n1) const { return ovl_get(c.o, (long)N2 * n1 + c.n2); }
 };
 template <int N1, int N2, int B> struct ColStorer {
+    struct Ctx { float2* col; unsigned n2; };
     const BigParams& p; int tile; long blk;
-    FDC_HD void operator()(int batch, int k1, float2 v) const
+    FDC_HD Ctx begin(int batch) const
     {
-        const int n2 = tile * B + batch;
-        const unsigned m = (unsigned)n2 * (unsigned)k1;                 /* < N1*N2 */
+        Ctx c; c.n2 = (unsigned)(tile * B + batch); c.col = p.mid + blk * ((long)N1 * N2) + c.n2;
+        return c;
+    }
+    FDC_HD void put(const Ctx& c, int k1, float2 v) const
+    {
+        const unsigned m = c.n2 * (unsigned)k1;                        /* < N1*N2 */
         const float2 w = cmul(fdc_ldg(p.twlo + (m & ((1u << p.tws_log2) - 1u))), fdc_ldg(p.twhi + (m >> p.tws_log2)));
-        p.mid[blk * ((long)N1 * N2) + (long)k1 * N2 + n2] = cmul(v, w);
+        c.col[(long)k1 * N2] = cmul(v, w);
     }
 };
 template <int N1, int N2, int B> struct RowLoader {     /* signal = row k1, element index = n2 */
+    typedef const float2* Ctx;
     const BigParams& p; int tile; long blk;
-    FDC_HD float2 operator()(int batch, int n2) const
-    {
-        const int k1 = tile * B + batch;
-        return p.mid[blk * ((long)N1 * N2) + (long)k1 * N2 + n2];
-    }
+    FDC_HD Ctx begin(int batch) const { return p.mid + blk * ((long)N1 * N2) + (long)(tile * B + batch) * N2; }
+    FDC_HD float2 get(const Ctx& row, int n2) const { return row[n2]; }
 };
 template <int N1, int N2, int B> struct RowStorer {
+    struct Ctx { float2* spec; int k1; };
     const BigParams& p; int tile; long blk;
-    FDC_HD void operator()(int batch, int k2, float2 v) const
+    FDC_HD Ctx begin(int batch) const
     {
-        const int k1 = tile * B + batch;
-        const int k = k1 + N1 * k2;
-        p.spec[blk * ((long)N1 * N2) + (k ^ (N1 * N2 / 2))] = make_float2(v.x * p.scale, v.y * p.scale);
+        Ctx c; c.k1 = tile * B + batch; c.spec = p.spec + blk * ((long)N1 * N2);
+        return c;
+    }
+    FDC_HD void put(const Ctx& c, int k2, float2 v) const
+    {
+        const int k = c.k1 + N1 * k2;
+        c.spec[k ^ (N1 * N2 / 2)] = make_float2(v.x * p.scale, v.y * p.scale);
     }
 };
 
@@ -120,33 +155,47 @@ struct ExtractParams {
     long nb;               /* blocks in this chunk */
     long call_blocks;      /* blocks of the whole call (slab size) */
     long call_blk0;        /* index of the chunk's first block inside the call */
-    long glob_blk0;        /* global index of the chunk's first block (phase origin) */
+    int glob_phase0;       /* (global index of the chunk's first block) mod nphase */
     int nphase;
 };
 template <int L, int B> struct ExtractLoader {
+    struct Ctx { const float2* x; const float2* w; };
     const ExtractParams& p; int tile; int ysel;
-    FDC_HD float2 operator()(int batch, int n) const
+    FDC_HD Ctx begin(int batch) const
     {
+        Ctx c; c.x = 0; c.w = 0;
         const long b = (long)tile * B + batch;
-        if (b >= p.nb) return make_float2(0.f, 0.f);
-        const ChanDev& c = p.chans[fdc_ldg(p.sel + ysel)];
-        const int phase = (int)((((p.glob_blk0 + b) % p.nphase) * c.shift) % p.nphase);
+        if (b >= p.nb) return c;
+        const ChanDev& ch = p.chans[fdc_ldg(p.sel + ysel)];
+        const unsigned np = (unsigned)p.nphase;
+        const unsigned phase = ((((unsigned)p.glob_phase0 + ((unsigned)b % np)) % np) * (unsigned)ch.shift) % np;
+        c.x = p.spec + b * p.spec_stride + ch.f;
+        c.w = p.tables + ch.tab_off + (long)phase * L;
+        return c;
+    }
+    FDC_HD float2 get(const Ctx& c, int n) const
+    {
+        if (!c.x) return make_float2(0.f, 0.f);
         const int m = (n + L / 2) & (L - 1);              /* fft_vcc inverse+shift: dst[n] = in[(n + l/2) mod l] */
-        const float2 x = fdc_ldg(p.spec + b * p.spec_stride + c.f + m);
-        const float2 w = fdc_ldg(p.tables + c.tab_off + (long)phase * L + m);
-        return cmul_exact(x, w);
+        return cmul_exact(fdc_ldg(c.x + m), fdc_ldg(c.w + m));
     }
 };
 template <int L, int B> struct ExtractStorer {
+    struct Ctx { float2* dst; int skip; float gain; };
     const ExtractParams& p; int tile; int ysel;
-    FDC_HD void operator()(int batch, int k, float2 v) const
+    FDC_HD Ctx begin(int batch) const
     {
+        Ctx c; c.dst = 0; c.skip = 0; c.gain = 0.f;
         const long b = (long)tile * B + batch;
-        if (b >= p.nb) return;
-        const ChanDev& c = p.chans[fdc_ldg(p.sel + ysel)];
-        const int skip = L - c.lout;
-        if (k < skip) return;
-        p.out[p.call_blocks * c.lout_prefix + (p.call_blk0 + b) * c.lout + (k - skip)] = make_float2(v.x * c.gain, v.y * c.gain);
+        if (b >= p.nb) return c;
+        const ChanDev& ch = p.chans[fdc_ldg(p.sel + ysel)];
+        c.skip = L - ch.lout; c.gain = ch.gain;
+        c.dst = p.out + p.call_blocks * ch.lout_prefix + (p.call_blk0 + b) * ch.lout - c.skip;
+        return c;
+    }
+    FDC_HD void put(const Ctx& c, int k, float2 v) const
+    {
+        if (c.dst && k >= c.skip) c.dst[k] = make_float2(v.x * c.gain, v.y * c.gain);
     }
 };
 
@@ -166,49 +215,70 @@ struct JobParams {
     const float2* tables; const ExtractJob* jobs; float2* out; int njobs;
 };
 template <int L, int B> struct JobLoader {
+    struct Ctx { const float2* x; const float2* w; };
     const JobParams& p; int tile;
-    FDC_HD float2 operator()(int batch, int n) const
+    FDC_HD Ctx begin(int batch) const
     {
+        Ctx c; c.x = 0; c.w = 0;
         const int ji = tile * B + batch;
-        if (ji >= p.njobs) return make_float2(0.f, 0.f);
+        if (ji >= p.njobs) return c;
         const ExtractJob& jb = p.jobs[ji];
+        c.x = (jb.row < 0 ? p.hist : p.spec + (long)jb.row * p.spec_stride) + jb.start;
+        c.w = p.tables + jb.tab_off;
+        return c;
+    }
+    FDC_HD float2 get(const Ctx& c, int n) const
+    {
+        if (!c.x) return make_float2(0.f, 0.f);
         const int m = (n + L / 2) & (L - 1);
-        const float2* row = jb.row < 0 ? p.hist : p.spec + (long)jb.row * p.spec_stride;
-        return cmul_exact(fdc_ldg(row + jb.start + m), fdc_ldg(p.tables + jb.tab_off + m));
+        return cmul_exact(fdc_ldg(c.x + m), fdc_ldg(c.w + m));
     }
 };
 template <int L, int B> struct JobStorer {
+    struct Ctx { float2* dst; int skip; };
     const JobParams& p; int tile;
-    FDC_HD void operator()(int batch, int k, float2 v) const
+    FDC_HD Ctx begin(int batch) const
     {
+        Ctx c; c.dst = 0; c.skip = 0;
         const int ji = tile * B + batch;
-        if (ji >= p.njobs) return;
+        if (ji >= p.njobs) return c;
         const ExtractJob& jb = p.jobs[ji];
-        if (k < jb.skip) return;
-        p.out[jb.dst_off + (k - jb.skip)] = v;
+        c.skip = jb.skip; c.dst = p.out + jb.dst_off - jb.skip;
+        return c;
     }
+    FDC_HD void put(const Ctx& c, int k, float2 v) const { if (c.dst && k >= c.skip) c.dst[k] = v; }
 };
 
 /* ------------------------------------------------- plain batched FFT (fft_vcc stage replacement) */
 struct PlainParams { const float2* in; float2* out; long nvec; int shift; };
 template <int L, int B, int DIR> struct PlainLoader {
+    typedef const float2* Ctx;
     const PlainParams& p; int tile;
-    FDC_HD float2 operator()(int batch, int n) const
+    FDC_HD Ctx begin(int batch) const
     {
         const long v = (long)tile * B + batch;
-        if (v >= p.nvec) return make_float2(0.f, 0.f);
+        return v < p.nvec ? p.in + v * L : (const float2*)0;
+    }
+    FDC_HD float2 get(const Ctx& row, int n) const
+    {
+        if (!row) return make_float2(0.f, 0.f);
         const int m = (DIR < 0 && p.shift) ? ((n + L / 2) & (L - 1)) : n;
-        return fdc_ldg(p.in + v * L + m);
+        return fdc_ldg(row + m);
     }
 };
 template <int L, int B, int DIR> struct PlainStorer {
+    typedef float2* Ctx;
     const PlainParams& p; int tile;
-    FDC_HD void operator()(int batch, int k, float2 v) const
+    FDC_HD Ctx begin(int batch) const
     {
-        const long vv = (long)tile * B + batch;
-        if (vv >= p.nvec) return;
+        const long v = (long)tile * B + batch;
+        return v < p.nvec ? p.out + v * L : (float2*)0;
+    }
+    FDC_HD void put(const Ctx& row, int k, float2 v) const
+    {
+        if (!row) return;
         const int m = (DIR > 0 && p.shift) ? (k ^ (L / 2)) : k;
-        p.out[vv * L + m] = v;
+        row[m] = v;
     }
 };
 

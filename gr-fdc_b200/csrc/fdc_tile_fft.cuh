@@ -111,8 +111,9 @@ struct TileFFT {
 #pragma unroll
         for (int u = 0; u < PS::U; u++) {
             int batch, j; PS::map(tid, u, batch, j);
+            const typename Loader::Ctx c = ld.begin(batch);       /* per-signal addressing, hoisted out of the element loop */
 #pragma unroll
-            for (int t = 0; t < PS::R; t++) v[u * PS::R + t] = ld(batch, j + t * PS::NBF);
+            for (int t = 0; t < PS::R; t++) v[u * PS::R + t] = ld.get(c, j + t * PS::NBF);
         }
     }
     template <int P> static FDC_HD void read_smem(int tid, float2* v, const float2* smem)
@@ -145,8 +146,9 @@ struct TileFFT {
             int batch, j; PS::map(tid, u, batch, j);
             const int k = j % PS::NS;
             const int o = (j - k) * PS::R + k;
+            const typename Storer::Ctx c = st.begin(batch);
 #pragma unroll
-            for (int t = 0; t < PS::R; t++) st(batch, o + t * PS::NS, v[u * PS::R + t]);
+            for (int t = 0; t < PS::R; t++) st.put(c, o + t * PS::NS, v[u * PS::R + t]);
         }
     }
 

@@ -8,8 +8,8 @@
 using namespace fdc;
 typedef std::complex<double> cd;
 
-struct Ld { const float2* in; int L; float2 operator()(int batch, int n) const { return in[batch * L + n]; } };
-struct St { float2* out; int L; void operator()(int batch, int k, float2 v) const { out[batch * L + k] = v; } };
+struct Ld { typedef const float2* Ctx; const float2* in; int L; Ctx begin(int batch) const { return in + batch * L; } float2 get(const Ctx& c, int n) const { return c[n]; } };
+struct St { typedef float2* Ctx; float2* out; int L; Ctx begin(int batch) const { return out + batch * L; } void put(const Ctx& c, int k, float2 v) const { c[k] = v; } };
 
 template <class ENG, int PH> struct Run {
     static void go(std::vector<std::array<float2, 16>>& regs, float2* smem, const float2* tw, Ld& ld, St& st)
