@@ -1,0 +1,386 @@
+/* fdc_act_state.cc -- see fdc_act_state.h.  Compile with -ffp-contract=off: the geometry below is compared
+ * integer for integer with the reference, and its float/double mix follows the reference expression by expression. */
+#include "fdc_act_state.h"
+#include <algorithm>
+#include <cmath>
+#include <ctime>
+#include <limits>
+#include <sstream>
+#include <stdexcept>
+
+namespace fdc {
+
+template <class T> static std::string num2str(T v) { std::ostringstream ss; ss << v; return ss.str(); }
+
+std::string current_time_string()
+{
+    /* lib/SegmentDetection_impl.cc:680-694 */
+    time_t raw; time(&raw);
+    struct tm ti; localtime_r(&raw, &ti);
+    char p[80];
+    strftime(p, sizeof(p), "%Y-%m-%d-%H-%M-%S", &ti);
+    return std::string(p);
+}
+
+/* fmod(fmod(x, y) + 1, y) -- lib/SegmentDetection_impl.cc:700-703 */
+static float mod_f(float x, float y) { return (float)fmod(fmod((double)x, (double)y) + 1.0, (double)y); }
+static int nextpow2_shift(double v) { return 1 << (int)ceil(log2(v)); }   /* lib/SegmentDetection_impl.cc:705-708 */
+
+/* ---- windows ------------------------------------------------------------------------------------ */
+void build_flank_windows(int blocklen, int relinvovl, double flank_puffer, std::vector<cfloat>& tab, std::vector<long>& offsets)
+{
+    const int nsizes = (int)log2((double)blocklen) + 1;
+    offsets.assign((size_t)nsizes + 1, 0);
+    for (int s = 0; s < nsizes; s++) offsets[s + 1] = offsets[s] + (long)relinvovl * (1L << s);
+    tab.assign((size_t)offsets[nsizes], cfloat(0.f, 0.f));
+    for (int s = 0; s < nsizes; s++) {
+        const int w = 1 << s;
+        const int puffersamples = (int)(flank_puffer * (double)w);
+        for (int i = 0; i < relinvovl; i++) {
+            cfloat* v = tab.data() + offsets[s] + (long)i * w;
+            const cfloat ph(std::polar(1.0, 2.0 * M_PI * (double)i / (double)relinvovl));
+            for (int k = 0; k < w; k++) v[k] = ph;
+            for (int k = 0; k < puffersamples; k++) {
+                const float fl = 0.5f - 0.5f * (float)cos(M_PI * (double)k / (double)puffersamples);
+                v[k] *= fl;
+                v[w - 1 - k] *= fl;
+            }
+        }
+    }
+}
+
+void build_pac_windows(int blocklen, int relinvovl, int rampsamps, std::vector<cfloat>& tab)
+{
+    tab.assign((size_t)relinvovl * blocklen, cfloat(0.f, 0.f));
+    for (int i = 0; i < relinvovl; i++) {
+        const cfloat ph = std::polar(1.0f, (float)(2.0f * M_PI * (double)i / (double)relinvovl));
+        for (int k = 0; k < blocklen; k++) tab[(size_t)i * blocklen + k] = ph;
+    }
+    /* rising edge on the first rampsamps entries, mirrored onto the end of the length-blocklen vector */
+    for (int i = 0; i < rampsamps; i++)
+        for (int r = 0; r < relinvovl; r++) {
+            cfloat* v = tab.data() + (size_t)r * blocklen;
+            v[i] *= (float)sin(0.5 * M_PI * (double)i / (double)(rampsamps + 1));
+            v[blocklen - i - 1] = v[i];
+        }
+}
+
+/* ---- segment geometry --------------------------------------------------------------------------- */
+SegGeometry segdet_geometry(int blocklen_i, float start, float stop, float minchandist)
+{
+    const size_t blocklen = (size_t)blocklen_i;
+    minchandist = mod_f(minchandist, 1.0f);
+    start = mod_f(start, 1.0f);
+    stop = mod_f(stop, 1.0f);
+    if (start == stop) throw std::invalid_argument("Start must not be equal to stop. ");
+    if (start > stop) { const float t = start; start = stop; stop = t; }
+    const double dec = (double)blocklen * (double)minchandist / 2.0;
+    const size_t D = dec < 2.0 ? 1 : (size_t)(int)dec;
+    size_t width = (size_t)((double)(stop - start) * (double)blocklen);
+    if (width % D) width += D - width % D;
+    if (width > blocklen) width = blocklen - (blocklen % D);
+    const size_t mid = (size_t)((double)(0.5f * (start + stop)) * (double)blocklen);
+    size_t s0 = mid < width / 2 ? 0 : mid - width / 2;
+    size_t s1 = s0 + width;
+    if (s1 > blocklen) { s1 = blocklen; s0 = s1 - blocklen; }          /* sic: lib/SegmentDetection_impl.cc:630-633 */
+    SegGeometry g; g.start = (long)s0; g.stop = (long)s1; g.width = (long)width; g.D = (long)D; g.M = (long)(width / D);
+    return g;
+}
+int actdet_decimation(int blocklen, float minchandist)
+{
+    if (minchandist <= 0.0f || minchandist >= 1.0)
+        throw std::invalid_argument(std::string("Minimum channel distance is invalid. Must be in (0,1), is ") + num2str(minchandist));
+    const double dec = (double)blocklen * (double)minchandist / 2.0;
+    return dec < 2.0 ? 1 : (int)dec;
+}
+SegGeometry actdet_geometry(int blocklen, float v0, float v1, int D)
+{
+    if (v0 >= v1 || v0 < 0.0f || v1 > 1.0f) {
+        std::string s = "Segment is incorrect. must be of size 2 with each member in (0,1), with v[0]<v[1]. v is [";
+        s += num2str(v0) + std::string(", ") + num2str(v1) + std::string(", ") + std::string("]");
+        throw std::invalid_argument(s);
+    }
+    const int mid = (int)std::abs(round(((double)v1 + (double)v0) * 0.5 * (double)blocklen));
+    int width = (int)std::abs(round(((double)v1 - (double)v0) * (double)blocklen));
+    width = (width % D == 0) ? width : width + D - width % D;
+    if (width >= blocklen) {
+        /* the reference loops `while(width>=blocklen) width=blocklen-(blocklen%D)` (…vcm_impl.cc:262-263), which never
+         * terminates when D divides blocklen; refuse that case instead of hanging */
+        if (blocklen % D == 0) throw std::invalid_argument("Segment spans the whole band (the reference does not terminate for this input). ");
+        width = blocklen - (blocklen % D);
+    }
+    int start = mid - width / 2 <= 0 ? 0 : mid - width / 2;
+    int stop = start + width;
+    if (stop > blocklen) { stop = blocklen; start = blocklen - width; }
+    if (start < 0 || stop > blocklen)
+        throw std::invalid_argument(std::string("Cannot evaluate start and stop of segment... start=") + num2str(start) + std::string(", stop=") + num2str(stop));
+    SegGeometry g; g.start = start; g.stop = stop; g.width = stop - start; g.D = D;
+    if (g.width % D)
+        throw std::invalid_argument(std::string("Invalid segment width. Not a multiple of channel detection decimation factor. width=") +
+                                    num2str(g.width) + std::string(", chan_det_dec_fact=") + num2str(D));
+    g.M = g.width / D;
+    return g;
+}
+
+/* ---- SegmentState --------------------------------------------------------------------------------- */
+typedef std::pair<float, size_t> fipair;
+static bool fipair_desc(fipair& a, fipair& b) { return a.first > b.first; }
+
+void SegmentState::candidates(const EdgeBlock& e, std::deque<std::array<long, 2> >& poss) const
+{
+    /* lib/SegmentDetection_impl.cc:195-244; the same containers and std::sort call so that ties between equal
+     * ratios resolve identically */
+    std::deque<fipair> rise;
+    std::deque<size_t> fall;
+    for (size_t n = 0; n < e.rise.size(); n++) rise.push_back(fipair(e.rise[n].first, (size_t)e.rise[n].second * (size_t)g.D + (size_t)g.start));
+    for (size_t n = 0; n < e.fall.size(); n++) fall.push_back(((size_t)e.fall[n] + 1) * (size_t)g.D + (size_t)g.start);
+    std::sort(rise.begin(), rise.end(), fipair_desc);
+    while (rise.size()) {
+        const size_t poss_start = rise.front().second;
+        rise.pop_front();
+        std::deque<size_t>::iterator next_end = std::upper_bound(fall.begin(), fall.end(), poss_start);
+        if (next_end == fall.end()) continue;
+        bool overlapping = false;
+        for (size_t k = 0; k < poss.size(); k++)
+            if ((long)poss_start < poss[k][1] && (long)*next_end >= poss[k][0]) { overlapping = true; break; }
+        if (overlapping) continue;
+        std::array<long, 2> a = {{(long)poss_start, (long)*next_end}};
+        poss.push_back(a);
+    }
+}
+
+bool SegmentState::activate(long detect_start, long detect_end, long& uid_counter)
+{
+    /* lib/SegmentDetection_impl.cc:290-344 */
+    const long detect_width = detect_end - detect_start;
+    const long extract_mid = detect_start + detect_width / 2;
+    const long extract_width = nextpow2_shift((double)(long)ceil((double)detect_width * (1.0 + 2.0 * flank)));
+    if (extract_width > blocklen) return false;         /* the reference logs to cerr and skips the carrier */
+    long extract_start = extract_mid - extract_width / 2, extract_end = extract_mid + extract_width / 2;
+    if (extract_start < 0) { extract_start = 0; extract_end = extract_width; }
+    if (extract_end > blocklen) { extract_end = blocklen; extract_start = blocklen - extract_width; }
+    ActiveChannel c;
+    c.ID = (int)chan_counter++;
+    c.detect_start = (int)detect_start; c.detect_stop = (int)detect_end;
+    c.extract_start = (int)extract_start; c.extract_stop = (int)extract_end; c.extract_width = (int)extract_width;
+    c.extract_window = (int)log2((double)extract_width);
+    c.ovlskip = (int)(extract_width / relinvovl);
+    c.outputsamples = c.extract_width - c.ovlskip;
+    c.count = 0; c.phase = 0; c.phaseincrement = (int)(extract_start % relinvovl); c.inactive = -1; c.part = 0;
+    c.msg_ID = current_time_string() + std::string(".DETECTED.") + num2str(seg_id) + std::string(".") + num2str(c.ID);
+    c.uid = uid_counter++; c.ndata = 0;
+    active.push_back(c);
+    return true;
+}
+
+void SegmentState::match(std::deque<std::array<long, 2> >& poss, long& uid_counter)
+{
+    /* lib/SegmentDetection_impl.cc:246-288 */
+    if (poss.empty()) {
+        for (size_t k = 0; k < active.size(); k++) active[k].inactive += 1;
+        return;
+    }
+    for (size_t k = 0; k < active.size(); k++) {
+        ActiveChannel& c = active[k];
+        bool inactive = true;
+        size_t i = 0;
+        while (i < poss.size()) {
+            const int pc_start = (int)poss[i][0], pc_end = (int)poss[i][1];
+            if (pc_start < c.detect_stop && pc_end >= c.detect_start) {
+                c.inactive = 0; inactive = false;
+                poss.erase(poss.begin() + i);
+            } else i++;
+        }
+        if (inactive) c.inactive += 1;
+    }
+    for (size_t i = 0; i < poss.size(); i++) activate(poss[i][0], poss[i][1], uid_counter);
+}
+
+void SegmentState::job(ActiveChannel& c, int row, std::vector<ActJob>& jobs, std::vector<ActOp>& ops)
+{
+    /* process_channel, lib/SegmentDetection_impl.cc:399-429 */
+    ActJob j; j.L = c.extract_width; j.row = row; j.start = c.extract_start;
+    j.tab_off = (*win_offsets)[c.extract_window] + (long)c.phase * c.extract_width;
+    j.skip = c.ovlskip; j.uid = c.uid;
+    ActOp o; o.kind = ActOp::PUSH; o.uid = c.uid; o.job = (int)jobs.size(); o.ntake = 0; o.blocksamples = c.outputsamples;
+    jobs.push_back(j); ops.push_back(o);
+    c.ndata++; c.count++;
+    c.phase = (c.phase + c.phaseincrement) % relinvovl;
+}
+
+MsgMeta SegmentState::meta(const ActiveChannel& c, long blockcount, bool fin) const
+{
+    MsgMeta m;
+    m.id = c.msg_ID; m.finalized = fin; m.publish = msg_output;
+    m.part = fin ? (c.part > 0 ? c.part : -1) : c.part;
+    m.rel_bw = (double)c.extract_width / (double)blocklen;
+    m.rel_cfreq = (double)(c.extract_start + c.extract_stop) / 2.0 / (double)blocklen;
+    m.blockstart = blockcount - c.count; m.blockend = blockcount;
+    m.vectorstart = c.extract_start; m.vectorend = c.extract_stop;
+    if (fileoutput) m.filename = path + std::string("/") + c.msg_ID + (fin ? std::string(".fin") : std::string(".parted.") + std::to_string(c.part));
+    if (verbose) {
+        m.logline = c.msg_ID + (fin ? std::string(".fin: ") : std::string(".part: ")) + std::string("start=") + num2str(c.extract_start) +
+                    std::string(", stop=") + num2str(c.extract_stop) + (fin ? std::string("") : std::string(", part=") + num2str(c.part + 1)) +
+                    std::string(", blockstart=") + num2str(blockcount - c.count) + std::string(", blockend=") + num2str(blockcount);
+    }
+    return m;
+}
+
+void SegmentState::emit_final(ActiveChannel& c, long blockcount, std::vector<ActOp>& ops)
+{
+    /* emit_channel, lib/SegmentDetection_impl.cc:437-482: everything buffered, even nothing */
+    ActOp o; o.kind = ActOp::EMIT; o.uid = c.uid; o.job = -1; o.ntake = -1; o.blocksamples = c.outputsamples;
+    o.meta = meta(c, blockcount, true);
+    ops.push_back(o);
+    c.ndata = 0;
+}
+
+void SegmentState::emit_partial(ActiveChannel& c, long blockcount, std::vector<ActOp>& ops)
+{
+    /* emit_unfinished_channel, lib/SegmentDetection_impl.cc:484-539 */
+    if (maxblocks < 0 || c.ndata < maxblocks) return;
+    const int ntx = maxblocks == 0 ? c.ndata : maxblocks;
+    if (ntx <= 0) return;
+    ActOp o; o.kind = ActOp::EMIT; o.uid = c.uid; o.job = -1; o.ntake = ntx; o.blocksamples = c.outputsamples;
+    o.meta = meta(c, blockcount, false);
+    ops.push_back(o);
+    c.ndata -= ntx;
+    c.part++;
+}
+
+void SegmentState::block(int row, const EdgeBlock& e, long blockcount, long& uid_counter, std::vector<ActJob>& jobs, std::vector<ActOp>& ops)
+{
+    std::deque<std::array<long, 2> > poss;
+    candidates(e, poss);
+    match(poss, uid_counter);
+    /* process_active_channels_single_thread, lib/SegmentDetection_impl.cc:346-365 */
+    for (size_t k = 0; k < active.size(); k++) {
+        ActiveChannel& c = active[k];
+        if (c.inactive < 0) { job(c, row - 1, jobs, ops); job(c, row, jobs, ops); c.inactive = 0; }
+        else if (c.inactive > delay) emit_final(c, blockcount, ops);
+        else job(c, row, jobs, ops);
+        if (emit_inside_loop && maxblocks >= 0 && c.ndata >= maxblocks) emit_partial(c, blockcount, ops);
+    }
+    if (!emit_inside_loop && maxblocks >= 0)
+        for (size_t k = 0; k < active.size(); k++)
+            if (active[k].ndata >= maxblocks) emit_partial(active[k], blockcount, ops);
+    /* clear_inactive_channels, lib/SegmentDetection_impl.cc:541-549 */
+    size_t i = 0;
+    while (i < active.size()) {
+        if (active[i].inactive > delay) {
+            ActOp o; o.kind = ActOp::DROP; o.uid = active[i].uid; o.job = -1; o.ntake = 0; o.blocksamples = 0;
+            ops.push_back(o);
+            active.erase(active.begin() + i);
+        } else i++;
+    }
+}
+
+/* ---- PacState ------------------------------------------------------------------------------------- */
+static int pac_nextpow2(int k)
+{
+    if (k <= 0) throw std::invalid_argument(std::string("Can't eval nextpow2 from ") + std::to_string(k) + std::string("\n"));
+    return (int)std::pow(2, ceil(log2((double)k)));
+}
+
+void PacState::init(int v_blocklen, float cfreq, float bw, int v_relinvovl, float v_thresh, int v_maxblocks, int v_delay, int v_ID)
+{
+    /* constructor + set_startstop + set_thresh, lib/PowerActivationChannel_impl.cc:42-135, 314-381 */
+    ID = v_ID;
+    if (v_blocklen <= 0) throw std::invalid_argument(std::string("Blocklen invalid, must be >0, is ") + std::to_string(v_blocklen));
+    blocklen = v_blocklen;
+    if (v_relinvovl <= 0 || v_relinvovl != pac_nextpow2(v_relinvovl))
+        throw std::invalid_argument(std::string("Relinvovl invalid, must be >0 and power of 2, is ") + std::to_string(v_relinvovl));
+    relinvovl = v_relinvovl;
+
+    bw = bw > 0.0f ? bw : -bw;
+    if (bw > 1.0 || cfreq - bw / 2.0f < 0.0f || cfreq + bw / 2.0f > 1.0f)
+        throw std::invalid_argument(std::string("Desired channel is out of band: cfreq=") + std::to_string(cfreq) + std::string(", bw=") + std::to_string(bw));
+    extract_width = pac_nextpow2((int)ceil((double)bw * (double)blocklen));
+    if (extract_width > blocklen) extract_width = blocklen;
+    const int mid = (int)round((double)cfreq * (double)blocklen);
+    extract_start = mid - extract_width / 2;
+    if (extract_start < 0) extract_start = 0;
+    extract_stop = extract_start + extract_width;
+    if (extract_stop > blocklen) { extract_stop = blocklen; extract_start = extract_stop - blocklen; }   /* sic, :333-336 */
+    measure_start = (int)round((double)(cfreq - bw / 2.0f) * (double)blocklen);
+    measure_stop = (int)round((double)(cfreq + bw / 2.0f) * (double)blocklen);
+    if (measure_start < extract_start) measure_start = extract_start;
+    if (measure_stop > extract_stop) measure_stop = extract_stop;
+    rampsamps = ((extract_stop - extract_start) - (measure_stop - measure_start)) / 3;
+    deltaphase = extract_start % relinvovl;
+    phase = 0;
+    output_ovl_offset = extract_width / relinvovl;
+    output_len = extract_width - output_ovl_offset;
+
+    if (v_thresh <= 0.0f) throw std::invalid_argument(std::string("Threshold is interpreted as dB and must be >0.0, is ") + std::to_string(v_thresh));
+    thresh = (float)pow(10.0, (double)v_thresh / 10.0);
+    maxblocks = v_maxblocks;
+    deactivation_delay = v_delay <= 0 ? 0 : v_delay;
+    lastpower = std::numeric_limits<float>::max();
+    active = false;
+    blockcount = 1;
+    finished_channels = 0; count = 0; part = 0; uid = -1; ndata = 0;
+}
+
+void PacState::job(int row, std::vector<ActJob>& jobs, std::vector<ActOp>& ops)
+{
+    /* process_channel, lib/PowerActivationChannel_impl.cc:260-284 */
+    ActJob j; j.L = extract_width; j.row = row; j.start = extract_start; j.tab_off = (long)phase * blocklen; j.skip = output_ovl_offset; j.uid = uid;
+    ActOp o; o.kind = ActOp::PUSH; o.uid = uid; o.job = (int)jobs.size(); o.ntake = 0; o.blocksamples = output_len;
+    jobs.push_back(j); ops.push_back(o);
+    ndata++; count++;
+    phase = (phase + deltaphase) % relinvovl;
+}
+
+void PacState::emit(bool fin, std::vector<ActOp>& ops)
+{
+    /* emit_data, lib/PowerActivationChannel_impl.cc:212-258 */
+    ActOp o; o.kind = ActOp::EMIT; o.uid = uid; o.job = -1; o.ntake = -1; o.blocksamples = output_len;
+    MsgMeta& m = o.meta;
+    m.id = msgID + (fin ? std::string(".fin") : std::string(".part"));
+    m.finalized = fin; m.part = part;
+    m.rel_cfreq = (double)(extract_start + extract_stop) / 2.0 / (double)blocklen;
+    m.rel_bw = (double)extract_width / (double)blocklen;
+    m.blockstart = blockcount - count; m.blockend = blockcount; m.vectorstart = -1; m.vectorend = -1;
+    m.publish = msg;                           /* no message port: only the file / log side effects remain */
+    if (fileoutput) m.filename = path + std::string("/") + msgID + (fin ? std::string(".fin") : (std::string(".parted.") + std::to_string(part)));
+    if (verbose)
+        m.logline = msgID + (fin ? std::string(".fin") : (std::string(".parted.") + std::to_string(part))) + std::string(": ") + std::string("start=") +
+                    std::to_string(extract_start) + std::string(", stop=") + std::to_string(extract_stop) + std::string(", blockstart=") +
+                    std::to_string(blockcount - count) + std::string(", blockend=") + std::to_string(blockcount);
+    ops.push_back(o);
+    ndata = 0;
+    part++;
+}
+
+void PacState::block(int row, float pwr, long& uid_counter, std::vector<ActJob>& jobs, std::vector<ActOp>& ops)
+{
+    /* work + measure_power decision, lib/PowerActivationChannel_impl.cc:137-177, 286-306 */
+    if (pwr == 0.0f) pwr = std::numeric_limits<float>::min();
+    bool toggle = false;
+    if ((!active) && pwr / lastpower >= thresh) toggle = true;
+    else if (active && lastpower / pwr >= thresh) toggle = true;
+    lastpower = pwr;
+    if (toggle) {
+        if (!active) {
+            /* activate: previous and current block, :198-210 */
+            part = 0; count = 0; active = true; phase = 0; ndata = 0;
+            if (uid >= 0) { ActOp d; d.kind = ActOp::DROP; d.uid = uid; d.job = -1; d.ntake = 0; d.blocksamples = 0; ops.push_back(d); }
+            uid = uid_counter++;
+            msgID = current_time_string() + std::string(".PowActChan.") + std::to_string(ID) + std::string(".") + std::to_string(finished_channels);
+            job(row - 1, jobs, ops);
+            job(row, jobs, ops);
+        } else {
+            job(row, jobs, ops);
+            active = false;
+            emit(true, ops);
+            finished_channels++;
+        }
+    } else if (active) {
+        job(row, jobs, ops);
+        if (maxblocks == 0 || (maxblocks > 0 && count % maxblocks == 0)) emit(false, ops);
+    }
+    blockcount++;
+}
+
+}  // namespace fdc

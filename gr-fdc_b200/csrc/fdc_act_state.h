@@ -1,0 +1,127 @@
+/* fdc_act_state.h -- host-side state of the activity-gated blocks (no CUDA here).
+ *
+ * The GPU does the arithmetic (power sums, ratio thresholds, window multiply + IFFT); what stays on the host is the
+ * small, strictly sequential bookkeeping the reference does per block: pairing rising/falling edges, matching
+ * candidates against the active-channel list, activation geometry, deactivation counters, PDU metadata.  All of it is
+ * integer work on a handful of channels per block and has to be reproduced exactly.
+ *
+ * Because extraction is batched (one kernel launch per work() call, not one FFT per block), the per-block pass does not
+ * touch sample data: it emits extraction JOBS and an ordered list of OPS (push the result of job j onto channel u's
+ * buffer / publish a message from the first n buffered blocks of channel u).  After the kernel has run the ops are
+ * replayed on the real data, which reproduces the reference's PDU sequence. */
+#ifndef FDC_ACT_STATE_H
+#define FDC_ACT_STATE_H
+#include <array>
+#include <complex>
+#include <deque>
+#include <string>
+#include <vector>
+
+namespace fdc {
+
+typedef std::complex<float> cfloat;
+
+struct ActJob {
+    int L;            /* extract width (IFFT length) */
+    int row;          /* spectrum row of this call, -1 = history block */
+    int start;        /* extract_start */
+    long tab_off;     /* offset (in complex items) of the phase-selected window in the block's table buffer */
+    int skip;         /* leading IFFT outputs dropped */
+    long uid;         /* channel instance the result belongs to */
+};
+struct MsgMeta {
+    std::string id;
+    bool finalized;
+    long part;                    /* -1: key absent */
+    double rel_cfreq, rel_bw;
+    long blockstart, blockend, vectorstart, vectorend;   /* vector*: -1 = key absent */
+    bool publish;                 /* message port connected (msg / messageoutput constructor flag) */
+    std::string filename;         /* non-empty: also write the payload there (raw cfp32) */
+    std::string logline;
+};
+struct ActOp {
+    enum Kind { PUSH, EMIT, DROP } kind;
+    long uid;
+    int job;                      /* PUSH: index into the call's job list */
+    int ntake;                    /* EMIT: number of buffered blocks to publish, -1 = all */
+    int blocksamples;             /* EMIT: samples per buffered block */
+    MsgMeta meta;
+};
+
+std::string current_time_string();            /* "%Y-%m-%d-%H-%M-%S" */
+
+/* ---- windows ---------------------------------------------------------------------------------- */
+/* lib/SegmentDetection_impl.cc:551-583 == lib/activity_detection_channelizer_vcm_impl.cc:199-228:
+ * for every width 2^s <= blocklen, relinvovl phase-rotated rectangles with raised-cosine flanks.
+ * Flat layout: offsets[s] + phase * 2^s. */
+void build_flank_windows(int blocklen, int relinvovl, double flank_puffer, std::vector<cfloat>& tab, std::vector<long>& offsets);
+/* lib/PowerActivationChannel_impl.cc:357-375: relinvovl vectors of length blocklen */
+void build_pac_windows(int blocklen, int relinvovl, int rampsamps, std::vector<cfloat>& tab);
+
+/* ---- one detection segment (SegmentDetection, or one `segment` of activity_detection_channelizer_vcm) ---- */
+struct ActiveChannel {
+    int ID, detect_start, detect_stop, extract_start, extract_stop, extract_width, extract_window, ovlskip, outputsamples;
+    int count, phase, phaseincrement, inactive, part;
+    std::string msg_ID;
+    long uid;
+    int ndata;                    /* number of buffered blocks (the reference's data.size()) */
+};
+struct EdgeBlock {                /* detection result of one block, ascending bin order */
+    std::vector<std::pair<float, int> > rise;    /* (ratio, power-bin index i) */
+    std::vector<int> fall;                       /* power-bin index i */
+};
+
+struct SegGeometry { long start, stop, width, D, M; };
+/* lib/SegmentDetection_impl.cc:592-637 (throws std::invalid_argument with the reference's text) */
+SegGeometry segdet_geometry(int blocklen, float start, float stop, float minchandist);
+/* lib/activity_detection_channelizer_vcm_impl.cc:230-279 */
+int actdet_decimation(int blocklen, float minchandist);
+SegGeometry actdet_geometry(int blocklen, float v0, float v1, int D);
+
+class SegmentState {
+public:
+    int seg_id;                   /* ID used in message ids */
+    int blocklen, relinvovl, maxblocks, delay;
+    double flank;
+    SegGeometry g;
+    bool emit_inside_loop;        /* activity_detection single-thread order (…vcm_impl.cc:306-337) vs SegmentDetection order */
+    std::deque<ActiveChannel> active;
+    long chan_counter;
+    const std::vector<long>* win_offsets;
+    std::string path; bool fileoutput; bool verbose; bool msg_output;
+
+    SegmentState() : seg_id(0), blocklen(0), relinvovl(1), maxblocks(-1), delay(0), flank(0.0), emit_inside_loop(false),
+                     chan_counter(0), win_offsets(0), fileoutput(false), verbose(false), msg_output(true) {}
+    /* detection + bookkeeping of one block; `blockcount` is the reference's counter value during this block */
+    void block(int row, const EdgeBlock& e, long blockcount, long& uid_counter, std::vector<ActJob>& jobs, std::vector<ActOp>& ops);
+private:
+    void candidates(const EdgeBlock& e, std::deque<std::array<long, 2> >& poss) const;
+    void match(std::deque<std::array<long, 2> >& poss, long& uid_counter);
+    bool activate(long detect_start, long detect_end, long& uid_counter);
+    void job(ActiveChannel& c, int row, std::vector<ActJob>& jobs, std::vector<ActOp>& ops);
+    void emit_final(ActiveChannel& c, long blockcount, std::vector<ActOp>& ops);
+    void emit_partial(ActiveChannel& c, long blockcount, std::vector<ActOp>& ops);
+    MsgMeta meta(const ActiveChannel& c, long blockcount, bool fin) const;
+};
+
+/* ---- PowerActivationChannel --------------------------------------------------------------------- */
+class PacState {
+public:
+    int blocklen, relinvovl, extract_start, extract_stop, extract_width, output_len, output_ovl_offset, measure_start,
+        measure_stop, maxblocks, deactivation_delay, rampsamps;
+    float thresh, lastpower;
+    bool active;
+    int count, phase, deltaphase, ID, part, finished_channels, blockcount;
+    std::string msgID, path; bool msg, fileoutput; int verbose;
+    long uid; int ndata;
+
+    /* constructor arguments of lib/PowerActivationChannel_impl.cc:42; throws std::invalid_argument like the reference */
+    void init(int v_blocklen, float cfreq, float bw, int v_relinvovl, float v_thresh, int v_maxblocks, int v_delay, int v_ID);
+    void block(int row, float pwr, long& uid_counter, std::vector<ActJob>& jobs, std::vector<ActOp>& ops);
+private:
+    void job(int row, std::vector<ActJob>& jobs, std::vector<ActOp>& ops);
+    void emit(bool fin, std::vector<ActOp>& ops);
+};
+
+}  // namespace fdc
+#endif

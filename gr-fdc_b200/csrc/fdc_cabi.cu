@@ -57,6 +57,30 @@ void* fdc_host_alloc(size_t bytes)
 }
 void fdc_host_free(void* p) { if (p) cudaFreeHost(p); }
 unsigned long long fdc_launch_count(void) { return launch_count(); }
+void* fdc_dev_alloc(size_t bytes)
+{
+    void* p = 0;
+    if (!require_device()) return 0;
+    const cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
+    if (e != cudaSuccess) { cuda_fail(e, "cudaMalloc"); return 0; }
+    return p;
+}
+void fdc_dev_free(void* p) { if (p) cudaFree(p); }
+int fdc_memcpy_h2d(void* dst, const void* src, size_t bytes)
+{
+    const cudaError_t e = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+    return e == cudaSuccess ? 0 : cuda_fail(e, "fdc_memcpy_h2d");
+}
+int fdc_memcpy_d2h(void* dst, const void* src, size_t bytes)
+{
+    const cudaError_t e = cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost);
+    return e == cudaSuccess ? 0 : cuda_fail(e, "fdc_memcpy_d2h");
+}
+int fdc_device_synchronize(void)
+{
+    const cudaError_t e = cudaDeviceSynchronize();
+    return e == cudaSuccess ? 0 : cuda_fail(e, "fdc_device_synchronize");
+}
 
 int fdc_opt_channelparams(int blocksize, int relinvovl, double freq, double bw, int* f, int* l, int* lout, double* passband,
                           double* stopband)

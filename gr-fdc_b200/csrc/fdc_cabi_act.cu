@@ -1,36 +1,555 @@
-/* fdc_cabi_act.cu -- activity-gated blocks (placeholder until the state machines land): every entry point fails loudly. */
+/* fdc_cabi_act.cu -- C ABI of the activity-gated blocks: PowerActivationChannel, SegmentDetection,
+ * activity_detection_channelizer_vcm.  Per work() call:
+ *   1. K3 on the whole call: power sums / ratio thresholds / compacted edge lists  (GPU)
+ *   2. per block, in order: the reference's bookkeeping on those few numbers -> extraction jobs + ordered ops (host)
+ *   3. K2 job kernel: window multiply, half swap, backward FFT, overlap discard for ALL jobs of the call (GPU)
+ *   4. replay of the ops on the extracted blocks -> PDUs / files in the reference's order (host) */
 #include "fdc_cabi_internal.h"
+#include "fdc_act_state.h"
+#include <algorithm>
+#include <cfloat>
+#include <cstdio>
+#include <cstring>
+#include <iostream>
+#include <map>
+
 using namespace fdc;
-#define NI(ret) { fail("not implemented yet"); return ret; }
-extern "C" {
-fdc_pac* fdc_pac_create(int, float, float, int, float, int, int, int, int, const char*, int, int) NI(0)
-int fdc_pac_work_host(fdc_pac*, int, const void*) NI(-1)
-int fdc_pac_work_device(fdc_pac*, int, const void*, void*) NI(-1)
-int fdc_pac_state(const fdc_pac*, int*, float*) NI(-1)
-int fdc_pac_tables(const fdc_pac*, float*) NI(-1)
-int fdc_pac_msg_count(const fdc_pac*) NI(-1)
-int fdc_pac_msg_get(const fdc_pac*, int, fdc_msg*) NI(-1)
-void fdc_pac_msg_clear(fdc_pac*) {}
-void fdc_pac_destroy(fdc_pac*) {}
-fdc_segdet* fdc_segdet_create(int, int, int, float, float, float, float, float, int, int, int, int, const char*, int, int) NI(0)
-int fdc_segdet_work_host(fdc_segdet*, int, const void*) NI(-1)
-int fdc_segdet_work_device(fdc_segdet*, int, const void*, void*) NI(-1)
-int fdc_segdet_state(const fdc_segdet*, long*, float*) NI(-1)
-int fdc_segdet_window(const fdc_segdet*, int, int, float*) NI(-1)
-int fdc_segdet_power(const fdc_segdet*, float*) NI(-1)
-int fdc_segdet_active(const fdc_segdet*, int, int*) NI(-1)
-int fdc_segdet_msg_count(const fdc_segdet*) NI(-1)
-int fdc_segdet_msg_get(const fdc_segdet*, int, fdc_msg*) NI(-1)
-void fdc_segdet_msg_clear(fdc_segdet*) {}
-void fdc_segdet_destroy(fdc_segdet*) {}
-fdc_actdet* fdc_actdet_create(int, const float*, int, float, int, int, int, int, const char*, int, float, int, double, int) NI(0)
-int fdc_actdet_work_host(fdc_actdet*, int, const void*) NI(-1)
-int fdc_actdet_work_device(fdc_actdet*, int, const void*, void*) NI(-1)
-int fdc_actdet_nsegments(const fdc_actdet*) NI(-1)
-int fdc_actdet_segment(const fdc_actdet*, int, int*) NI(-1)
-int fdc_actdet_power(const fdc_actdet*, int, float*) NI(-1)
-int fdc_actdet_msg_count(const fdc_actdet*) NI(-1)
-int fdc_actdet_msg_get(const fdc_actdet*, int, fdc_msg*) NI(-1)
-void fdc_actdet_msg_clear(fdc_actdet*) {}
-void fdc_actdet_destroy(fdc_actdet*) {}
+
+namespace {
+
+struct OutMsg { MsgMeta meta; std::vector<cfloat> data; long logic_samples; OutMsg() : logic_samples(-1) {} };
+
+static void log_line(int verbose, const std::string& logfile, std::string s)
+{
+    /* verbose 1 = console, 2 = file (append, one line per call) -- lib/SegmentDetection_impl.cc:659-672 */
+    if (verbose == 1) std::cout << s << std::endl;
+    else if (verbose == 2) {
+        FILE* f = fopen(logfile.c_str(), "a");
+        if (!f) std::cerr << "Outputfile not writable: " << logfile << std::endl;
+        else { s += "\n"; fwrite(s.c_str(), 1, s.size(), f); fclose(f); }
+    }
 }
+static void init_logfile(int verbose, const std::string& logfile)
+{
+    if (verbose != 2) return;
+    FILE* f = fopen(logfile.c_str(), "w");
+    if (!f) std::cerr << "Logfile not writable: " << logfile << std::endl;
+    else { fwrite("\n", 1, 1, f); fclose(f); }
+}
+
+/* device side shared by the three blocks */
+struct ActEngine {
+    int N; int verbose; std::string logfile;
+    cudaStream_t s;
+    DevBuf d_in, d_hist, d_tab, d_jobs, d_out, d_P, d_cnt, d_rr, d_ri, d_fi, d_pw;
+    PinBuf h_out, h_misc;
+    std::map<long, std::deque<std::vector<cfloat> > > pending;
+    std::vector<OutMsg> msgs;
+    long uid_counter;
+    bool logic_only;               /* host-logic hooks: no device, messages carry metadata and sample counts only */
+
+    ActEngine() : N(0), verbose(0), s(0), uid_counter(0), logic_only(false) {}
+    ~ActEngine() { if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); } }
+
+    bool init(int blocklen, const std::vector<cfloat>& tab)
+    {
+        N = blocklen;
+        if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return false;
+        if (!d_hist.reserve(sizeof(float2) * (size_t)N) || cudaMemset(d_hist.p, 0, sizeof(float2) * (size_t)N) != cudaSuccess) return false;
+        return d_tab.upload(tab.data(), sizeof(cfloat) * tab.size());
+    }
+
+    /* run all extraction jobs of a call and replay the ops */
+    int finish(const float2* d_rows, std::vector<ActJob>& jobs, const std::vector<ActOp>& ops, cudaStream_t st)
+    {
+        std::vector<long> dst(jobs.size(), 0);
+        if (logic_only) {
+            for (size_t i = 0; i < ops.size(); i++) {
+                const ActOp& o = ops[i];
+                if (o.kind == ActOp::PUSH) pending[o.uid].push_back(std::vector<cfloat>());
+                else if (o.kind == ActOp::DROP) pending.erase(o.uid);
+                else {
+                    std::deque<std::vector<cfloat> >& q = pending[o.uid];
+                    const size_t ntake = o.ntake < 0 ? q.size() : std::min((size_t)o.ntake, q.size());
+                    OutMsg m; m.meta = o.meta; m.logic_samples = (long)(ntake * (size_t)o.blocksamples);
+                    q.erase(q.begin(), q.begin() + ntake);
+                    if (m.meta.publish) msgs.push_back(m);
+                }
+            }
+            return 0;
+        }
+        if (!jobs.empty()) {
+            /* group by IFFT length, assign output offsets */
+            std::vector<int> order(jobs.size());
+            for (size_t i = 0; i < jobs.size(); i++) order[i] = (int)i;
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return jobs[a].L < jobs[b].L; });
+            std::vector<ExtractJob> ej(jobs.size());
+            long total = 0;
+            for (size_t k = 0; k < order.size(); k++) {
+                const ActJob& j = jobs[order[k]];
+                if (!tile_len_supported(j.L)) return fail("activity channel wider than 16384 bins is not supported by the extract kernel");
+                ej[k].row = j.row; ej[k].start = j.start; ej[k].tab_off = (int)j.tab_off; ej[k].skip = j.skip; ej[k].dst_off = total;
+                dst[order[k]] = total;
+                total += j.L - j.skip;
+            }
+            if (!d_jobs.upload(ej.data(), sizeof(ExtractJob) * ej.size()) || !d_out.reserve(sizeof(float2) * (size_t)total) ||
+                !h_out.reserve(sizeof(float2) * (size_t)total))
+                return cuda_fail(cudaGetLastError(), "activity extract buffers");
+            size_t k = 0;
+            while (k < order.size()) {
+                size_t e = k; const int L = jobs[order[k]].L;
+                while (e < order.size() && jobs[order[e]].L == L) e++;
+                JobParams p; p.spec = d_rows; p.spec_stride = N; p.hist = (const float2*)d_hist.p; p.tables = (const float2*)d_tab.p;
+                p.jobs = (const ExtractJob*)d_jobs.p + k; p.out = (float2*)d_out.p; p.njobs = (int)(e - k);
+                const cudaError_t ce = launch_jobs(p, L, st);
+                if (ce != cudaSuccess) return cuda_fail(ce, "activity extract launch");
+                k = e;
+            }
+            cudaError_t ce = cudaMemcpyAsync(h_out.p, d_out.p, sizeof(float2) * (size_t)total, cudaMemcpyDeviceToHost, st);
+            if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+            if (ce != cudaSuccess) return cuda_fail(ce, "activity extract D2H");
+        }
+        const cfloat* res = (const cfloat*)h_out.p;
+        for (size_t i = 0; i < ops.size(); i++) {
+            const ActOp& o = ops[i];
+            if (o.kind == ActOp::PUSH) {
+                const ActJob& j = jobs[o.job];
+                pending[o.uid].push_back(std::vector<cfloat>(res + dst[o.job], res + dst[o.job] + (j.L - j.skip)));
+            } else if (o.kind == ActOp::DROP) {
+                pending.erase(o.uid);
+            } else {
+                std::deque<std::vector<cfloat> >& q = pending[o.uid];
+                const size_t ntake = o.ntake < 0 ? q.size() : std::min((size_t)o.ntake, q.size());
+                OutMsg m; m.meta = o.meta;
+                m.data.reserve(ntake * (size_t)o.blocksamples);
+                for (size_t b = 0; b < ntake; b++) m.data.insert(m.data.end(), q[b].begin(), q[b].end());
+                q.erase(q.begin(), q.begin() + ntake);
+                if (!m.meta.filename.empty()) {
+                    FILE* fh = fopen(m.meta.filename.c_str(), "wb");
+                    if (!fh) std::cerr << "Cannot write to file " << m.meta.filename << std::endl;
+                    else { fwrite(m.data.data(), sizeof(cfloat), m.data.size(), fh); fclose(fh); }
+                }
+                if (!m.meta.logline.empty()) log_line(verbose, logfile, m.meta.logline);
+                if (m.meta.publish) msgs.push_back(m);
+            }
+        }
+        return 0;
+    }
+    int save_hist(const float2* d_rows, int n, cudaStream_t st)
+    {
+        cudaError_t e = cudaMemcpyAsync(d_hist.p, d_rows + (size_t)(n - 1) * N, sizeof(float2) * (size_t)N, cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        return e == cudaSuccess ? 0 : cuda_fail(e, "history save");
+    }
+    const float2* stage_host(const void* in, int n)
+    {
+        if (!d_in.reserve(sizeof(float2) * (size_t)n * N)) { cuda_fail(cudaGetLastError(), "input staging"); return 0; }
+        const cudaError_t e = cudaMemcpyAsync(d_in.p, in, sizeof(float2) * (size_t)n * N, cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) { cuda_fail(e, "H2D"); return 0; }
+        return (const float2*)d_in.p;
+    }
+    int msg_get(int i, fdc_msg* out) const
+    {
+        if (i < 0 || i >= (int)msgs.size() || !out) return fail("message index out of range");
+        const OutMsg& m = msgs[i];
+        memset(out, 0, sizeof(*out));
+        strncpy(out->id, m.meta.id.c_str(), sizeof(out->id) - 1);
+        out->finalized = m.meta.finalized ? 1 : 0; out->part = m.meta.part; out->rel_cfreq = m.meta.rel_cfreq; out->rel_bw = m.meta.rel_bw;
+        out->blockstart = m.meta.blockstart; out->blockend = m.meta.blockend; out->vectorstart = m.meta.vectorstart; out->vectorend = m.meta.vectorend;
+        out->nsamples = m.logic_samples >= 0 ? m.logic_samples : (long)m.data.size();
+        out->data = m.logic_samples >= 0 ? (const float*)0 : (const float*)m.data.data();
+        return 0;
+    }
+};
+
+/* detection front end of one segment for a whole call: K3 kernels + D2H of the compacted edge lists */
+struct SegDetect {
+    enum { CAP = 1024 };
+    std::vector<float> last_power;
+    int run(ActEngine& e, const float2* d_rows, int n, const SegGeometry& g, float T, int mean, int guard, std::vector<EdgeBlock>& out, cudaStream_t st)
+    {
+        const int M = (int)g.M;
+        out.assign((size_t)n, EdgeBlock());
+        last_power.assign((size_t)std::max(M, 0), 0.0f);
+        if (M <= 0) return 0;
+        const int cap = std::max(1, std::min(M - 1, (int)CAP));
+        if (!e.d_P.reserve(sizeof(float) * (size_t)n * M) || !e.d_cnt.reserve(sizeof(int) * 2 * (size_t)n) ||
+            !e.d_rr.reserve(sizeof(float) * (size_t)n * cap) || !e.d_ri.reserve(sizeof(int) * (size_t)n * cap) ||
+            !e.d_fi.reserve(sizeof(int) * (size_t)n * cap))
+            return cuda_fail(cudaGetLastError(), "detection buffers");
+        const size_t bytes = (size_t)n * (2 * sizeof(int) + (size_t)cap * 12) + sizeof(float) * (size_t)M;
+        if (!e.h_misc.reserve(bytes)) return cuda_fail(cudaGetLastError(), "detection host buffer");
+        cudaError_t ce = launch_group_power(d_rows, e.N, n, (int)g.start, (int)g.D, M, mean, (float*)e.d_P.p, st);
+        const float invT = 1.0f / T;
+        if (ce == cudaSuccess) ce = launch_edges((const float*)e.d_P.p, n, M, T, invT, guard, cap, (int*)e.d_cnt.p, (float*)e.d_rr.p, (int*)e.d_ri.p, (int*)e.d_fi.p, st);
+        char* h = (char*)e.h_misc.p;
+        int* h_cnt = (int*)h; float* h_rr = (float*)(h_cnt + 2 * (size_t)n); int* h_ri = (int*)(h_rr + (size_t)n * cap); int* h_fi = h_ri + (size_t)n * cap;
+        float* h_last = (float*)(h_fi + (size_t)n * cap);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(h_cnt, e.d_cnt.p, sizeof(int) * 2 * (size_t)n, cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(h_rr, e.d_rr.p, sizeof(float) * (size_t)n * cap, cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(h_ri, e.d_ri.p, sizeof(int) * (size_t)n * cap, cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(h_fi, e.d_fi.p, sizeof(int) * (size_t)n * cap, cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(h_last, (const float*)e.d_P.p + (size_t)(n - 1) * M, sizeof(float) * (size_t)M, cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+        if (ce != cudaSuccess) return cuda_fail(ce, "detection kernels");
+        memcpy(last_power.data(), h_last, sizeof(float) * (size_t)M);
+        std::vector<float> row;
+        for (int b = 0; b < n; b++) {
+            const int nr = h_cnt[2 * b], nf = h_cnt[2 * b + 1];
+            EdgeBlock& eb = out[(size_t)b];
+            if (nr <= cap && nf <= cap) {
+                for (int k = 0; k < nr; k++) eb.rise.push_back(std::make_pair(h_rr[(size_t)b * cap + k], h_ri[(size_t)b * cap + k]));
+                eb.fall.assign(h_fi + (size_t)b * cap, h_fi + (size_t)b * cap + nf);
+            } else {
+                /* more edges than the compact lists hold (dense noise-only detections): classify this block from its power row,
+                 * same IEEE divisions and comparisons as the kernel */
+                row.resize((size_t)M);
+                ce = cudaMemcpy(row.data(), (const float*)e.d_P.p + (size_t)b * M, sizeof(float) * (size_t)M, cudaMemcpyDeviceToHost);
+                if (ce != cudaSuccess) return cuda_fail(ce, "power row D2H");
+                for (int i = 0; i + 1 < M; i++) {
+                    float den = row[(size_t)i];
+                    if (guard && den == 0.0f) den = FLT_MIN;
+                    const float r = row[(size_t)i + 1] / den;
+                    if (r > T) eb.rise.push_back(std::make_pair(r, i));
+                    else if (r < invT) eb.fall.push_back(i);
+                }
+            }
+        }
+        return 0;
+    }
+};
+
+}  // namespace
+
+/* ================================================================================================ PAC */
+struct fdc_pac { ActEngine e; PacState st; std::vector<cfloat> tab; };
+
+extern "C" {
+
+static fdc_pac* pac_build(bool logic_only, int blocklen, float cfreq, float bw, int relinvovl, float thresh, int maxblocks,
+                          int deactivation_delay, int msg, int fileoutput, const char* path, int verbose, int ID)
+{
+    fdc_pac* b = new fdc_pac;
+    b->e.logic_only = logic_only;
+    try {
+        b->e.verbose = (verbose == 1 || verbose == 2) ? verbose : 0;
+        b->e.logfile = std::string("gr-FDC.PowActChan.") + std::to_string(ID) + std::string(".log");
+        init_logfile(b->e.verbose, b->e.logfile);
+        b->st.init(blocklen, cfreq, bw, relinvovl, thresh, maxblocks, deactivation_delay, ID);
+        b->st.msg = msg != 0; b->st.fileoutput = fileoutput != 0; b->st.path = path ? path : ""; b->st.verbose = b->e.verbose;
+        build_pac_windows(blocklen, relinvovl, b->st.rampsamps, b->tab);
+        if (logic_only) { b->e.N = blocklen; return b; }
+        if (b->st.extract_width > 16384) throw std::invalid_argument("PowerActivationChannel: channels wider than 16384 bins are not supported by the extract kernel");
+        if (!require_device()) throw std::runtime_error(fdc_last_error());
+        if (!b->e.init(blocklen, b->tab)) throw std::runtime_error(std::string("PowerActivationChannel: ") + cudaGetErrorString(cudaGetLastError()));
+        twiddle_table(b->st.extract_width);
+        return b;
+    } catch (const std::exception& ex) { const std::string w = ex.what(); fail(w); delete b; return 0; }
+}
+fdc_pac* fdc_pac_create(int blocklen, float cfreq, float bw, int relinvovl, float thresh, int maxblocks, int deactivation_delay,
+                        int msg, int fileoutput, const char* path, int verbose, int ID)
+{ return pac_build(false, blocklen, cfreq, bw, relinvovl, thresh, maxblocks, deactivation_delay, msg, fileoutput, path, verbose, ID); }
+fdc_pac* fdc_pac_create_logic(int blocklen, float cfreq, float bw, int relinvovl, float thresh, int maxblocks, int deactivation_delay,
+                              int msg, int fileoutput, const char* path, int verbose, int ID)
+{ return pac_build(true, blocklen, cfreq, bw, relinvovl, thresh, maxblocks, deactivation_delay, msg, fileoutput, path, verbose, ID); }
+int fdc_pac_logic_work(fdc_pac* b, int n, const float* pwr)
+{
+    if (!b || !b->e.logic_only || n < 0) return fail("fdc_pac_logic_work: needs a context from fdc_pac_create_logic");
+    std::vector<ActJob> jobs; std::vector<ActOp> ops;
+    for (int i = 0; i < n; i++) b->st.block(i, pwr[i], b->e.uid_counter, jobs, ops);
+    return b->e.finish(0, jobs, ops, 0) ? -1 : n;
+}
+int fdc_pac_work_device(fdc_pac* b, int n, const void* d_in, void* stream)
+{
+    if (!b || n < 0 || b->e.logic_only) return fail("PowerActivationChannel work: bad arguments");
+    if (n == 0) return 0;
+    cudaStream_t st = stream ? (cudaStream_t)stream : b->e.s;
+    const float2* rows = (const float2*)d_in;
+    if (!b->e.d_pw.reserve(sizeof(float) * (size_t)n) || !b->e.h_misc.reserve(sizeof(float) * (size_t)n)) return cuda_fail(cudaGetLastError(), "power buffers");
+    cudaError_t ce = launch_band_power(rows, b->e.N, n, b->st.measure_start, b->st.measure_stop, (float*)b->e.d_pw.p, st);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(b->e.h_misc.p, b->e.d_pw.p, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    if (ce != cudaSuccess) return cuda_fail(ce, "band power");
+    const float* pw = (const float*)b->e.h_misc.p;
+    std::vector<ActJob> jobs; std::vector<ActOp> ops;
+    for (int i = 0; i < n; i++) b->st.block(i, pw[i], b->e.uid_counter, jobs, ops);
+    if (b->e.finish(rows, jobs, ops, st)) return -1;
+    if (b->e.save_hist(rows, n, st)) return -1;
+    return n;
+}
+int fdc_pac_work_host(fdc_pac* b, int n, const void* in)
+{
+    if (!b || n < 0 || b->e.logic_only) return fail("PowerActivationChannel work: bad arguments");
+    if (n == 0) return 0;
+    const float2* rows = b->e.stage_host(in, n);
+    return rows ? fdc_pac_work_device(b, n, rows, 0) : -1;
+}
+int fdc_pac_state(const fdc_pac* b, int* geo, float* f)
+{
+    if (!b) return fail("null block");
+    const PacState& p = b->st;
+    const int g[12] = {p.extract_start, p.extract_stop, p.extract_width, p.measure_start, p.measure_stop, p.deltaphase, p.output_len,
+                       p.output_ovl_offset, p.active ? 1 : 0, p.count, p.phase, p.blockcount};
+    memcpy(geo, g, sizeof(g)); f[0] = p.thresh; f[1] = p.lastpower;
+    return 0;
+}
+int fdc_pac_tables(const fdc_pac* b, float* out)
+{
+    if (!b) return fail("null block");
+    memcpy(out, b->tab.data(), sizeof(cfloat) * b->tab.size()); return 0;
+}
+int fdc_pac_msg_count(const fdc_pac* b) { return b ? (int)b->e.msgs.size() : -1; }
+int fdc_pac_msg_get(const fdc_pac* b, int i, fdc_msg* out) { return b ? b->e.msg_get(i, out) : fail("null block"); }
+void fdc_pac_msg_clear(fdc_pac* b) { if (b) b->e.msgs.clear(); }
+void fdc_pac_destroy(fdc_pac* b) { delete b; }
+
+}  // extern "C"
+
+/* ================================================================================================ SegmentDetection */
+struct fdc_segdet { ActEngine e; SegmentState st; SegDetect det; std::vector<cfloat> tab; std::vector<long> offs; float thresh; long blockcount; };
+
+extern "C" {
+
+static fdc_segdet* segdet_build(bool logic_only, int ID, int blocklen, int relinvovl, float seg_start, float seg_stop, float thresh,
+                                float minchandist, float window_flank_puffer, int maxblocks_to_emit, int channel_deactivation_delay,
+                                int messageoutput, int fileoutput, const char* path, int threads, int verbose)
+{
+    (void)threads;     /* the reference's std::thread-per-carrier mode changes scheduling only; all carriers of a call share one launch here */
+    fdc_segdet* b = new fdc_segdet;
+    b->e.logic_only = logic_only;
+    try {
+        b->e.verbose = verbose == 2 ? 2 : (verbose == 1 ? 1 : 0);
+        b->e.logfile = std::string("gr-FDC.ActDetChan.ID_") + std::to_string(ID) + std::string(".log");
+        init_logfile(b->e.verbose, b->e.logfile);
+        /* validation order and texts of lib/SegmentDetection_impl.cc:66-86 */
+        if (blocklen < 1 || (blocklen & (blocklen - 1))) throw std::invalid_argument("Blocklen must be Power of 2. ");
+        if (relinvovl < 1 || (relinvovl & (relinvovl - 1))) throw std::invalid_argument("Relinvovl must be Power of 2. ");
+        if (thresh < 0.0f) throw std::invalid_argument("Threshold is interpreted as dB and must be greater zero to detect channels accordingly. ");
+        b->thresh = db_to_ratio(thresh);
+        if (window_flank_puffer < 0.0) throw std::invalid_argument("Window flank puffer must not be smaller 0.0. \n");
+        SegmentState& s = b->st;
+        s.seg_id = ID; s.blocklen = blocklen; s.relinvovl = relinvovl; s.maxblocks = maxblocks_to_emit; s.delay = channel_deactivation_delay;
+        s.flank = (double)window_flank_puffer;
+        s.g = segdet_geometry(blocklen, seg_start, seg_stop, minchandist);
+        s.emit_inside_loop = false; s.msg_output = messageoutput != 0; s.fileoutput = fileoutput != 0; s.path = path ? path : ""; s.verbose = b->e.verbose != 0;
+        build_flank_windows(blocklen, relinvovl, s.flank, b->tab, b->offs);
+        s.win_offsets = &b->offs;
+        b->blockcount = 0;
+        if (logic_only) { b->e.N = blocklen; return b; }
+        if (!require_device()) throw std::runtime_error(fdc_last_error());
+        if (!b->e.init(blocklen, b->tab)) throw std::runtime_error(std::string("SegmentDetection: ") + cudaGetErrorString(cudaGetLastError()));
+        return b;
+    } catch (const std::exception& ex) { const std::string w = ex.what(); fail(w); delete b; return 0; }
+}
+fdc_segdet* fdc_segdet_create(int ID, int blocklen, int relinvovl, float seg_start, float seg_stop, float thresh, float minchandist,
+                              float window_flank_puffer, int maxblocks_to_emit, int channel_deactivation_delay, int messageoutput,
+                              int fileoutput, const char* path, int threads, int verbose)
+{ return segdet_build(false, ID, blocklen, relinvovl, seg_start, seg_stop, thresh, minchandist, window_flank_puffer, maxblocks_to_emit,
+                      channel_deactivation_delay, messageoutput, fileoutput, path, threads, verbose); }
+fdc_segdet* fdc_segdet_create_logic(int ID, int blocklen, int relinvovl, float seg_start, float seg_stop, float thresh, float minchandist,
+                                    float window_flank_puffer, int maxblocks_to_emit, int channel_deactivation_delay, int messageoutput,
+                                    int fileoutput, const char* path, int threads, int verbose)
+{ return segdet_build(true, ID, blocklen, relinvovl, seg_start, seg_stop, thresh, minchandist, window_flank_puffer, maxblocks_to_emit,
+                      channel_deactivation_delay, messageoutput, fileoutput, path, threads, verbose); }
+/* host classification of decimated power rows: the same IEEE divisions and comparisons as k_edges */
+static void classify_rows(const float* P, int n, int M, float T, int guard, std::vector<EdgeBlock>& out)
+{
+    const float invT = 1.0f / T;
+    out.assign((size_t)n, EdgeBlock());
+    for (int b = 0; b < n; b++)
+        for (int i = 0; i + 1 < M; i++) {
+            float den = P[(size_t)b * M + i];
+            if (guard && den == 0.0f) den = FLT_MIN;
+            const float r = P[(size_t)b * M + i + 1] / den;
+            if (r > T) out[(size_t)b].rise.push_back(std::make_pair(r, i));
+            else if (r < invT) out[(size_t)b].fall.push_back(i);
+        }
+}
+int fdc_segdet_logic_work(fdc_segdet* b, int n, const float* P)
+{
+    if (!b || !b->e.logic_only || n < 0) return fail("fdc_segdet_logic_work: needs a context from fdc_segdet_create_logic");
+    std::vector<EdgeBlock> edges;
+    classify_rows(P, n, (int)b->st.g.M, b->thresh, 0, edges);
+    std::vector<ActJob> jobs; std::vector<ActOp> ops;
+    for (int i = 0; i < n; i++) { b->st.block(i, edges[(size_t)i], b->blockcount, b->e.uid_counter, jobs, ops); b->blockcount++; }
+    if (n > 0) b->det.last_power.assign(P + (size_t)(n - 1) * b->st.g.M, P + (size_t)n * b->st.g.M);
+    return b->e.finish(0, jobs, ops, 0) ? -1 : n;
+}
+int fdc_segdet_work_device(fdc_segdet* b, int n, const void* d_in, void* stream)
+{
+    if (!b || n < 0 || b->e.logic_only) return fail("SegmentDetection work: bad arguments");
+    if (n == 0) return 0;
+    cudaStream_t st = stream ? (cudaStream_t)stream : b->e.s;
+    const float2* rows = (const float2*)d_in;
+    std::vector<EdgeBlock> edges;
+    if (b->det.run(b->e, rows, n, b->st.g, b->thresh, 0, 0, edges, st)) return -1;
+    std::vector<ActJob> jobs; std::vector<ActOp> ops;
+    for (int i = 0; i < n; i++) { b->st.block(i, edges[(size_t)i], b->blockcount, b->e.uid_counter, jobs, ops); b->blockcount++; }
+    if (b->e.finish(rows, jobs, ops, st)) return -1;
+    if (b->e.save_hist(rows, n, st)) return -1;
+    return n;
+}
+int fdc_segdet_work_host(fdc_segdet* b, int n, const void* in)
+{
+    if (!b || n < 0 || b->e.logic_only) return fail("SegmentDetection work: bad arguments");
+    if (n == 0) return 0;
+    const float2* rows = b->e.stage_host(in, n);
+    return rows ? fdc_segdet_work_device(b, n, rows, 0) : -1;
+}
+int fdc_segdet_state(const fdc_segdet* b, long* geo, float* f)
+{
+    if (!b) return fail("null block");
+    const SegmentState& s = b->st;
+    geo[0] = s.g.start; geo[1] = s.g.stop; geo[2] = s.g.width; geo[3] = s.g.D; geo[4] = s.g.M; geo[5] = b->blockcount;
+    geo[6] = (long)s.active.size(); geo[7] = s.chan_counter; f[0] = b->thresh;
+    return 0;
+}
+int fdc_segdet_window(const fdc_segdet* b, int log2w, int phase, float* out)
+{
+    if (!b || log2w < 0 || log2w + 1 >= (int)b->offs.size() || phase < 0 || phase >= b->st.relinvovl) return fail("no such window");
+    memcpy(out, b->tab.data() + b->offs[(size_t)log2w] + ((long)phase << log2w), sizeof(cfloat) << log2w);
+    return 0;
+}
+int fdc_segdet_power(const fdc_segdet* b, float* out)
+{
+    if (!b) return fail("null block");
+    memcpy(out, b->det.last_power.data(), sizeof(float) * b->det.last_power.size()); return 0;
+}
+int fdc_segdet_active(const fdc_segdet* b, int i, int* out)
+{
+    if (!b || i < 0 || i >= (int)b->st.active.size()) return fail("active channel index out of range");
+    const ActiveChannel& c = b->st.active[(size_t)i];
+    const int v[14] = {c.ID, c.detect_start, c.detect_stop, c.extract_start, c.extract_stop, c.extract_width, c.ovlskip, c.outputsamples, c.count,
+                       c.phase, c.phaseincrement, c.inactive, c.part, c.ndata};
+    memcpy(out, v, sizeof(v)); return 0;
+}
+int fdc_segdet_msg_count(const fdc_segdet* b) { return b ? (int)b->e.msgs.size() : -1; }
+int fdc_segdet_msg_get(const fdc_segdet* b, int i, fdc_msg* out) { return b ? b->e.msg_get(i, out) : fail("null block"); }
+void fdc_segdet_msg_clear(fdc_segdet* b) { if (b) b->e.msgs.clear(); }
+void fdc_segdet_destroy(fdc_segdet* b) { delete b; }
+
+}  // extern "C"
+
+/* ================================================================================================ activity_detection_channelizer_vcm */
+struct fdc_actdet {
+    ActEngine e; std::vector<SegmentState> segs; std::vector<SegDetect> det; std::vector<cfloat> tab; std::vector<long> offs;
+    float thresh; long blockcount;
+};
+
+extern "C" {
+
+static fdc_actdet* actdet_build(bool logic_only, int blocklen, const float* segments, int nsegs, float thresh, int relinvovl, int maxblocks,
+                                int message, int fileoutput, const char* path, int threads, float minchandist,
+                                int channel_deactivation_delay, double window_flank_puffer, int verbose)
+{
+    fdc_actdet* b = new fdc_actdet;
+    b->e.logic_only = logic_only;
+    try {
+        b->e.verbose = (verbose == 1 || verbose == 2) ? verbose : 0;
+        b->e.logfile = "gr-FDC.ActDetChan.log";
+        init_logfile(b->e.verbose, b->e.logfile);
+        /* validation order and texts of lib/activity_detection_channelizer_vcm_impl.cc:104-140 */
+        if (blocklen < 2 || (blocklen & (blocklen - 1))) throw std::invalid_argument("Blocklen invalid. ");
+        const int D = actdet_decimation(blocklen, minchandist);
+        if (thresh < 0.0f) throw std::invalid_argument("Threshold is interpreted as dB and must be greater zero. ");
+        b->thresh = db_to_ratio(thresh);
+        if (relinvovl < 1 || (relinvovl & (relinvovl - 1))) throw std::invalid_argument("Relative inverse overlap is invalid, must be >0 and a power of 2. ");
+        if (channel_deactivation_delay < 0) throw std::invalid_argument("Channel deactication delay must not be smaller 0. \n");
+        if (window_flank_puffer < 0.0) throw std::invalid_argument("Window flank puffer must not be smaller 0.0. \n");
+        if (nsegs < 0 || (nsegs > 0 && !segments)) throw std::invalid_argument("Segment is incorrect. ");
+        build_flank_windows(blocklen, relinvovl, window_flank_puffer, b->tab, b->offs);
+        b->segs.resize((size_t)nsegs); b->det.resize((size_t)nsegs);
+        for (int i = 0; i < nsegs; i++) {
+            SegmentState& s = b->segs[(size_t)i];
+            s.seg_id = i; s.blocklen = blocklen; s.relinvovl = relinvovl; s.maxblocks = maxblocks; s.delay = channel_deactivation_delay;
+            s.flank = window_flank_puffer;
+            s.g = actdet_geometry(blocklen, segments[2 * i], segments[2 * i + 1], D);
+            s.emit_inside_loop = threads == 0;          /* single-thread order, …vcm_impl.cc:306-337; threaded mode emits parts after all carriers */
+            s.msg_output = message != 0; s.fileoutput = fileoutput != 0; s.path = path ? path : ""; s.verbose = b->e.verbose != 0;
+            s.win_offsets = &b->offs;
+        }
+        b->blockcount = 1;
+        if (logic_only) { b->e.N = blocklen; return b; }
+        if (!require_device()) throw std::runtime_error(fdc_last_error());
+        if (!b->e.init(blocklen, b->tab)) throw std::runtime_error(std::string("activity_detection_channelizer_vcm: ") + cudaGetErrorString(cudaGetLastError()));
+        return b;
+    } catch (const std::exception& ex) { const std::string w = ex.what(); fail(w); delete b; return 0; }
+}
+fdc_actdet* fdc_actdet_create(int blocklen, const float* segments, int nsegs, float thresh, int relinvovl, int maxblocks, int message,
+                              int fileoutput, const char* path, int threads, float minchandist, int channel_deactivation_delay,
+                              double window_flank_puffer, int verbose)
+{ return actdet_build(false, blocklen, segments, nsegs, thresh, relinvovl, maxblocks, message, fileoutput, path, threads, minchandist,
+                      channel_deactivation_delay, window_flank_puffer, verbose); }
+fdc_actdet* fdc_actdet_create_logic(int blocklen, const float* segments, int nsegs, float thresh, int relinvovl, int maxblocks, int message,
+                                    int fileoutput, const char* path, int threads, float minchandist, int channel_deactivation_delay,
+                                    double window_flank_puffer, int verbose)
+{ return actdet_build(true, blocklen, segments, nsegs, thresh, relinvovl, maxblocks, message, fileoutput, path, threads, minchandist,
+                      channel_deactivation_delay, window_flank_puffer, verbose); }
+/* P: for every block the decimated (mean) power rows of all segments, concatenated in segment order */
+int fdc_actdet_logic_work(fdc_actdet* b, int n, const float* P)
+{
+    if (!b || !b->e.logic_only || n < 0) return fail("fdc_actdet_logic_work: needs a context from fdc_actdet_create_logic");
+    long rowlen = 0;
+    for (size_t s = 0; s < b->segs.size(); s++) rowlen += b->segs[s].g.M;
+    std::vector<ActJob> jobs; std::vector<ActOp> ops;
+    std::vector<EdgeBlock> eb;
+    for (int i = 0; i < n; i++) {
+        long off = 0;
+        for (size_t s = 0; s < b->segs.size(); s++) {
+            const int M = (int)b->segs[s].g.M;
+            classify_rows(P + (size_t)i * rowlen + off, 1, M, b->thresh, 1, eb);
+            b->segs[s].block(i, eb[0], b->blockcount, b->e.uid_counter, jobs, ops);
+            b->det[s].last_power.assign(P + (size_t)i * rowlen + off, P + (size_t)i * rowlen + off + M);
+            off += M;
+        }
+        b->blockcount++;
+    }
+    return b->e.finish(0, jobs, ops, 0) ? -1 : n;
+}
+int fdc_actdet_work_device(fdc_actdet* b, int n, const void* d_in, void* stream)
+{
+    if (!b || n < 0 || b->e.logic_only) return fail("activity_detection_channelizer_vcm work: bad arguments");
+    if (n == 0) return 0;
+    cudaStream_t st = stream ? (cudaStream_t)stream : b->e.s;
+    const float2* rows = (const float2*)d_in;
+    std::vector<std::vector<EdgeBlock> > edges(b->segs.size());
+    for (size_t s = 0; s < b->segs.size(); s++)
+        if (b->det[s].run(b->e, rows, n, b->segs[s].g, b->thresh, 1, 1, edges[s], st)) return -1;
+    std::vector<ActJob> jobs; std::vector<ActOp> ops;
+    for (int i = 0; i < n; i++) {
+        /* detection in every segment first, then extraction segment by segment (work(), …vcm_impl.cc:553-566); both orders coincide
+         * because a segment's detection only touches its own channel list */
+        for (size_t s = 0; s < b->segs.size(); s++) b->segs[s].block(i, edges[s][(size_t)i], b->blockcount, b->e.uid_counter, jobs, ops);
+        b->blockcount++;
+    }
+    if (b->e.finish(rows, jobs, ops, st)) return -1;
+    if (b->e.save_hist(rows, n, st)) return -1;
+    return n;
+}
+int fdc_actdet_work_host(fdc_actdet* b, int n, const void* in)
+{
+    if (!b || n < 0 || b->e.logic_only) return fail("activity_detection_channelizer_vcm work: bad arguments");
+    if (n == 0) return 0;
+    const float2* rows = b->e.stage_host(in, n);
+    return rows ? fdc_actdet_work_device(b, n, rows, 0) : -1;
+}
+int fdc_actdet_nsegments(const fdc_actdet* b) { return b ? (int)b->segs.size() : -1; }
+int fdc_actdet_segment(const fdc_actdet* b, int i, int* out)
+{
+    if (!b || i < 0 || i >= (int)b->segs.size()) return fail("segment index out of range");
+    const SegmentState& s = b->segs[(size_t)i];
+    out[0] = s.seg_id; out[1] = (int)s.g.start; out[2] = (int)s.g.stop; out[3] = (int)s.g.width; out[4] = (int)s.g.D; out[5] = (int)s.g.M;
+    out[6] = (int)s.active.size();
+    return 0;
+}
+int fdc_actdet_power(const fdc_actdet* b, int seg, float* out)
+{
+    if (!b || seg < 0 || seg >= (int)b->segs.size()) return fail("segment index out of range");
+    memcpy(out, b->det[(size_t)seg].last_power.data(), sizeof(float) * b->det[(size_t)seg].last_power.size()); return 0;
+}
+int fdc_actdet_msg_count(const fdc_actdet* b) { return b ? (int)b->e.msgs.size() : -1; }
+int fdc_actdet_msg_get(const fdc_actdet* b, int i, fdc_msg* out) { return b ? b->e.msg_get(i, out) : fail("null block"); }
+void fdc_actdet_msg_clear(fdc_actdet* b) { if (b) b->e.msgs.clear(); }
+void fdc_actdet_destroy(fdc_actdet* b) { delete b; }
+
+}  // extern "C"

@@ -37,6 +37,11 @@ SIGNATURES = {
     "fdc_host_alloc": (_vp, [C.c_size_t]),
     "fdc_host_free": (None, [_vp]),
     "fdc_launch_count": (C.c_ulonglong, []),
+    "fdc_dev_alloc": (_vp, [C.c_size_t]),
+    "fdc_dev_free": (None, [_vp]),
+    "fdc_memcpy_h2d": (_i, [_vp, _vp, C.c_size_t]),
+    "fdc_memcpy_d2h": (_i, [_vp, _vp, C.c_size_t]),
+    "fdc_device_synchronize": (_i, []),
     "fdc_opt_channelparams": (_i, [_i, _i, _d, _d, _ip, _ip, _ip, _dp, _dp]),
     "fdc_psw_build_tables": (_i, [_i, _i, _f, _f, _i, _vp]),
     "fdc_chan_create": (_vp, [_i, _i, _i, _i, _vp]),
@@ -97,6 +102,12 @@ SIGNATURES = {
     "fdc_actdet_msg_get": (_i, [_vp, _i, _vp]),
     "fdc_actdet_msg_clear": (None, [_vp]),
     "fdc_actdet_destroy": (None, [_vp]),
+    "fdc_pac_create_logic": (_vp, [_i, _f, _f, _i, _f, _i, _i, _i, _i, _cp, _i, _i]),
+    "fdc_pac_logic_work": (_i, [_vp, _i, _vp]),
+    "fdc_segdet_create_logic": (_vp, [_i, _i, _i, _f, _f, _f, _f, _f, _i, _i, _i, _i, _cp, _i, _i]),
+    "fdc_segdet_logic_work": (_i, [_vp, _i, _vp]),
+    "fdc_actdet_create_logic": (_vp, [_i, _vp, _i, _f, _i, _i, _i, _i, _cp, _i, _f, _i, _d, _i]),
+    "fdc_actdet_logic_work": (_i, [_vp, _i, _vp]),
 }
 
 

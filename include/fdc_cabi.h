@@ -38,6 +38,13 @@ int fdc_device_count(void);                        /* number of CUDA devices, <=
 int fdc_set_device(int device);                    /* device used by contexts created afterwards on this thread */
 void* fdc_host_alloc(size_t bytes);                /* pinned host memory for the *_host entry points */
 void fdc_host_free(void* p);
+/* plain device memory + blocking copies, so that a host language without a CUDA binding can keep a call's
+ * spectrum on the GPU between fdc_chan_work_device and the activity-gated blocks' *_work_device */
+void* fdc_dev_alloc(size_t bytes);
+void fdc_dev_free(void* p);
+int fdc_memcpy_h2d(void* dst_device, const void* src_host, size_t bytes);
+int fdc_memcpy_d2h(void* dst_host, const void* src_device, size_t bytes);
+int fdc_device_synchronize(void);
 /* number of kernel launches this library has enqueued so far (all contexts, this process) */
 unsigned long long fdc_launch_count(void);
 
@@ -192,6 +199,26 @@ int fdc_actdet_msg_count(const fdc_actdet* b);
 int fdc_actdet_msg_get(const fdc_actdet* b, int i, fdc_msg* out);
 void fdc_actdet_msg_clear(fdc_actdet* b);
 void fdc_actdet_destroy(fdc_actdet* b);
+
+/* ---- host-logic hooks -------------------------------------------------------------------------
+ * Contexts made by *_create_logic run ONLY the host-side bookkeeping of the activity-gated blocks (argument checks,
+ * geometry, window tables, edge pairing, channel matching, PDU metadata) and need no CUDA device.  They exist so that the
+ * CPU test-suite can compare that logic with the reference; *_work_host / *_work_device refuse them, and the messages they
+ * produce carry metadata and sample counts but no samples (data == NULL).  Input is what K3 would have measured:
+ * one band power per block (PowerActivationChannel) or the decimated power rows (M floats per block and segment). */
+fdc_pac* fdc_pac_create_logic(int blocklen, float cfreq, float bw, int relinvovl, float thresh, int maxblocks,
+                              int deactivation_delay, int msg, int fileoutput, const char* path, int verbose, int ID);
+int fdc_pac_logic_work(fdc_pac* b, int nblocks, const float* band_power);
+fdc_segdet* fdc_segdet_create_logic(int ID, int blocklen, int relinvovl, float seg_start, float seg_stop, float thresh,
+                                    float minchandist, float window_flank_puffer, int maxblocks_to_emit,
+                                    int channel_deactivation_delay, int messageoutput, int fileoutput, const char* path,
+                                    int threads, int verbose);
+int fdc_segdet_logic_work(fdc_segdet* b, int nblocks, const float* power_rows);
+fdc_actdet* fdc_actdet_create_logic(int blocklen, const float* segments, int nsegs, float thresh, int relinvovl,
+                                    int maxblocks, int message, int fileoutput, const char* path, int threads,
+                                    float minchandist, int channel_deactivation_delay, double window_flank_puffer,
+                                    int verbose);
+int fdc_actdet_logic_work(fdc_actdet* b, int nblocks, const float* power_rows);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop
