@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstring>
 #include <map>
+#include <string>
 
 using namespace fdc;
 
@@ -110,13 +111,19 @@ struct fdc_chan {
     bool big; int N1, N2;
     std::vector<ChanDev> chans;
     std::vector<int> l;
-    std::vector<std::pair<int, std::pair<int, int> > > groups;    /* (l, (first index in sel, count)) */
+    std::vector<std::pair<int, std::pair<int, int> > > groups;    /* (l, (first index in d_chans, count)) */
     long lout_total;
     long blockcount;
     long chunk_blocks;                 /* blocks per K1->K2 round trip: spectrum ring sized to stay in L2 */
-    DevBuf d_chans, d_sel, d_tables, d_hist, d_hist2, d_spec, d_mid;
-    const float2 *twlo, *twhi; int tws_log2;
+    DevBuf d_chans, d_tables, d_hist, d_hist2, d_stage;
+    const float2* tw4;                 /* four-step twiddles (big N) */
     cudaStream_t stream;
+    /* device path: chunks alternate between NWORK worker streams, each with its own spectrum / intermediate ring, so
+     * that the tail of one chunk's kernels overlaps the head of the next chunk's */
+    enum { NWORK = 2 };
+    cudaStream_t ws[NWORK];
+    DevBuf w_spec[NWORK], w_mid[NWORK];
+    cudaEvent_t ev_start, ev_done[NWORK];
     /* host path: NSLOT pipelined chunk slots */
     enum { NSLOT = 3 };
     cudaStream_t hs[NSLOT];
@@ -126,7 +133,11 @@ struct fdc_chan {
     bool prof;
     std::vector<cudaEvent_t> prof_ev;      /* triples: before K1, after K1, after K2 */
     std::vector<cudaEvent_t> prof_pool;
-    fdc_chan() : stream(0), host_chunk(0), prof(false) { for (int i = 0; i < NSLOT; i++) hs[i] = 0; }
+    fdc_chan() : tw4(0), stream(0), ev_start(0), host_chunk(0), prof(false)
+    {
+        for (int i = 0; i < NSLOT; i++) hs[i] = 0;
+        for (int i = 0; i < NWORK; i++) { ws[i] = 0; ev_done[i] = 0; }
+    }
     cudaEvent_t ev()
     {
         cudaEvent_t e = 0;
@@ -139,26 +150,26 @@ struct fdc_chan {
 
 static long pick_chunk_blocks(int N)
 {
-    /* spectrum ring of about 32 MiB: with the (equally large) four-step intermediate it stays well inside the
-     * 126 MB L2, so the K1 -> K2 hand-over does not touch HBM; never fewer than one wave of CTAs. */
+    /* spectrum ring of about 32 MiB per worker stream: with the (equally large) four-step intermediate the
+     * K1 -> K2 hand-over mostly stays inside the 126 MB L2; never fewer than one wave of CTAs. */
     long c = (32L << 20) / ((long)N * 8);
     if (c < 8) c = 8;
     return c;
 }
 
-/* enqueue K1 + K2 for nb blocks whose input starts at d_in (history at d_hist) */
-static int chan_enqueue_chunk(fdc_chan* c, const float2* d_in, const float2* d_hist, long nb, float2* d_spec, float2* d_mid,
+/* enqueue K1 + K2 for nb blocks; block b reads d_in[b*hop - ovl, b*hop + hop) */
+static int chan_enqueue_chunk(fdc_chan* c, const float2* d_in, long nb, float2* d_spec, float2* d_mid,
                               float2* d_out, long call_blocks, long call_blk0, long glob_blk0, cudaStream_t s)
 {
     cudaError_t e;
     if (c->prof) cudaEventRecord(c->ev(), s);
     if (!c->big) {
-        FwdParams p; p.in = d_in; p.hist = d_hist; p.spec = d_spec; p.nblocks = nb; p.hop = c->hop; p.ovl = c->ovl; p.N = c->N;
+        FwdParams p; p.in = d_in; p.spec = d_spec; p.nblocks = nb; p.hop = c->hop; p.ovl = c->ovl; p.N = c->N;
         p.scale = 1.0f / (float)c->N;
         e = launch_fwd_small(p, s);
     } else {
-        BigParams p; p.in = d_in; p.hist = d_hist; p.mid = d_mid; p.spec = d_spec; p.twlo = c->twlo; p.twhi = c->twhi;
-        p.tws_log2 = c->tws_log2; p.nblocks = nb; p.hop = c->hop; p.ovl = c->ovl; p.scale = 1.0f / (float)c->N;
+        BigParams p; p.in = d_in; p.mid = d_mid; p.spec = d_spec; p.tw4 = c->tw4;
+        p.nblocks = nb; p.hop = c->hop; p.ovl = c->ovl; p.scale = 1.0f / (float)c->N;
         e = launch_fwd_big(p, c->N, s);
     }
     if (e != cudaSuccess) return cuda_fail(e, "forward FFT launch");
@@ -166,9 +177,10 @@ static int chan_enqueue_chunk(fdc_chan* c, const float2* d_in, const float2* d_h
     if (!d_out) { if (c->prof) cudaEventRecord(c->ev(), s); return 0; }
     for (size_t g = 0; g < c->groups.size(); g++) {
         ExtractParams q; q.spec = d_spec; q.spec_stride = c->N; q.tables = (const float2*)c->d_tables.p;
-        q.chans = (const ChanDev*)c->d_chans.p; q.sel = (const int*)c->d_sel.p + c->groups[g].second.first; q.out = d_out;
+        q.chans = (const ChanDev*)c->d_chans.p + c->groups[g].second.first;
+        q.nsel = c->groups[g].second.second; q.ny = 0; q.out = d_out;
         q.nb = nb; q.call_blocks = call_blocks; q.call_blk0 = call_blk0; q.glob_phase0 = (int)(glob_blk0 % c->nphase); q.nphase = c->nphase;
-        e = launch_extract(q, c->groups[g].first, c->groups[g].second.second, s);
+        e = launch_extract(q, c->groups[g].first, s);
         if (e != cudaSuccess) return cuda_fail(e, "channel extract launch");
     }
     if (c->prof) cudaEventRecord(c->ev(), s);
@@ -187,15 +199,17 @@ fdc_chan* fdc_chan_create(int N, int ovl, int nphase, int nchan, const fdc_chan_
     fdc_chan* c = new fdc_chan;
     cudaGetDevice(&c->dev);
     c->N = N; c->ovl = ovl; c->hop = N - ovl; c->nphase = nphase; c->nchan = nchan; c->blockcount = 0;
-    c->big = false; c->N1 = c->N2 = 0; c->twlo = c->twhi = 0; c->tws_log2 = 0;
+    c->big = false; c->N1 = c->N2 = 0;
     if (!fwd_small_supported(N)) {
         if (!fwd_big_supported(N, &c->N1, &c->N2)) { fail("fdc_chan_create: unsupported FFT length"); delete c; return 0; }
         c->big = true;
-        big_twiddle_tables(N, &c->twlo, &c->twhi, &c->tws_log2);
+        c->tw4 = fourstep_table(c->N1, c->N2);
+        if (!c->tw4) { fail("fdc_chan_create: four-step twiddle table allocation failed"); delete c; return 0; }
     }
     /* channels: validate, group by l, pack tables */
     std::vector<float2> tables;
     std::map<int, std::vector<int> > by_l;
+    std::map<std::string, long> seen;
     long prefix = 0;
     for (int i = 0; i < nchan; i++) {
         const fdc_chan_desc& d = ch[i];
@@ -205,22 +219,41 @@ fdc_chan* fdc_chan_create(int N, int ovl, int nphase, int nchan, const fdc_chan_
         if (!d.table) { fail("fdc_chan_create: channel table missing"); delete c; return 0; }
         ChanDev cd; memset(&cd, 0, sizeof(cd));
         cd.f = d.f; cd.lout = d.lout; cd.shift = ((d.shift % nphase) + nphase) % nphase;
-        cd.tab_off = (long)tables.size(); cd.lout_prefix = prefix; cd.gain = d.gain;
+        cd.lout_prefix = prefix; cd.gain = d.gain;
         prefix += d.lout;
-        const float2* t = (const float2*)d.table;
-        tables.insert(tables.end(), t, t + (size_t)nphase * d.l);
+        /* channels whose tables are bit-identical share one copy (equal-bandwidth channel plans have a single table,
+         * which then lives in L1/L2 instead of being streamed once per channel) */
+        const size_t tbytes = sizeof(float2) * (size_t)nphase * d.l;
+        const std::string key((const char*)d.table, tbytes);
+        std::map<std::string, long>::iterator hit = seen.find(key);
+        if (hit != seen.end()) cd.tab_off = hit->second;
+        else {
+            cd.tab_off = (long)tables.size();
+            seen[key] = cd.tab_off;
+            const float2* t = (const float2*)d.table;
+            tables.insert(tables.end(), t, t + (size_t)nphase * d.l);
+        }
         c->chans.push_back(cd); c->l.push_back(d.l); by_l[d.l].push_back(i);
     }
     c->lout_total = prefix;
     std::vector<int> sel;
     for (std::map<int, std::vector<int> >::iterator it = by_l.begin(); it != by_l.end(); ++it) {
         c->groups.push_back(std::make_pair(it->first, std::make_pair((int)sel.size(), (int)it->second.size())));
-        sel.insert(sel.end(), it->second.begin(), it->second.end());
+        /* neighbours in frequency share a CTA tile: their slices overlap in the spectrum */
+        std::vector<int> order(it->second);
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return c->chans[a].f < c->chans[b].f; });
+        sel.insert(sel.end(), order.begin(), order.end());
     }
     c->chunk_blocks = pick_chunk_blocks(N);
     bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
-    ok = ok && c->d_chans.upload(c->chans.data(), sizeof(ChanDev) * c->chans.size());
-    ok = ok && c->d_sel.upload(sel.data(), sizeof(int) * sel.size());
+    ok = ok && cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < fdc_chan::NWORK && ok; i++)
+        ok = cudaStreamCreateWithFlags(&c->ws[i], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming) == cudaSuccess;
+    /* device copy of the channel descriptors in launch order (grouped by l, ascending f) */
+    std::vector<ChanDev> ordered(sel.size());
+    for (size_t i = 0; i < sel.size(); i++) ordered[i] = c->chans[(size_t)sel[i]];
+    ok = ok && c->d_chans.upload(ordered.data(), sizeof(ChanDev) * ordered.size());
     ok = ok && c->d_tables.upload(tables.data(), sizeof(float2) * tables.size());
     ok = ok && c->d_hist.reserve(sizeof(float2) * (size_t)std::max(ovl, 1)) && c->d_hist2.reserve(sizeof(float2) * (size_t)std::max(ovl, 1));
     ok = ok && cudaMemset(c->d_hist.p, 0, sizeof(float2) * (size_t)std::max(ovl, 1)) == cudaSuccess;
@@ -238,6 +271,8 @@ void fdc_chan_destroy(fdc_chan* c)
     if (!c) return;
     cudaDeviceSynchronize();
     if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->ev_start) cudaEventDestroy(c->ev_start);
+    for (int i = 0; i < fdc_chan::NWORK; i++) { if (c->ws[i]) cudaStreamDestroy(c->ws[i]); if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]); }
     for (size_t i = 0; i < c->prof_ev.size(); i++) cudaEventDestroy(c->prof_ev[i]);
     for (size_t i = 0; i < c->prof_pool.size(); i++) cudaEventDestroy(c->prof_pool[i]);
     for (int i = 0; i < fdc_chan::NSLOT; i++) if (c->hs[i]) cudaStreamDestroy(c->hs[i]);
@@ -292,16 +327,44 @@ int fdc_chan_work_device(fdc_chan* c, const void* d_in_v, long nblocks, void* d_
     if (nblocks == 0) return 0;
     const float2* d_in = (const float2*)d_in_v; float2* d_out = (float2*)d_out_v; float2* d_spectrum = (float2*)d_spectrum_v;
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
-    const long chunk = d_spectrum ? nblocks : std::min(nblocks, c->chunk_blocks);
-    if (!d_spectrum && !c->d_spec.reserve(sizeof(float2) * (size_t)chunk * c->N)) return cuda_fail(cudaGetLastError(), "spectrum ring");
-    if (c->big && !c->d_mid.reserve(sizeof(float2) * (size_t)std::min(nblocks, c->chunk_blocks) * c->N)) return cuda_fail(cudaGetLastError(), "four-step intermediate");
-    const long step = c->big ? std::min(chunk, c->chunk_blocks) : chunk;
-    for (long b0 = 0; b0 < nblocks; b0 += step) {
-        const long nb = std::min(step, nblocks - b0);
-        const float2* in = d_in + b0 * c->hop;
-        const float2* hist = b0 == 0 ? (const float2*)c->d_hist.p : in - c->ovl;
-        float2* spec = d_spectrum ? d_spectrum + b0 * c->N : (float2*)c->d_spec.p;
-        if (chan_enqueue_chunk(c, in, hist, nb, spec, (float2*)c->d_mid.p, d_out, nblocks, b0, c->blockcount + b0, s)) return -1;
+    cudaError_t e = cudaSuccess;
+    /* The first nh blocks reach back into the previous call: they are run from a staging copy [history | their samples]
+     * (lib/overlap_save_impl.cc:70-78 keeps the same history); all later blocks read the caller's buffer directly. */
+    const long nh = c->ovl ? std::min(nblocks, ((long)c->ovl + c->hop - 1) / c->hop) : 0;
+    if (nh) {
+        if (!c->d_stage.reserve(sizeof(float2) * (size_t)(c->ovl + nh * c->hop))) return cuda_fail(cudaGetLastError(), "history staging");
+        float2* st = (float2*)c->d_stage.p;
+        e = cudaMemcpyAsync(st, c->d_hist.p, sizeof(float2) * (size_t)c->ovl, cudaMemcpyDeviceToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(st + c->ovl, d_in, sizeof(float2) * (size_t)(nh * c->hop), cudaMemcpyDeviceToDevice, s);
+        if (e != cudaSuccess) return cuda_fail(e, "history staging copy");
+    }
+    /* worker streams (profiling serialises everything on the caller's stream so that the per-kernel events are clean) */
+    const int nw = (c->prof || tuning().streams < 2 || nblocks <= nh + c->chunk_blocks / 2) ? 1 : (int)fdc_chan::NWORK;
+    cudaStream_t wk[fdc_chan::NWORK];
+    for (int i = 0; i < fdc_chan::NWORK; i++) wk[i] = nw == 1 ? s : c->ws[i];
+    const long ring = std::min(nblocks, c->chunk_blocks);
+    for (int i = 0; i < nw; i++) {
+        if (!d_spectrum && !c->w_spec[i].reserve(sizeof(float2) * (size_t)ring * c->N)) return cuda_fail(cudaGetLastError(), "spectrum ring");
+        if (c->big && !c->w_mid[i].reserve(sizeof(float2) * (size_t)ring * c->N)) return cuda_fail(cudaGetLastError(), "four-step intermediate");
+    }
+    if (nw > 1) {
+        if ((e = cudaEventRecord(c->ev_start, s)) != cudaSuccess) return cuda_fail(e, "event record");
+        for (int i = 0; i < nw; i++) if ((e = cudaStreamWaitEvent(wk[i], c->ev_start, 0)) != cudaSuccess) return cuda_fail(e, "stream wait");
+    }
+    int w = 0;
+    for (long b0 = 0; b0 < nblocks; w = (w + 1) % nw) {
+        const bool head = b0 < nh;
+        const long nb = head ? nh : std::min(c->chunk_blocks, nblocks - b0);
+        const float2* in = head ? (const float2*)c->d_stage.p + c->ovl : d_in + b0 * c->hop;
+        float2* spec = d_spectrum ? d_spectrum + b0 * c->N : (float2*)c->w_spec[w].p;
+        if (chan_enqueue_chunk(c, in, nb, spec, (float2*)c->w_mid[w].p, d_out, nblocks, b0, c->blockcount + b0, wk[w])) return -1;
+        b0 += nb;
+    }
+    if (nw > 1) {
+        for (int i = 0; i < nw; i++) {
+            if ((e = cudaEventRecord(c->ev_done[i], wk[i])) != cudaSuccess) return cuda_fail(e, "event record");
+            if ((e = cudaStreamWaitEvent(s, c->ev_done[i], 0)) != cudaSuccess) return cuda_fail(e, "stream wait");
+        }
     }
     if (chan_save_history(c, d_in, nblocks, s)) return -1;
     c->blockcount += nblocks;
@@ -349,6 +412,7 @@ int fdc_chan_sync(fdc_chan* c)
 {
     if (!c) return fail("null context");
     cudaError_t e = cudaStreamSynchronize(c->stream);
+    for (int i = 0; i < fdc_chan::NWORK && e == cudaSuccess; i++) if (c->ws[i]) e = cudaStreamSynchronize(c->ws[i]);
     for (int i = 0; i < fdc_chan::NSLOT && e == cudaSuccess; i++) if (c->hs[i]) e = cudaStreamSynchronize(c->hs[i]);
     return e == cudaSuccess ? 0 : cuda_fail(e, "fdc_chan_sync");
 }
@@ -398,7 +462,7 @@ int fdc_chan_work_host(fdc_chan* c, const void* in_v, long nblocks, void* const*
         }
         if (e != cudaSuccess) return cuda_fail(e, "H2D");
         float2* d_out = (outs && c->nchan) ? (float2*)c->h_out[slot].p : 0;
-        if (chan_enqueue_chunk(c, d_in + c->ovl, d_in, nb, (float2*)c->h_spec[slot].p, (float2*)c->h_mid[slot].p, d_out, nb, 0,
+        if (chan_enqueue_chunk(c, d_in + c->ovl, nb, (float2*)c->h_spec[slot].p, (float2*)c->h_mid[slot].p, d_out, nb, 0,
                                c->blockcount + b0, s)) return -1;
         if (d_out) {
             if (uniform) {

@@ -1,17 +1,22 @@
 /* fdc_functors.cuh -- the global-memory sides of the tile FFT: what each kernel fuses into its
  * first-pass loads and last-pass stores.  Host/device code (see fdc_hd.h).
  *
- * Every functor has   Ctx begin(batch)   -- per-signal addressing (block / channel / job lookup, phase selection,
- *                                            row pointers), evaluated once per butterfly, and
- *                     get(ctx, n) / put(ctx, k, v)  -- the per-element access, index arithmetic only.
+ * Loader :  Ctx begin(batch, j)                    -- one address computation per butterfly
+ *           fetch<R, STRIDE>(ctx, t)               -- raw load of FFT input element j + t*STRIDE (t unrolled, so the
+ *                                                     access is base + immediate); issued one tile ahead (prefetch)
+ *           finish<R, STRIDE>(ctx, t, raw)         -- arithmetic on the fetched value (HAS_FINISH)
+ * Storer :  Ctx begin(batch, o)                    -- o < NS
+ *           put<R, NS>(ctx, t, v)                  -- FFT output element o + t*NS
+ * Half swaps (fft_vcc shift=True) are static permutations of t: L/2 = (R/2) * STRIDE on the load side and
+ * (R/2) * NS on the store side.
  *
  * HBM layout
- *   input stream  : contiguous cfp32 samples of this call, preceded logically by `hist`
- *                   (the last ovl samples of the previous call, zeros at stream start --
- *                   lib/overlap_save_impl.cc:52,70-78)
+ *   input stream  : contiguous cfp32 samples; block b reads in[b*hop - ovl, b*hop + hop): the ovl samples
+ *                   before in[0] must be addressable (the C-ABI layer stages [history | first blocks] for the
+ *                   blocks that reach back into the previous call -- lib/overlap_save_impl.cc:52,70-78)
  *   spectrum      : [block][N] cfp32, fft-shifted (DC at N/2) and scaled by 1/N -- exactly what
  *                   the hier block's normalize_input emits (python/FrequencyDomainChannelizer.py:206,216)
- *   tables        : per channel [phase][l] cfp32 (lib/windows.h:41-78)
+ *   tables        : [phase][l] cfp32 per distinct table (lib/windows.h:41-78); channels with equal tables share one
  *   outputs       : channel-major slabs, channel c at out + nblocks_call * lout_prefix[c]      */
 #ifndef FDC_FUNCTORS_CUH
 #define FDC_FUNCTORS_CUH
@@ -19,56 +24,64 @@
 
 namespace fdc {
 
-/* overlap-save window of one block: element n is in[blk*hop - ovl + n]; the first `nhist` elements of the very
- * first blocks of a launch come from the saved history instead (lib/overlap_save_impl.cc:70-78) */
-struct OvlCtx { const float2* base; const float2* hbase; int nhist; };
-FDC_HD OvlCtx ovl_ctx(const float2* in, const float2* hist, long blk, int hop, int ovl, bool valid)
+FDC_HD float2 fdc_zero2() { return make_float2(0.f, 0.f); }
+
+/* tile index = outer * ninner + inner (inner runs fastest).  Persistent loops split their first tile and their stride
+ * once and then advance the pair without dividing. */
+struct TilePos { int inner; int outer; };
+FDC_HD TilePos tile_split(long tile, int ninner)
 {
-    OvlCtx c;
-    const long start = blk * hop - ovl;                 /* may be negative for the first blocks */
-    c.base = in + start; c.hbase = hist + blk * hop;
-    c.nhist = start < 0 ? (int)(-start) : 0;
-    if (!valid) { c.base = 0; c.nhist = -1; }
-    return c;
+    TilePos s; s.outer = (int)(tile / ninner); s.inner = (int)(tile - (long)s.outer * ninner);
+    return s;
 }
-FDC_HD float2 ovl_get(const OvlCtx& c, long n)
+FDC_HD TilePos tile_advance(TilePos a, TilePos step, int ninner)
 {
-    if (c.nhist < 0) return make_float2(0.f, 0.f);
-    return n < c.nhist ? fdc_ldg(c.hbase + n) : fdc_ldg(c.base + n);
+    a.inner += step.inner; a.outer += step.outer;
+    if (a.inner >= ninner) { a.inner -= ninner; a.outer++; }
+    return a;
 }
 
 /* ------------------------------------------------------------------ K1: forward FFT, N in one CTA */
 struct FwdParams {
-    const float2* in;      /* new samples of this launch: block b starts at in[b*hop - ovl] */
-    const float2* hist;    /* ovl samples preceding in[0] */
+    const float2* in;      /* block b is in[b*hop - ovl, b*hop + hop) */
     float2* spec;          /* [nblocks][N] */
     long nblocks;
     int hop, ovl, N;
     float scale;           /* 1/N (a power of two: exact) */
 };
 template <int N, int B> struct FwdLoader {
-    typedef OvlCtx Ctx;
-    const FwdParams& p; int tile;
-    FDC_HD Ctx begin(int batch) const
+    typedef const float2* Ctx;
+    static constexpr bool HAS_FINISH = false;
+    const FwdParams& p; long tile;
+    FDC_HD Ctx begin(int batch, int j) const
     {
-        const long blk = (long)tile * B + batch;
-        return ovl_ctx(p.in, p.hist, blk, p.hop, p.ovl, blk < p.nblocks);
+        /* a ragged last tile re-reads the last block (its results are not stored) */
+        long blk = tile * B + batch;
+        if (blk >= p.nblocks) blk = p.nblocks - 1;
+        return p.in + (blk * p.hop - p.ovl + j);
     }
-    FDC_HD float2 get(const Ctx& c, int n) const { return ovl_get(c, n); }
+    template <int R, int STRIDE> FDC_HD float2 fetch(const Ctx& c, int t) const { return fdc_ldg(c + t * STRIDE); }
+    template <int R, int STRIDE> FDC_HD float2 finish(const Ctx&, int, float2 raw) const { return raw; }
 };
 template <int N, int B> struct FwdStorer {
     typedef float2* Ctx;
-    const FwdParams& p; int tile;
-    FDC_HD Ctx begin(int batch) const
+    const FwdParams& p; long tile;
+    FDC_HD Ctx begin(int batch, int o) const
     {
-        const long blk = (long)tile * B + batch;
-        return blk < p.nblocks ? p.spec + blk * N : (float2*)0;
+        const long blk = tile * B + batch;
+        return blk < p.nblocks ? p.spec + (blk * N + o) : (float2*)0;
     }
-    FDC_HD void put(const Ctx& row, int k, float2 v) const
+    template <int R, int NS> FDC_HD void put(const Ctx& row, int t, float2 v) const
     {
         /* fft_vcc shift=True for a forward transform: out[0:N/2] = Y[N/2:N], out[N/2:N] = Y[0:N/2] */
-        if (row) row[k ^ (N / 2)] = make_float2(v.x * p.scale, v.y * p.scale);
+        if (row) row[(t ^ (R / 2)) * NS] = make_float2(v.x * p.scale, v.y * p.scale);
     }
+};
+template <int N, int B> struct FwdTiles {
+    const FwdParams& p;
+    FDC_HD int ninner() const { return 1; }
+    FDC_HD FwdLoader<N, B> loader(TilePos t) const { return FwdLoader<N, B>{p, (long)t.outer}; }
+    FDC_HD FwdStorer<N, B> storer(TilePos t) const { return FwdStorer<N, B>{p, (long)t.outer}; }
 };
 
 /* ------------------------------------------------------ K1 (large N = N1*N2): four-step, two kernels
@@ -76,60 +89,68 @@ template <int N, int B> struct FwdStorer {
  *   pass A (columns): for every n2   A[k1][n2] = W_N^{n2 k1} * sum_n1 x[N2 n1 + n2] W_N1^{n1 k1}
  *   pass B (rows)   : for every k1   X[k1 + N1 k2] = sum_n2 A[k1][n2] W_N2^{n2 k2}
  * Both kernels work on tiles of 16 adjacent columns / rows so that every global access is a full
- * 128-byte line.  W_N^m is formed from two short tables: W_N^m = twlo[m & (TWS-1)] * twhi[m >> log2 TWS]. */
+ * 128-byte line.  W_N^{n2 k1} comes from a table laid out like the intermediate ([k1][n2], N entries,
+ * L2 resident); a persistent CTA keeps one column tile, so its 32 KB of the table stay in L1. */
 struct BigParams {
-    const float2* in; const float2* hist;
+    const float2* in;
     float2* mid;           /* [nblocks][N1][N2] intermediate */
     float2* spec;          /* [nblocks][N] */
-    const float2* twlo; const float2* twhi; int tws_log2;
+    const float2* tw4;     /* [N1][N2] four-step twiddles */
     long nblocks;
     int hop, ovl;
     float scale;
 };
 template <int N1, int N2, int B> struct ColLoader {     /* signal = column n2, element index = n1 */
-    struct Ctx { OvlCtx o; int n2; };
-    const BigParams& p; int tile; long blk;
-    FDC_HD Ctx begin(int batch) const
-    {
-        Ctx c; c.n2 = tile * B + batch; c.o = ovl_ctx(p.in, p.hist, blk, p.hop, p.ovl, true);
-        return c;
-    }
-    FDC_HD float2 get(const Ctx& c, int n1) const { return ovl_get(c.o, (long)N2 * n1 + c.n2); }
+    typedef const float2* Ctx;
+    static constexpr bool HAS_FINISH = false;
+    const BigParams& p; int ctile; long blk;
+    FDC_HD Ctx begin(int batch, int j) const { return p.in + (blk * p.hop - p.ovl + (long)N2 * j + (ctile * B + batch)); }
+    template <int R, int STRIDE> FDC_HD float2 fetch(const Ctx& c, int t) const { return fdc_ldg(c + (long)t * STRIDE * N2); }
+    template <int R, int STRIDE> FDC_HD float2 finish(const Ctx&, int, float2 raw) const { return raw; }
 };
 template <int N1, int N2, int B> struct ColStorer {
-    struct Ctx { float2* col; unsigned n2; };
-    const BigParams& p; int tile; long blk;
-    FDC_HD Ctx begin(int batch) const
+    struct Ctx { float2* col; const float2* tw; };
+    const BigParams& p; int ctile; long blk;
+    FDC_HD Ctx begin(int batch, int o) const
     {
-        Ctx c; c.n2 = (unsigned)(tile * B + batch); c.col = p.mid + blk * ((long)N1 * N2) + c.n2;
+        const long off = (long)o * N2 + (ctile * B + batch);
+        Ctx c; c.col = p.mid + (blk * ((long)N1 * N2) + off); c.tw = p.tw4 + off;
         return c;
     }
-    FDC_HD void put(const Ctx& c, int k1, float2 v) const
+    template <int R, int NS> FDC_HD void put(const Ctx& c, int t, float2 v) const
     {
-        const unsigned m = c.n2 * (unsigned)k1;                        /* < N1*N2 */
-        const float2 w = cmul(fdc_ldg(p.twlo + (m & ((1u << p.tws_log2) - 1u))), fdc_ldg(p.twhi + (m >> p.tws_log2)));
-        c.col[(long)k1 * N2] = cmul(v, w);
+        c.col[(long)t * NS * N2] = cmul(v, fdc_ldg(c.tw + (long)t * NS * N2));
     }
+};
+template <int N1, int N2, int B> struct ColTiles {      /* tile = blk * (N2/B) + column tile */
+    const BigParams& p;
+    FDC_HD int ninner() const { return N2 / B; }
+    FDC_HD ColLoader<N1, N2, B> loader(TilePos t) const { return ColLoader<N1, N2, B>{p, t.inner, (long)t.outer}; }
+    FDC_HD ColStorer<N1, N2, B> storer(TilePos t) const { return ColStorer<N1, N2, B>{p, t.inner, (long)t.outer}; }
 };
 template <int N1, int N2, int B> struct RowLoader {     /* signal = row k1, element index = n2 */
     typedef const float2* Ctx;
-    const BigParams& p; int tile; long blk;
-    FDC_HD Ctx begin(int batch) const { return p.mid + blk * ((long)N1 * N2) + (long)(tile * B + batch) * N2; }
-    FDC_HD float2 get(const Ctx& row, int n2) const { return row[n2]; }
+    static constexpr bool HAS_FINISH = false;
+    const BigParams& p; int rtile; long blk;
+    FDC_HD Ctx begin(int batch, int j) const { return p.mid + (blk * ((long)N1 * N2) + (long)(rtile * B + batch) * N2 + j); }
+    template <int R, int STRIDE> FDC_HD float2 fetch(const Ctx& row, int t) const { return row[t * STRIDE]; }
+    template <int R, int STRIDE> FDC_HD float2 finish(const Ctx&, int, float2 raw) const { return raw; }
 };
 template <int N1, int N2, int B> struct RowStorer {
-    struct Ctx { float2* spec; int k1; };
-    const BigParams& p; int tile; long blk;
-    FDC_HD Ctx begin(int batch) const
+    typedef float2* Ctx;
+    const BigParams& p; int rtile; long blk;
+    FDC_HD Ctx begin(int batch, int o) const { return p.spec + (blk * ((long)N1 * N2) + (rtile * B + batch) + (long)N1 * o); }
+    template <int R, int NS> FDC_HD void put(const Ctx& c, int t, float2 v) const
     {
-        Ctx c; c.k1 = tile * B + batch; c.spec = p.spec + blk * ((long)N1 * N2);
-        return c;
+        /* k = k1 + N1 (o + t NS); k ^ (N/2) flips bit log2(N2/2) of k2, i.e. t -> t ^ (R/2) */
+        c[(long)N1 * NS * (t ^ (R / 2))] = make_float2(v.x * p.scale, v.y * p.scale);
     }
-    FDC_HD void put(const Ctx& c, int k2, float2 v) const
-    {
-        const int k = c.k1 + N1 * k2;
-        c.spec[k ^ (N1 * N2 / 2)] = make_float2(v.x * p.scale, v.y * p.scale);
-    }
+};
+template <int N1, int N2, int B> struct RowTiles {      /* tile = blk * (N1/B) + row tile */
+    const BigParams& p;
+    FDC_HD int ninner() const { return N1 / B; }
+    FDC_HD RowLoader<N1, N2, B> loader(TilePos t) const { return RowLoader<N1, N2, B>{p, t.inner, (long)t.outer}; }
+    FDC_HD RowStorer<N1, N2, B> storer(TilePos t) const { return RowStorer<N1, N2, B>{p, t.inner, (long)t.outer}; }
 };
 
 /* ------------------------------------------------------------------ K2: batched channel extract
@@ -139,18 +160,19 @@ template <int N1, int N2, int B> struct RowStorer {
  * phase_shifting_windowing_vcc::work (lib/phase_shifting_windowing_vcc_impl.cc:81-82) the table multiply with
  * phase = (blocks seen so far * shift) mod nphase, fft_vcc(l, inverse, shift=True) the half swap + backward FFT,
  * the second vector_cut drops the first l-lout samples, multiply_const the gain.
- * A CTA handles B consecutive blocks of ONE channel so the table stays in L1 and the stores are one run. */
+ * A CTA handles B channels that are neighbours in frequency on ONE block: their slices overlap, so the spectrum is
+ * read from L2 once and the second use hits in L1. */
 struct ChanDev {
     int f, lout, shift, pad0;
-    long tab_off;          /* float2 offset of table_c[0][0] in `tables` */
+    long tab_off;          /* float2 offset of table[0][0] in `tables` */
     long lout_prefix;      /* sum of lout over the channels before this one */
     float gain; int pad1;
 };
 struct ExtractParams {
     const float2* spec; long spec_stride;   /* rows of the spectrum (ring) holding this chunk */
     const float2* tables;
-    const ChanDev* chans;
-    const int* sel;        /* channel indices handled by this launch (all share l) */
+    const ChanDev* chans;  /* the nsel channels handled by this launch (all share l), ascending f */
+    int nsel, ny;          /* ny = ceil(nsel / B) channel tiles */
     float2* out;
     long nb;               /* blocks in this chunk */
     long call_blocks;      /* blocks of the whole call (slab size) */
@@ -160,43 +182,52 @@ struct ExtractParams {
 };
 template <int L, int B> struct ExtractLoader {
     struct Ctx { const float2* x; const float2* w; };
-    const ExtractParams& p; int tile; int ysel;
-    FDC_HD Ctx begin(int batch) const
+    static constexpr bool HAS_FINISH = true;
+    const ExtractParams& p; int ytile; long b; unsigned bphase;     /* bphase = (global block index) mod nphase */
+    FDC_HD Ctx begin(int batch, int j) const
     {
-        Ctx c; c.x = 0; c.w = 0;
-        const long b = (long)tile * B + batch;
-        if (b >= p.nb) return c;
-        const ChanDev& ch = p.chans[fdc_ldg(p.sel + ysel)];
-        const unsigned np = (unsigned)p.nphase;
-        const unsigned phase = ((((unsigned)p.glob_phase0 + ((unsigned)b % np)) % np) * (unsigned)ch.shift) % np;
-        c.x = p.spec + b * p.spec_stride + ch.f;
-        c.w = p.tables + ch.tab_off + (long)phase * L;
+        Ctx c;
+        int s = ytile * B + batch;
+        if (s >= p.nsel) s = p.nsel - 1;                   /* ragged last tile: recompute the last channel, store nothing */
+        const ChanDev& ch = p.chans[s];
+        const unsigned phase = (bphase * (unsigned)ch.shift) % (unsigned)p.nphase;
+        c.x = p.spec + (b * p.spec_stride + ch.f + j);
+        c.w = p.tables + (ch.tab_off + (long)phase * L + j);
         return c;
     }
-    FDC_HD float2 get(const Ctx& c, int n) const
+    /* fft_vcc inverse+shift: FFT input n takes bin (n + l/2) mod l; n = j + t STRIDE, l/2 = (R/2) STRIDE */
+    template <int R, int STRIDE> FDC_HD float2 fetch(const Ctx& c, int t) const { return fdc_ldg(c.x + ((t + R / 2) % R) * STRIDE); }
+    template <int R, int STRIDE> FDC_HD float2 finish(const Ctx& c, int t, float2 raw) const
     {
-        if (!c.x) return make_float2(0.f, 0.f);
-        const int m = (n + L / 2) & (L - 1);              /* fft_vcc inverse+shift: dst[n] = in[(n + l/2) mod l] */
-        return cmul_exact(fdc_ldg(c.x + m), fdc_ldg(c.w + m));
+        return cmul_exact(raw, fdc_ldg(c.w + ((t + R / 2) % R) * STRIDE));
     }
 };
 template <int L, int B> struct ExtractStorer {
     struct Ctx { float2* dst; int skip; float gain; };
-    const ExtractParams& p; int tile; int ysel;
-    FDC_HD Ctx begin(int batch) const
+    const ExtractParams& p; int ytile; long b;
+    FDC_HD Ctx begin(int batch, int o) const
     {
-        Ctx c; c.dst = 0; c.skip = 0; c.gain = 0.f;
-        const long b = (long)tile * B + batch;
-        if (b >= p.nb) return c;
-        const ChanDev& ch = p.chans[fdc_ldg(p.sel + ysel)];
-        c.skip = L - ch.lout; c.gain = ch.gain;
-        c.dst = p.out + p.call_blocks * ch.lout_prefix + (p.call_blk0 + b) * ch.lout - c.skip;
+        Ctx c; c.dst = p.out; c.skip = 1 << 30; c.gain = 0.f;          /* skip beyond L: nothing is stored */
+        const int s = ytile * B + batch;
+        if (s >= p.nsel) return c;
+        const ChanDev& ch = p.chans[s];
+        c.skip = L - ch.lout - o; c.gain = ch.gain;
+        c.dst = p.out + (p.call_blocks * ch.lout_prefix + (p.call_blk0 + b) * ch.lout - (L - ch.lout) + o);
         return c;
     }
-    FDC_HD void put(const Ctx& c, int k, float2 v) const
+    template <int R, int NS> FDC_HD void put(const Ctx& c, int t, float2 v) const
     {
-        if (c.dst && k >= c.skip) c.dst[k] = make_float2(v.x * c.gain, v.y * c.gain);
+        if (t * NS >= c.skip) c.dst[t * NS] = make_float2(v.x * c.gain, v.y * c.gain);
     }
+};
+template <int L, int B> struct ExtractTiles {           /* tile = block * ny + channel tile */
+    const ExtractParams& p;
+    FDC_HD int ninner() const { return p.ny; }
+    FDC_HD ExtractLoader<L, B> loader(TilePos t) const
+    {
+        return ExtractLoader<L, B>{p, t.inner, (long)t.outer, ((unsigned)p.glob_phase0 + (unsigned)t.outer) % (unsigned)p.nphase};
+    }
+    FDC_HD ExtractStorer<L, B> storer(TilePos t) const { return ExtractStorer<L, B>{p, t.inner, (long)t.outer}; }
 };
 
 /* ------------------------------------------------- K2 (activity gated): explicit job list
@@ -216,70 +247,84 @@ struct JobParams {
 };
 template <int L, int B> struct JobLoader {
     struct Ctx { const float2* x; const float2* w; };
-    const JobParams& p; int tile;
-    FDC_HD Ctx begin(int batch) const
+    static constexpr bool HAS_FINISH = true;
+    const JobParams& p; long tile;
+    FDC_HD Ctx begin(int batch, int j) const
     {
-        Ctx c; c.x = 0; c.w = 0;
-        const int ji = tile * B + batch;
-        if (ji >= p.njobs) return c;
+        Ctx c;
+        long ji = tile * B + batch;
+        if (ji >= p.njobs) ji = p.njobs - 1;
         const ExtractJob& jb = p.jobs[ji];
-        c.x = (jb.row < 0 ? p.hist : p.spec + (long)jb.row * p.spec_stride) + jb.start;
-        c.w = p.tables + jb.tab_off;
+        c.x = (jb.row < 0 ? p.hist : p.spec + (long)jb.row * p.spec_stride) + (jb.start + j);
+        c.w = p.tables + (jb.tab_off + j);
         return c;
     }
-    FDC_HD float2 get(const Ctx& c, int n) const
+    template <int R, int STRIDE> FDC_HD float2 fetch(const Ctx& c, int t) const { return fdc_ldg(c.x + ((t + R / 2) % R) * STRIDE); }
+    template <int R, int STRIDE> FDC_HD float2 finish(const Ctx& c, int t, float2 raw) const
     {
-        if (!c.x) return make_float2(0.f, 0.f);
-        const int m = (n + L / 2) & (L - 1);
-        return cmul_exact(fdc_ldg(c.x + m), fdc_ldg(c.w + m));
+        return cmul_exact(raw, fdc_ldg(c.w + ((t + R / 2) % R) * STRIDE));
     }
 };
 template <int L, int B> struct JobStorer {
     struct Ctx { float2* dst; int skip; };
-    const JobParams& p; int tile;
-    FDC_HD Ctx begin(int batch) const
+    const JobParams& p; long tile;
+    FDC_HD Ctx begin(int batch, int o) const
     {
-        Ctx c; c.dst = 0; c.skip = 0;
-        const int ji = tile * B + batch;
+        Ctx c; c.dst = p.out; c.skip = 1 << 30;
+        const long ji = tile * B + batch;
         if (ji >= p.njobs) return c;
         const ExtractJob& jb = p.jobs[ji];
-        c.skip = jb.skip; c.dst = p.out + jb.dst_off - jb.skip;
+        c.skip = jb.skip - o; c.dst = p.out + (jb.dst_off - jb.skip + o);
         return c;
     }
-    FDC_HD void put(const Ctx& c, int k, float2 v) const { if (c.dst && k >= c.skip) c.dst[k] = v; }
+    template <int R, int NS> FDC_HD void put(const Ctx& c, int t, float2 v) const { if (t * NS >= c.skip) c.dst[t * NS] = v; }
+};
+template <int L, int B> struct JobTiles {
+    const JobParams& p;
+    FDC_HD int ninner() const { return 1; }
+    FDC_HD JobLoader<L, B> loader(TilePos t) const { return JobLoader<L, B>{p, (long)t.outer}; }
+    FDC_HD JobStorer<L, B> storer(TilePos t) const { return JobStorer<L, B>{p, (long)t.outer}; }
 };
 
 /* ------------------------------------------------- plain batched FFT (fft_vcc stage replacement) */
 struct PlainParams { const float2* in; float2* out; long nvec; int shift; };
 template <int L, int B, int DIR> struct PlainLoader {
     typedef const float2* Ctx;
-    const PlainParams& p; int tile;
-    FDC_HD Ctx begin(int batch) const
+    static constexpr bool HAS_FINISH = false;
+    const PlainParams& p; long tile;
+    FDC_HD Ctx begin(int batch, int j) const
     {
-        const long v = (long)tile * B + batch;
-        return v < p.nvec ? p.in + v * L : (const float2*)0;
+        long v = tile * B + batch;
+        if (v >= p.nvec) v = p.nvec - 1;
+        return p.in + (v * L + j);
     }
-    FDC_HD float2 get(const Ctx& row, int n) const
+    template <int R, int STRIDE> FDC_HD float2 fetch(const Ctx& row, int t) const
     {
-        if (!row) return make_float2(0.f, 0.f);
-        const int m = (DIR < 0 && p.shift) ? ((n + L / 2) & (L - 1)) : n;
-        return fdc_ldg(row + m);
+        const int tt = (DIR < 0 && p.shift) ? (t + R / 2) % R : t;       /* inverse + shift: half swap of the input */
+        return fdc_ldg(row + tt * STRIDE);
     }
+    template <int R, int STRIDE> FDC_HD float2 finish(const Ctx&, int, float2 raw) const { return raw; }
 };
 template <int L, int B, int DIR> struct PlainStorer {
     typedef float2* Ctx;
-    const PlainParams& p; int tile;
-    FDC_HD Ctx begin(int batch) const
+    const PlainParams& p; long tile;
+    FDC_HD Ctx begin(int batch, int o) const
     {
-        const long v = (long)tile * B + batch;
-        return v < p.nvec ? p.out + v * L : (float2*)0;
+        const long v = tile * B + batch;
+        return v < p.nvec ? p.out + (v * L + o) : (float2*)0;
     }
-    FDC_HD void put(const Ctx& row, int k, float2 v) const
+    template <int R, int NS> FDC_HD void put(const Ctx& row, int t, float2 v) const
     {
         if (!row) return;
-        const int m = (DIR > 0 && p.shift) ? (k ^ (L / 2)) : k;
-        row[m] = v;
+        const int tt = (DIR > 0 && p.shift) ? (t ^ (R / 2)) : t;         /* forward + shift: half swap of the output */
+        row[tt * NS] = v;
     }
+};
+template <int L, int B, int DIR> struct PlainTiles {
+    const PlainParams& p;
+    FDC_HD int ninner() const { return 1; }
+    FDC_HD PlainLoader<L, B, DIR> loader(TilePos t) const { return PlainLoader<L, B, DIR>{p, (long)t.outer}; }
+    FDC_HD PlainStorer<L, B, DIR> storer(TilePos t) const { return PlainStorer<L, B, DIR>{p, (long)t.outer}; }
 };
 
 }  // namespace fdc

@@ -7,46 +7,49 @@
 
 namespace fdc {
 
-template <int L, int B>
-__global__ void __launch_bounds__((TileFFT<L, B, -1, false, false>::T), min_ctas(TileFFT<L, B, -1, false, false>::T))
-k_extract(const ExtractParams p, const float2* __restrict__ tw)
+template <int L, int B, bool PF>
+__global__ void __launch_bounds__((TileFFT<L, B, -1, false, false>::T), min_ctas(TileFFT<L, B, -1, false, false>::T, PF))
+k_extract(const ExtractParams p, const float2* __restrict__ tw, long ntiles)
 {
-    typedef TileFFT<L, B, -1, false, false> ENG;
-    ExtractLoader<L, B> ld{p, (int)blockIdx.x, (int)blockIdx.y};
-    ExtractStorer<L, B> st{p, (int)blockIdx.x, (int)blockIdx.y};
-    tile_fft_run<ENG>(reinterpret_cast<float2*>(fdc_smem_raw), tw, ld, st);
+    tile_kernel_body<TileFFT<L, B, -1, false, false>, PF>(ExtractTiles<L, B>{p}, tw, ntiles);
 }
 template <int L, int B>
-__global__ void __launch_bounds__((TileFFT<L, B, -1, false, false>::T), min_ctas(TileFFT<L, B, -1, false, false>::T))
-k_jobs(const JobParams p, const float2* __restrict__ tw)
+__global__ void __launch_bounds__((TileFFT<L, B, -1, false, false>::T), min_ctas(TileFFT<L, B, -1, false, false>::T, false))
+k_jobs(const JobParams p, const float2* __restrict__ tw, long ntiles)
 {
-    typedef TileFFT<L, B, -1, false, false> ENG;
-    JobLoader<L, B> ld{p, (int)blockIdx.x};
-    JobStorer<L, B> st{p, (int)blockIdx.x};
-    tile_fft_run<ENG>(reinterpret_cast<float2*>(fdc_smem_raw), tw, ld, st);
+    tile_kernel_body<TileFFT<L, B, -1, false, false>, false>(JobTiles<L, B>{p}, tw, ntiles);
 }
 
-template <int L> static cudaError_t go_extract(const ExtractParams& p, int nsel, cudaStream_t s)
+template <int L, bool PF> static cudaError_t go_extract(const ExtractParams& p0, cudaStream_t s)
 {
     constexpr int B = tile_batch(L);
     typedef TileFFT<L, B, -1, false, false> ENG;
-    FDC_CHECK(set_smem(k_extract<L, B>, ENG::SMEM_BYTES));
-    const unsigned gx = (unsigned)((p.nb + B - 1) / B);
-    for (int y0 = 0; y0 < nsel; y0 += 65535) {
-        ExtractParams q = p; q.sel = p.sel + y0;
-        const int ny = nsel - y0 < 65535 ? nsel - y0 : 65535;
-        k_extract<L, B><<<dim3(gx, (unsigned)ny), ENG::T, ENG::SMEM_BYTES, s>>>(q, twiddle_table(L));
-        count_launch();
-    }
+    FDC_CHECK(set_smem(k_extract<L, B, PF>, ENG::SMEM_BYTES));
+    ExtractParams p = p0;
+    p.ny = (p.nsel + B - 1) / B;
+    const long ntiles = p.nb * p.ny;
+    unsigned grid = 1;
+    FDC_CHECK(persistent_grid(k_extract<L, B, PF>, ENG::T, ENG::SMEM_BYTES, ntiles, 1, &grid));
+    k_extract<L, B, PF><<<grid, ENG::T, ENG::SMEM_BYTES, s>>>(p, twiddle_table(L), ntiles);
+    count_launch();
     return cudaGetLastError();
+}
+template <int L> static cudaError_t go_extract_pf(const ExtractParams& p, cudaStream_t s)
+{
+    if constexpr (can_prefetch(TileFFT<L, tile_batch(L), -1, false, false>::T)) {
+        if (tuning().prefetch) return go_extract<L, true>(p, s);
+    }
+    return go_extract<L, false>(p, s);
 }
 template <int L> static cudaError_t go_jobs(const JobParams& p, cudaStream_t s)
 {
     constexpr int B = tile_batch(L);
     typedef TileFFT<L, B, -1, false, false> ENG;
     FDC_CHECK(set_smem(k_jobs<L, B>, ENG::SMEM_BYTES));
-    const unsigned gx = (unsigned)((p.njobs + B - 1) / B);
-    k_jobs<L, B><<<gx, ENG::T, ENG::SMEM_BYTES, s>>>(p, twiddle_table(L));
+    const long ntiles = ((long)p.njobs + B - 1) / B;
+    unsigned grid = 1;
+    FDC_CHECK(persistent_grid(k_jobs<L, B>, ENG::T, ENG::SMEM_BYTES, ntiles, 1, &grid));
+    k_jobs<L, B><<<grid, ENG::T, ENG::SMEM_BYTES, s>>>(p, twiddle_table(L), ntiles);
     count_launch();
     return cudaGetLastError();
 }
@@ -54,11 +57,11 @@ bool tile_len_supported(int L) { return L >= 2 && L <= 16384 && (L & (L - 1)) ==
 
 #define FDC_FOR_TILE_LENGTHS(X) X(2) X(4) X(8) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096) X(8192) X(16384)
 
-cudaError_t launch_extract(const ExtractParams& p, int l, int nsel, cudaStream_t s)
+cudaError_t launch_extract(const ExtractParams& p, int l, cudaStream_t s)
 {
-    if (p.nb <= 0 || nsel <= 0) return cudaSuccess;
+    if (p.nb <= 0 || p.nsel <= 0) return cudaSuccess;
     switch (l) {
-#define X(LL) case LL: return go_extract<LL>(p, nsel, s);
+#define X(LL) case LL: return go_extract_pf<LL>(p, s);
         FDC_FOR_TILE_LENGTHS(X)
 #undef X
     }

@@ -7,6 +7,7 @@
 #include <vector>
 #include <cmath>
 #include <cfloat>
+#include <cstdlib>
 
 namespace fdc {
 
@@ -14,41 +15,65 @@ static std::atomic<unsigned long long> g_launches(0);
 void count_launch(int n) { g_launches += (unsigned long long)n; }
 unsigned long long launch_count() { return g_launches.load(); }
 
+/* ---- run-time switches ------------------------------------------------------------------------ */
+static int env_int(const char* name, int dflt)
+{
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+const Tuning& tuning()
+{
+    static const Tuning t = { env_int("FDC_PREFETCH", 1), env_int("FDC_CTAS_PER_SM", 0), env_int("FDC_STREAMS", 2) };
+    return t;
+}
+
 /* ---- twiddle tables (per device, per length) ------------------------------------------------ */
 static std::mutex g_tw_mutex;
 static std::map<std::pair<int, long>, float2*> g_tw;      /* (device, key) -> device pointer */
 
-static float2* upload_roots(long n, long N, long stride)   /* exp(-2 pi i m*stride / N), m < n */
+static float2 root(long m, long N)                          /* exp(-2 pi i m / N), computed in long double */
 {
-    std::vector<float2> h((size_t)n);
-    for (long m = 0; m < n; m++) {
-        const long double a = -2.0L * 3.141592653589793238462643383279502884L * (long double)((m * stride) % N) / (long double)N;
-        h[(size_t)m] = make_float2((float)cosl(a), (float)sinl(a));
-    }
+    const long double a = -2.0L * 3.141592653589793238462643383279502884L * (long double)(m % N) / (long double)N;
+    return make_float2((float)cosl(a), (float)sinl(a));
+}
+static float2* upload(const std::vector<float2>& h)
+{
     float2* d = 0;
-    if (cudaMalloc(&d, sizeof(float2) * (size_t)n) != cudaSuccess) return 0;
-    if (cudaMemcpy(d, h.data(), sizeof(float2) * (size_t)n, cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return 0; }
+    if (cudaMalloc(&d, sizeof(float2) * h.size()) != cudaSuccess) return 0;
+    if (cudaMemcpy(d, h.data(), sizeof(float2) * h.size(), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return 0; }
     return d;
+}
+static void host_pass_twiddles(int L, std::vector<float2>& h)
+{
+    h.assign((size_t)fft_twsize(L), make_float2(1.f, 0.f));
+    const int np = fft_npasses(L);
+    for (int p = 1; p < np; p++) {
+        const int R = fft_radix(L, p), NS = fft_ns(L, p), off = fft_twoff(L, p);
+        for (int t = 1; t < R; t++)
+            for (int k = 0; k < NS; k++) h[(size_t)(off + (t - 1) * NS + k)] = root((long)k * t, (long)NS * R);
+    }
 }
 const float2* twiddle_table(int L)
 {
     int dev = 0; cudaGetDevice(&dev);
     std::lock_guard<std::mutex> g(g_tw_mutex);
     float2*& p = g_tw[std::make_pair(dev, (long)L)];
-    if (!p) p = upload_roots(L < 1 ? 1 : L, L < 1 ? 1 : L, 1);
+    if (!p) { std::vector<float2> h; host_pass_twiddles(L < 1 ? 1 : L, h); p = upload(h); }
     return p;
 }
-void big_twiddle_tables(int N, const float2** lo, const float2** hi, int* tws_log2)
+const float2* fourstep_table(int N1, int N2)
 {
     int dev = 0; cudaGetDevice(&dev);
-    int lg = 0; while ((1 << lg) < N) lg++;
-    const int s = lg / 2;                       /* lo: 2^s entries, hi: N / 2^s entries */
+    const long N = (long)N1 * N2;
     std::lock_guard<std::mutex> g(g_tw_mutex);
-    float2*& a = g_tw[std::make_pair(dev, -(long)N)];
-    float2*& b = g_tw[std::make_pair(dev, -(long)N - (1L << 40))];
-    if (!a) a = upload_roots(1L << s, N, 1);
-    if (!b) b = upload_roots((long)N >> s, N, 1L << s);
-    *lo = a; *hi = b; *tws_log2 = s;
+    float2*& p = g_tw[std::make_pair(dev, -(N + ((long)N1 << 32)))];
+    if (!p) {
+        std::vector<float2> h((size_t)N);
+        for (long k1 = 0; k1 < N1; k1++)
+            for (long n2 = 0; n2 < N2; n2++) h[(size_t)(k1 * N2 + n2)] = root(k1 * n2, N);
+        p = upload(h);
+    }
+    return p;
 }
 
 /* ---- row copy: overlap_save (lib/overlap_save_impl.cc:70-78) and vector_cut_vxx (lib/vector_cut_vxx_impl.cc:67-68)

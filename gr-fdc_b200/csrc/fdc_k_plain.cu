@@ -5,26 +5,21 @@
 namespace fdc {
 
 template <int L, int B, int DIR>
-__global__ void __launch_bounds__((TileFFT<L, B, DIR, false, false>::T), min_ctas(TileFFT<L, B, DIR, false, false>::T))
-k_plain(const PlainParams p, const float2* __restrict__ tw)
+__global__ void __launch_bounds__((TileFFT<L, B, DIR, false, false>::T), min_ctas(TileFFT<L, B, DIR, false, false>::T, false))
+k_plain(const PlainParams p, const float2* __restrict__ tw, long ntiles)
 {
-    typedef TileFFT<L, B, DIR, false, false> ENG;
-    PlainLoader<L, B, DIR> ld{p, (int)blockIdx.x};
-    PlainStorer<L, B, DIR> st{p, (int)blockIdx.x};
-    tile_fft_run<ENG>(reinterpret_cast<float2*>(fdc_smem_raw), tw, ld, st);
+    tile_kernel_body<TileFFT<L, B, DIR, false, false>, false>(PlainTiles<L, B, DIR>{p}, tw, ntiles);
 }
 template <int L, int DIR> static cudaError_t go_plain(const PlainParams& p, cudaStream_t s)
 {
     constexpr int B = tile_batch(L);
     typedef TileFFT<L, B, DIR, false, false> ENG;
     FDC_CHECK(set_smem(k_plain<L, B, DIR>, ENG::SMEM_BYTES));
-    const long tiles = (p.nvec + B - 1) / B;
-    for (long t0 = 0; t0 < tiles; t0 += 1 << 30) {
-        PlainParams q = p; q.in = p.in + t0 * B * L; q.out = p.out + t0 * B * L; q.nvec = p.nvec - t0 * B;
-        const long nt = tiles - t0 < (1 << 30) ? tiles - t0 : (1 << 30);
-        k_plain<L, B, DIR><<<(unsigned)nt, ENG::T, ENG::SMEM_BYTES, s>>>(q, twiddle_table(L));
-        count_launch();
-    }
+    const long ntiles = (p.nvec + B - 1) / B;
+    unsigned grid = 1;
+    FDC_CHECK(persistent_grid(k_plain<L, B, DIR>, ENG::T, ENG::SMEM_BYTES, ntiles, 1, &grid));
+    k_plain<L, B, DIR><<<grid, ENG::T, ENG::SMEM_BYTES, s>>>(p, twiddle_table(L), ntiles);
+    count_launch();
     return cudaGetLastError();
 }
 cudaError_t launch_plain_fft(const PlainParams& p, int L, int forward, cudaStream_t s)

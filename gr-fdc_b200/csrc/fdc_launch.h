@@ -10,10 +10,15 @@ namespace fdc {
 void count_launch(int n = 1);
 unsigned long long launch_count();
 
-/* forward root table exp(-2 pi i m / L), m in [0, L), on the current device (cached per device and L) */
+/* run-time switches for measurements (environment: FDC_PREFETCH=0|1, FDC_CTAS_PER_SM=n, FDC_STREAMS=1|2) */
+struct Tuning { int prefetch; int ctas_per_sm; int streams; };
+const Tuning& tuning();
+
+/* per-pass Stockham twiddles of a length-L tile FFT (layout of fdc_tile_fft.cuh: pass p at fft_twoff(L, p), entry
+ * [(t-1)*Ns + k] = exp(-2 pi i k t / (Ns R))), on the current device (cached per device and L) */
 const float2* twiddle_table(int L);
-/* split table for W_N^m, N = N1*N2: lo has 2^tws_log2 entries, hi the rest */
-void big_twiddle_tables(int N, const float2** lo, const float2** hi, int* tws_log2);
+/* four-step twiddles W_N^{n2 k1} laid out [k1][n2] (N = N1*N2 entries) */
+const float2* fourstep_table(int N1, int N2);
 
 bool fwd_small_supported(int N);      /* N handled by one CTA (16 .. 16384) */
 bool fwd_big_supported(int N, int* N1, int* N2);
@@ -22,7 +27,7 @@ bool tile_len_supported(int L);       /* inverse / plain tile lengths (2 .. 1638
 cudaError_t launch_fwd_small(const FwdParams& p, cudaStream_t s);
 cudaError_t launch_fwd_big(const BigParams& p, int N, cudaStream_t s);
 /* nsel channels sharing slice length l */
-cudaError_t launch_extract(const ExtractParams& p, int l, int nsel, cudaStream_t s);
+cudaError_t launch_extract(const ExtractParams& p, int l, cudaStream_t s);
 cudaError_t launch_jobs(const JobParams& p, int l, cudaStream_t s);
 cudaError_t launch_plain_fft(const PlainParams& p, int L, int forward, cudaStream_t s);
 

@@ -3,22 +3,28 @@
  * One CTA transforms a tile of B independent length-L signals (B*L = 16*T elements, T threads,
  * 16 elements per thread held in registers).  Stockham autosort passes with register radix-16/8/4/2
  * butterflies; between passes the tile is exchanged through shared memory (in place: read all ->
- * barrier -> write all -> barrier).  The first pass reads its operands straight from global memory
- * through a Loader functor (overlap-save addressing, window multiply, half swap ... are fused
- * there), the last pass hands its results to a Storer functor (fft-shift, overlap discard, scaling).
+ * barrier -> write all -> barrier).  The first pass takes its operands from global memory through a
+ * Loader functor (overlap-save addressing, table multiply, half swap ... are fused there), the last
+ * pass hands its results to a Storer functor (fft-shift, four-step twiddle, overlap discard, gain).
  *
  * Pass p (radix R, Ns = product of the earlier radices), butterfly j in [0, L/R):
  *      k    = j mod Ns
  *      in   : x[j + t*L/R] * W_{Ns*R}^{k t},  t = 0..R-1
  *      out  : y[(j-k)*R + k + t*Ns]
- * The first pass is radix 16 whenever L >= 16, so Ns >= 16 afterwards and every later exchange is
- * bank-conflict free as is; the first exchange (Ns = 1, thread writes 16 consecutive points) is
- * stored with one pad slot per 16 points (pos + pos/16).  The per-signal stride LP is odd so that
- * the "batch-fast" thread mappings (lanes walk over signals; used when the global side is a strided
- * column tile) stay conflict free too.
+ * Every access of a butterfly is "base + t * compile-time stride": the functors and the shared-memory
+ * exchange compute one address per butterfly and the 16 element accesses become immediate offsets.
+ * The twiddles of pass p are stored as a [t-1][k] table (k fastest) so that lanes with consecutive k
+ * read consecutive entries.
  *
- * The code is organised in PHASES separated by CTA barriers so that the same functions run on the
- * device and under the host emulator (see fdc_hd.h). */
+ * The first exchange (Ns = 1, a thread writes 16 consecutive points) is stored with one pad slot per
+ * 16 points (pos + pos/16); Ns >= 16 afterwards and the later exchanges are conflict free as is.  The
+ * per-signal stride LP is odd so that the "batch-fast" thread mappings (lanes walk over signals; used
+ * when the global side is a strided column tile) stay conflict free too.
+ *
+ * Global loads are split in two steps, fetch (raw LDGs of the NEXT tile, issued before the current
+ * tile is computed so that they are in flight during the butterflies) and finish (the functor's
+ * arithmetic on the fetched values).  The code is organised in PHASES separated by CTA barriers so
+ * that the same functions run on the device and under the host emulator (see fdc_hd.h). */
 #ifndef FDC_TILE_FFT_CUH
 #define FDC_TILE_FFT_CUH
 #include "fdc_bfly.cuh"
@@ -31,7 +37,7 @@ constexpr int fft_npasses(int L)
     int n = 1, rem = L / 16;
     while (rem > 1) {
         if (rem >= 64 || rem == 16) rem /= 16;
-        else if (rem == 32) rem /= 8;
+        else if (rem == 32) rem /= 4;
         else rem = 1;
         n++;
     }
@@ -44,7 +50,7 @@ constexpr int fft_radix(int L, int p)
     int rem = L / 16, q = 1, r = 1;
     while (true) {
         if (rem >= 64 || rem == 16) r = 16;
-        else if (rem == 32) r = 8;
+        else if (rem == 32) r = 4;                    /* 32 = 4 * 8: the larger radix last, fewer store contexts per thread */
         else r = rem;
         if (q == p) return r;
         rem /= r; q++;
@@ -56,6 +62,14 @@ constexpr int fft_ns(int L, int p)
     for (int q = 0; q < p; q++) ns *= fft_radix(L, q);
     return ns;
 }
+/* offset of pass p's twiddles inside the per-length table, and the table's size (float2 units) */
+constexpr int fft_twoff(int L, int p)
+{
+    int off = 0;
+    for (int q = 1; q < p; q++) off += (fft_radix(L, q) - 1) * fft_ns(L, q);
+    return off;
+}
+constexpr int fft_twsize(int L) { const int n = fft_twoff(L, fft_npasses(L)); return n < 1 ? 1 : n; }
 constexpr int ilog2(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
 
 template <int L_, int B_, int DIR, bool LOAD_BF, bool STORE_BF>
@@ -75,6 +89,7 @@ struct TileFFT {
         static constexpr int NS = fft_ns(L, P);
         static constexpr int NBF = L / R;                     /* butterflies per signal */
         static constexpr int U = E / R;                       /* butterflies per thread */
+        static constexpr int TWOFF = fft_twoff(L, P);
         static constexpr bool BF = (P == 0 && LOAD_BF) || (P == NP - 1 && STORE_BF);
         static FDC_HD void map(int tid, int u, int& batch, int& j)
         {
@@ -85,7 +100,48 @@ struct TileFFT {
     };
     /* physical smem slot of logical position pos of signal batch in exchange e (= written by pass e) */
     template <int EX> static FDC_HD int phys(int batch, int pos) { return batch * LP + pos + (EX == 0 ? (pos >> 4) : 0); }
+    /* the same for pos + c with a compile-time c: returns the constant to add to phys(batch, pos) (c % 16 == 0 or EX > 0,
+     * or pos % 16 == 0 and c < 16) */
+    template <int EX> static constexpr int phys_step(int c) { return c + (EX == 0 ? c / 16 : 0); }
 
+    /* ---- global side --------------------------------------------------------------------------------------- */
+    template <class Loader> static FDC_HD void fetch(int tid, float2* raw, const Loader& ld)
+    {
+        typedef Pass<0> PS;
+#pragma unroll
+        for (int u = 0; u < PS::U; u++) {
+            int batch, j; PS::map(tid, u, batch, j);
+            const typename Loader::Ctx c = ld.begin(batch, j);
+#pragma unroll
+            for (int t = 0; t < PS::R; t++) raw[u * PS::R + t] = ld.template fetch<PS::R, PS::NBF>(c, t);
+        }
+    }
+    template <class Loader> static FDC_HD void finish(int tid, float2* v, const Loader& ld)
+    {
+        typedef Pass<0> PS;
+        if (!Loader::HAS_FINISH) return;
+#pragma unroll
+        for (int u = 0; u < PS::U; u++) {
+            int batch, j; PS::map(tid, u, batch, j);
+            const typename Loader::Ctx c = ld.begin(batch, j);
+#pragma unroll
+            for (int t = 0; t < PS::R; t++) v[u * PS::R + t] = ld.template finish<PS::R, PS::NBF>(c, t, v[u * PS::R + t]);
+        }
+    }
+    template <int P, class Storer> static FDC_HD void store_global(int tid, const float2* v, const Storer& st)
+    {
+        typedef Pass<P> PS;
+#pragma unroll
+        for (int u = 0; u < PS::U; u++) {
+            int batch, j; PS::map(tid, u, batch, j);
+            /* last pass: NS * R == L, hence k == j and the outputs are j + t*NS */
+            const typename Storer::Ctx c = st.begin(batch, j);
+#pragma unroll
+            for (int t = 0; t < PS::R; t++) st.template put<PS::R, PS::NS>(c, t, v[u * PS::R + t]);
+        }
+    }
+
+    /* ---- butterflies ---------------------------------------------------------------------------------------- */
     template <int P> static FDC_HD void twiddle_bfly(int tid, float2* v, const float2* tw)
     {
         typedef Pass<P> PS;
@@ -93,37 +149,30 @@ struct TileFFT {
         for (int u = 0; u < PS::U; u++) {
             if (P > 0) {
                 int batch, j; PS::map(tid, u, batch, j);
-                const int k = j % PS::NS;
-                const int step = k * (L / (PS::NS * PS::R));
+                const float2* twp = tw + PS::TWOFF + (j % PS::NS);
 #pragma unroll
                 for (int t = 1; t < PS::R; t++) {
-                    float2 w = fdc_ldg(tw + step * t);
-                    if (DIR < 0) w.y = -w.y;
-                    v[u * PS::R + t] = cmul(v[u * PS::R + t], w);
+                    const float2 w = fdc_ldg(twp + (t - 1) * PS::NS);
+                    const float2 a = v[u * PS::R + t];
+                    v[u * PS::R + t] = DIR > 0 ? make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x)
+                                               : make_float2(a.x * w.x + a.y * w.y, a.y * w.x - a.x * w.y);
                 }
             }
             Bfly<PS::R, DIR>::run(v + u * PS::R);
         }
     }
-    template <int P, class Loader> static FDC_HD void load_global(int tid, float2* v, Loader& ld)
-    {
-        typedef Pass<P> PS;
-#pragma unroll
-        for (int u = 0; u < PS::U; u++) {
-            int batch, j; PS::map(tid, u, batch, j);
-            const typename Loader::Ctx c = ld.begin(batch);       /* per-signal addressing, hoisted out of the element loop */
-#pragma unroll
-            for (int t = 0; t < PS::R; t++) v[u * PS::R + t] = ld.get(c, j + t * PS::NBF);
-        }
-    }
+
+    /* ---- shared-memory exchange ----------------------------------------------------------------------------- */
     template <int P> static FDC_HD void read_smem(int tid, float2* v, const float2* smem)
     {
         typedef Pass<P> PS;
+        static_assert(PS::NBF % 16 == 0, "exchange reads need a 16-aligned butterfly stride");
 #pragma unroll
         for (int u = 0; u < PS::U; u++) {
             int batch, j; PS::map(tid, u, batch, j);
+            const float2* s = smem + phys<P - 1>(batch, j);
 #pragma unroll
-            for (int t = 0; t < PS::R; t++) v[u * PS::R + t] = smem[phys<P - 1>(batch, j + t * PS::NBF)];
+            for (int t = 0; t < PS::R; t++) v[u * PS::R + t] = s[phys_step<P - 1>(t * PS::NBF)];
         }
     }
     template <int P> static FDC_HD void write_smem(int tid, const float2* v, float2* smem)
@@ -133,33 +182,22 @@ struct TileFFT {
         for (int u = 0; u < PS::U; u++) {
             int batch, j; PS::map(tid, u, batch, j);
             const int k = j % PS::NS;
-            const int o = (j - k) * PS::R + k;
+            const int o = (j - k) * PS::R + k;               /* P == 0: o = 16 j, offsets t < 16; P > 0: offsets t*NS, NS % 16 == 0 */
+            float2* s = smem + phys<P>(batch, o);
 #pragma unroll
-            for (int t = 0; t < PS::R; t++) smem[phys<P>(batch, o + t * PS::NS)] = v[u * PS::R + t];
-        }
-    }
-    template <int P, class Storer> static FDC_HD void store_global(int tid, const float2* v, Storer& st)
-    {
-        typedef Pass<P> PS;
-#pragma unroll
-        for (int u = 0; u < PS::U; u++) {
-            int batch, j; PS::map(tid, u, batch, j);
-            const int k = j % PS::NS;
-            const int o = (j - k) * PS::R + k;
-            const typename Storer::Ctx c = st.begin(batch);
-#pragma unroll
-            for (int t = 0; t < PS::R; t++) st.put(c, o + t * PS::NS, v[u * PS::R + t]);
+            for (int t = 0; t < PS::R; t++) s[phys_step<P>(t * PS::NS)] = v[u * PS::R + t];
         }
     }
 
-    /* one barrier-separated phase; v[16] is the calling thread's register tile and persists across phases */
+    /* one barrier-separated phase; v[16] is the calling thread's register tile and persists across phases.
+     * Phase 0 expects the raw fetched values in v. */
     template <int PH, class Loader, class Storer>
-    static FDC_HD void phase(int tid, float2* v, float2* smem, const float2* tw, Loader& ld, Storer& st)
+    static FDC_HD void phase(int tid, float2* v, float2* smem, const float2* tw, const Loader& ld, const Storer& st)
     {
         if constexpr (NP == 1) {
-            load_global<0>(tid, v, ld); twiddle_bfly<0>(tid, v, tw); store_global<0>(tid, v, st);
+            finish(tid, v, ld); twiddle_bfly<0>(tid, v, tw); store_global<0>(tid, v, st);
         } else if constexpr (PH == 0) {
-            load_global<0>(tid, v, ld); twiddle_bfly<0>(tid, v, tw); write_smem<0>(tid, v, smem);
+            finish(tid, v, ld); twiddle_bfly<0>(tid, v, tw); write_smem<0>(tid, v, smem);
         } else if constexpr (PH % 2 == 1) {
             constexpr int P = (PH + 1) / 2;
             read_smem<P>(tid, v, smem); twiddle_bfly<P>(tid, v, tw);
@@ -172,9 +210,9 @@ struct TileFFT {
 };
 
 #if defined(__CUDACC__)
-/* device driver: run all phases of one tile with CTA barriers in between */
+/* device driver: run all phases of one tile with CTA barriers in between (v holds the fetched values) */
 template <class ENG, int PH, class Loader, class Storer>
-__device__ __forceinline__ void tile_fft_from(float2* v, float2* smem, const float2* tw, Loader& ld, Storer& st)
+__device__ __forceinline__ void tile_fft_from(float2* v, float2* smem, const float2* tw, const Loader& ld, const Storer& st)
 {
     ENG::template phase<PH>(threadIdx.x, v, smem, tw, ld, st);
     if constexpr (PH + 1 < ENG::NPH) {
@@ -182,11 +220,36 @@ __device__ __forceinline__ void tile_fft_from(float2* v, float2* smem, const flo
         tile_fft_from<ENG, PH + 1, Loader, Storer>(v, smem, tw, ld, st);
     }
 }
-template <class ENG, class Loader, class Storer>
-__device__ __forceinline__ void tile_fft_run(float2* smem, const float2* tw, Loader& ld, Storer& st)
+/* Persistent tile loop: the CTA walks tiles first, first + stride, ... < ntiles; with PF the global loads of tile
+ * i+1 are issued before tile i is computed (register prefetch).  Tiles::loader(pos) / Tiles::storer(pos) make the
+ * functors from the (inner, outer) split of the tile index, which is advanced without divisions. */
+template <class ENG, bool PF, class Tiles>
+__device__ __forceinline__ void tile_fft_loop(float2* smem, const float2* tw, const Tiles& tiles, long first, long stride, long ntiles)
 {
+    if (first >= ntiles) return;
+    const int ninner = tiles.ninner();
+    const TilePos step = tile_split(stride, ninner);
+    TilePos pos = tile_split(first, ninner);
     float2 v[16];
-    tile_fft_from<ENG, 0, Loader, Storer>(v, smem, tw, ld, st);
+    if (PF) ENG::fetch(threadIdx.x, v, tiles.loader(pos));
+    for (long tile = first;;) {
+        const long next = tile + stride;
+        const TilePos npos = tile_advance(pos, step, ninner);
+        if constexpr (PF) {
+            float2 nx[16];
+            if (next < ntiles) ENG::fetch(threadIdx.x, nx, tiles.loader(npos));
+            tile_fft_from<ENG, 0>(v, smem, tw, tiles.loader(pos), tiles.storer(pos));
+            if (next >= ntiles) break;
+#pragma unroll
+            for (int i = 0; i < 16; i++) v[i] = nx[i];
+        } else {
+            ENG::fetch(threadIdx.x, v, tiles.loader(pos));
+            tile_fft_from<ENG, 0>(v, smem, tw, tiles.loader(pos), tiles.storer(pos));
+            if (next >= ntiles) break;
+        }
+        tile = next; pos = npos;
+        if (ENG::NP > 1) __syncthreads();          /* the exchange buffer is reused by the next tile */
+    }
 }
 #endif
 

@@ -1,66 +1,271 @@
-/* TEST INFRASTRUCTURE: host emulation of the tile-FFT phases (index arithmetic check), see csrc/fdc_hd.h */
+/* TEST INFRASTRUCTURE: host emulation of the tile-FFT phases and of the kernels' loader/storer functors
+ * (index arithmetic check before GPU time is spent), see csrc/fdc_hd.h.  Every phase is stepped over all
+ * thread ids of a CTA, phases in order = the barriers of the device code.  Checked against fp64 DFTs. */
 #include "fdc_tile_fft.cuh"
+#include "fdc_functors.cuh"
 #include <vector>
 #include <complex>
 #include <cstdio>
 #include <cstdlib>
 #include <array>
+#include <algorithm>
 using namespace fdc;
 typedef std::complex<double> cd;
 
-struct Ld { typedef const float2* Ctx; const float2* in; int L; Ctx begin(int batch) const { return in + batch * L; } float2 get(const Ctx& c, int n) const { return c[n]; } };
-struct St { typedef float2* Ctx; float2* out; int L; Ctx begin(int batch) const { return out + batch * L; } void put(const Ctx& c, int k, float2 v) const { c[k] = v; } };
+static std::vector<float2> pass_twiddles(int L)
+{
+    std::vector<float2> h((size_t)fft_twsize(L), make_float2(1.f, 0.f));
+    for (int p = 1; p < fft_npasses(L); p++) {
+        const int R = fft_radix(L, p), NS = fft_ns(L, p), off = fft_twoff(L, p);
+        for (int t = 1; t < R; t++)
+            for (int k = 0; k < NS; k++) {
+                const double a = -2.0 * M_PI * (double)(((long)k * t) % ((long)NS * R)) / ((double)NS * R);
+                h[(size_t)(off + (t - 1) * NS + k)] = make_float2((float)cos(a), (float)sin(a));
+            }
+    }
+    return h;
+}
+/* fp64 reference FFT (iterative radix-2), sign = -1 forward, +1 backward */
+static void fft64(std::vector<cd>& a, int sign)
+{
+    const size_t n = a.size();
+    for (size_t i = 1, j = 0; i < n; i++) {
+        size_t bit = n >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) std::swap(a[i], a[j]);
+    }
+    for (size_t len = 2; len <= n; len <<= 1) {
+        for (size_t i = 0; i < n; i += len)
+            for (size_t k = 0; k < len / 2; k++) {
+                const cd w = std::polar(1.0, sign * 2.0 * M_PI * (double)k / (double)len);
+                const cd u = a[i + k], v = a[i + k + len / 2] * w;
+                a[i + k] = u + v; a[i + k + len / 2] = u - v;
+            }
+    }
+}
+static float frand() { return (float)rand() / RAND_MAX - 0.5f; }
 
-template <class ENG, int PH> struct Run {
-    static void go(std::vector<std::array<float2, 16>>& regs, float2* smem, const float2* tw, Ld& ld, St& st)
+/* run one tile through all phases */
+template <class ENG, int PH, class LD, class ST> struct Run {
+    static void go(std::vector<std::array<float2, 16>>& regs, float2* smem, const float2* tw, const LD& ld, const ST& st)
     {
         for (int tid = 0; tid < ENG::T; tid++) ENG::template phase<PH>(tid, regs[tid].data(), smem, tw, ld, st);
-        if constexpr (PH + 1 < ENG::NPH) Run<ENG, PH + 1>::go(regs, smem, tw, ld, st);
+        if constexpr (PH + 1 < ENG::NPH) Run<ENG, PH + 1, LD, ST>::go(regs, smem, tw, ld, st);
     }
 };
-
-template <int L, int B, int DIR, bool LBF, bool SBF> double check()
+template <class ENG, class Tiles> static void run_tiles(const Tiles& tiles, long ntiles, const float2* tw)
 {
-    typedef TileFFT<L, B, DIR, LBF, SBF> ENG;
-    std::vector<float2> in(L * B), out(L * B), smem(ENG::SMEM_ELEMS), tw(L);
-    for (auto& v : in) { v.x = (float)rand() / RAND_MAX - 0.5f; v.y = (float)rand() / RAND_MAX - 0.5f; }
-    for (int m = 0; m < L; m++) { tw[m].x = (float)cos(-2.0 * M_PI * m / L); tw[m].y = (float)sin(-2.0 * M_PI * m / L); }
+    std::vector<float2> smem(ENG::SMEM_ELEMS);
     std::vector<std::array<float2, 16>> regs(ENG::T);
-    Ld ld{in.data(), L}; St st{out.data(), L};
-    Run<ENG, 0>::go(regs, smem.data(), tw.data(), ld, st);
-    double num = 0, den = 0;
-    for (int b = 0; b < B; b++)
-        for (int k = 0; k < L; k++) {
-            cd acc = 0;
-            for (int n = 0; n < L; n++) acc += cd(in[b * L + n].x, in[b * L + n].y) * std::polar(1.0, -DIR * 2.0 * M_PI * (double)((long)k * n % L) / L);
-            cd d = acc - cd(out[b * L + k].x, out[b * L + k].y);
-            num += std::norm(d); den += std::norm(acc);
-        }
-    double e = sqrt(num / den);
-    printf("L=%5d B=%3d DIR=%2d LBF=%d SBF=%d NP=%d T=%4d smem=%6zu  relL2=%.3e %s\n", L, B, DIR, LBF, SBF, ENG::NP, ENG::T, ENG::SMEM_BYTES, e, e < 2e-6 ? "ok" : "FAIL");
-    return e;
+    /* walk the tiles like a persistent CTA does: a stride that is not a multiple of ninner exercises tile_advance */
+    const int ninner = tiles.ninner();
+    const long stride = 3;
+    for (long first = 0; first < stride && first < ntiles; first++) {
+      TilePos pos = tile_split(first, ninner); const TilePos step = tile_split(stride, ninner);
+      for (long tile = first; tile < ntiles; tile += stride, pos = tile_advance(pos, step, ninner)) {
+        const TilePos chk = tile_split(tile, ninner);
+        if (chk.inner != pos.inner || chk.outer != pos.outer) { printf("tile_advance mismatch at %ld\n", tile); exit(2); }
+        auto ld = tiles.loader(pos); auto st = tiles.storer(pos);
+        for (int tid = 0; tid < ENG::T; tid++) ENG::fetch(tid, regs[tid].data(), ld);
+        Run<ENG, 0, decltype(ld), decltype(st)>::go(regs, smem.data(), tw, ld, st);
+      }
+    }
 }
+static double rel_err(const std::vector<cd>& want, const float2* got)
+{
+    double num = 0, den = 0;
+    for (size_t i = 0; i < want.size(); i++) { num += std::norm(want[i] - cd(got[i].x, got[i].y)); den += std::norm(want[i]); }
+    return sqrt(num / (den > 0 ? den : 1));
+}
+static int g_fail = 0;
+static void report(const char* what, double e, double tol)
+{
+    printf("%-64s relL2=%.3e %s\n", what, e, e < tol ? "ok" : "FAIL");
+    if (!(e < tol)) g_fail++;
+}
+
+/* ---- the plain engine at every length, both directions, with and without the shift permutations ---- */
+template <int L, int DIR> static void check_plain(int shift)
+{
+    constexpr int B = L >= 4096 ? 1 : 4096 / L;
+    typedef TileFFT<L, B, DIR, false, false> ENG;
+    const long nvec = 2 * B + 1 < 3 ? 3 : B + 1;                       /* a ragged last tile */
+    std::vector<float2> in((size_t)nvec * L), out((size_t)nvec * L, make_float2(7.f, 7.f));
+    for (auto& v : in) { v.x = frand(); v.y = frand(); }
+    const std::vector<float2> tw = pass_twiddles(L);
+    PlainParams p; p.in = in.data(); p.out = out.data(); p.nvec = nvec; p.shift = shift;
+    run_tiles<ENG>(PlainTiles<L, B, DIR>{p}, (nvec + B - 1) / B, tw.data());
+    double worst = 0;
+    for (long v = 0; v < nvec; v++) {
+        std::vector<cd> a(L);
+        for (int n = 0; n < L; n++) {
+            const int src = (DIR < 0 && shift) ? (n + L / 2) % L : n;
+            a[n] = cd(in[(size_t)v * L + src].x, in[(size_t)v * L + src].y);
+        }
+        if (L > 1) fft64(a, -DIR);
+        std::vector<cd> want(L);
+        for (int k = 0; k < L; k++) want[(DIR > 0 && shift) ? (k ^ (L / 2)) : k] = a[k];
+        worst = std::max(worst, rel_err(want, out.data() + (size_t)v * L));
+    }
+    char name[128]; snprintf(name, sizeof name, "plain L=%d DIR=%d shift=%d (NP=%d, T=%d, smem=%zu)", L, DIR, shift, ENG::NP, ENG::T, ENG::SMEM_BYTES);
+    report(name, worst, 2e-6);
+}
+
+/* ---- K1 small: overlap addressing, shift, scale ---- */
+template <int N> static void check_fwd_small(int ovl, long nblocks)
+{
+    constexpr int B = N >= 4096 ? 1 : 4096 / N;
+    typedef TileFFT<N, B, 1, false, false> ENG;
+    const int hop = N - ovl;
+    std::vector<float2> buf((size_t)ovl + (size_t)nblocks * hop), spec((size_t)nblocks * N);
+    for (auto& v : buf) { v.x = frand(); v.y = frand(); }
+    const std::vector<float2> tw = pass_twiddles(N);
+    FwdParams p; p.in = buf.data() + ovl; p.spec = spec.data(); p.nblocks = nblocks; p.hop = hop; p.ovl = ovl; p.N = N; p.scale = 1.0f / N;
+    run_tiles<ENG>(FwdTiles<N, B>{p}, (nblocks + B - 1) / B, tw.data());
+    double worst = 0;
+    for (long b = 0; b < nblocks; b++) {
+        std::vector<cd> a(N);
+        for (int n = 0; n < N; n++) a[n] = cd(buf[(size_t)b * hop + n].x, buf[(size_t)b * hop + n].y);
+        fft64(a, -1);
+        std::vector<cd> want(N);
+        for (int k = 0; k < N; k++) want[k ^ (N / 2)] = a[k] / (double)N;
+        worst = std::max(worst, rel_err(want, spec.data() + (size_t)b * N));
+    }
+    char name[128]; snprintf(name, sizeof name, "fwd_small N=%d ovl=%d nblocks=%ld", N, ovl, nblocks);
+    report(name, worst, 2e-6);
+}
+
+/* ---- K1 big: four-step with column/row tiles ---- */
+template <int N1, int N2> static void check_fwd_big(int ovl, long nblocks)
+{
+    constexpr int N = N1 * N2;
+    constexpr int BC = N1 <= 256 ? 16 : 4096 / N1, BR = N2 <= 256 ? 16 : 4096 / N2;
+    typedef TileFFT<N1, BC, 1, true, true> CE;
+    typedef TileFFT<N2, BR, 1, false, true> RE;
+    const int hop = N - ovl;
+    std::vector<float2> buf((size_t)ovl + (size_t)nblocks * hop), mid((size_t)nblocks * N), spec((size_t)nblocks * N), tw4((size_t)N);
+    for (auto& v : buf) { v.x = frand(); v.y = frand(); }
+    for (long k1 = 0; k1 < N1; k1++)
+        for (long n2 = 0; n2 < N2; n2++) {
+            const double a = -2.0 * M_PI * (double)((k1 * n2) % N) / N;
+            tw4[(size_t)(k1 * N2 + n2)] = make_float2((float)cos(a), (float)sin(a));
+        }
+    const std::vector<float2> twc = pass_twiddles(N1), twr = pass_twiddles(N2);
+    BigParams p; p.in = buf.data() + ovl; p.mid = mid.data(); p.spec = spec.data(); p.tw4 = tw4.data(); p.nblocks = nblocks;
+    p.hop = hop; p.ovl = ovl; p.scale = 1.0f / N;
+    run_tiles<CE>(ColTiles<N1, N2, BC>{p}, nblocks * (N2 / BC), twc.data());
+    run_tiles<RE>(RowTiles<N1, N2, BR>{p}, nblocks * (N1 / BR), twr.data());
+    double worst = 0;
+    for (long b = 0; b < nblocks; b++) {
+        std::vector<cd> a(N);
+        for (int n = 0; n < N; n++) a[n] = cd(buf[(size_t)b * hop + n].x, buf[(size_t)b * hop + n].y);
+        fft64(a, -1);
+        std::vector<cd> want(N);
+        for (int k = 0; k < N; k++) want[k ^ (N / 2)] = a[k] / (double)N;
+        worst = std::max(worst, rel_err(want, spec.data() + (size_t)b * N));
+    }
+    char name[128]; snprintf(name, sizeof name, "fwd_big N=%dx%d ovl=%d nblocks=%ld", N1, N2, ovl, nblocks);
+    report(name, worst, 2e-6);
+}
+
+/* ---- K2: channel tiles, shared tables, phase selection, overlap discard, gain ---- */
+template <int L> static void check_extract(int N, int nchan, long nb, int nphase)
+{
+    constexpr int B = L >= 4096 ? 1 : 4096 / L;
+    typedef TileFFT<L, B, -1, false, false> ENG;
+    std::vector<float2> spec((size_t)nb * N), tables((size_t)2 * nphase * L);
+    for (auto& v : spec) { v.x = frand(); v.y = frand(); }
+    for (auto& v : tables) { v.x = frand(); v.y = frand(); }
+    std::vector<ChanDev> chans(nchan);
+    long prefix = 0;
+    const long call_blocks = nb + 3, call_blk0 = 2; const int glob_phase0 = 1 % nphase;
+    for (int i = 0; i < nchan; i++) {
+        ChanDev& c = chans[i];
+        c.f = (int)(((long)i * (N - L)) / std::max(1, nchan - 1)); c.lout = L - L / 4 - (i % 3 == 1 ? 1 : 0); if (c.lout < 1) c.lout = 1;
+        c.shift = (c.f + i) % nphase; c.tab_off = (i % 2) * (long)nphase * L; c.lout_prefix = prefix; c.gain = (float)(1 + i % 4); c.pad0 = c.pad1 = 0;
+        prefix += c.lout;
+    }
+    std::vector<float2> out((size_t)(call_blocks * prefix), make_float2(-9.f, -9.f));
+    const std::vector<float2> tw = pass_twiddles(L);
+    ExtractParams p; p.spec = spec.data(); p.spec_stride = N; p.tables = tables.data(); p.chans = chans.data();
+    p.nsel = nchan; p.ny = (nchan + B - 1) / B; p.out = out.data(); p.nb = nb; p.call_blocks = call_blocks; p.call_blk0 = call_blk0;
+    p.glob_phase0 = glob_phase0; p.nphase = nphase;
+    run_tiles<ENG>(ExtractTiles<L, B>{p}, nb * p.ny, tw.data());
+    double worst = 0;
+    for (int i = 0; i < nchan; i++)
+        for (long b = 0; b < nb; b++) {
+            const ChanDev& c = chans[i];
+            const int phase = (int)((((glob_phase0 + b) % nphase) * c.shift) % nphase);
+            std::vector<cd> a(L);
+            for (int n = 0; n < L; n++) {
+                const int m = (n + L / 2) % L;
+                const float2 x = spec[(size_t)b * N + c.f + m], w = tables[(size_t)(c.tab_off + (long)phase * L + m)];
+                a[n] = cd(x.x, x.y) * cd(w.x, w.y);
+            }
+            if (L > 1) fft64(a, +1);
+            std::vector<cd> want(c.lout);
+            for (int k = 0; k < c.lout; k++) want[k] = a[L - c.lout + k] * (double)c.gain;
+            worst = std::max(worst, rel_err(want, out.data() + (size_t)(call_blocks * c.lout_prefix + (call_blk0 + b) * c.lout)));
+        }
+    /* nothing outside the slabs' [call_blk0, call_blk0 + nb) rows may have been written */
+    long stray = 0;
+    for (int i = 0; i < nchan; i++)
+        for (long b = 0; b < call_blocks; b++) {
+            if (b >= call_blk0 && b < call_blk0 + nb) continue;
+            const float2* r = out.data() + (size_t)(call_blocks * chans[i].lout_prefix + b * chans[i].lout);
+            for (int k = 0; k < chans[i].lout; k++) if (r[k].x != -9.f) stray++;
+        }
+    char name[128]; snprintf(name, sizeof name, "extract L=%d N=%d nchan=%d nb=%ld nphase=%d stray=%ld", L, N, nchan, nb, nphase, stray);
+    report(name, stray ? 1.0 : worst, 3e-6);
+}
+
+/* ---- activity-gated job list ---- */
+template <int L> static void check_jobs(int N, int njobs)
+{
+    constexpr int B = L >= 4096 ? 1 : 4096 / L;
+    typedef TileFFT<L, B, -1, false, false> ENG;
+    const int rows = 3;
+    std::vector<float2> spec((size_t)rows * N), hist((size_t)N), tables((size_t)4 * L);
+    for (auto& v : spec) { v.x = frand(); v.y = frand(); }
+    for (auto& v : hist) { v.x = frand(); v.y = frand(); }
+    for (auto& v : tables) { v.x = frand(); v.y = frand(); }
+    std::vector<ExtractJob> jobs(njobs);
+    long off = 0;
+    for (int i = 0; i < njobs; i++) {
+        jobs[i].row = (i % 4) - 1; jobs[i].start = (i * 37) % (N - L + 1); jobs[i].tab_off = (i % 4) * L; jobs[i].skip = L / 4;
+        jobs[i].dst_off = off; off += L - L / 4;
+    }
+    std::vector<float2> out((size_t)off);
+    const std::vector<float2> tw = pass_twiddles(L);
+    JobParams p; p.spec = spec.data(); p.spec_stride = N; p.hist = hist.data(); p.tables = tables.data(); p.jobs = jobs.data(); p.out = out.data(); p.njobs = njobs;
+    run_tiles<ENG>(JobTiles<L, B>{p}, (njobs + B - 1) / B, tw.data());
+    double worst = 0;
+    for (int i = 0; i < njobs; i++) {
+        const float2* src = (jobs[i].row < 0 ? hist.data() : spec.data() + (size_t)jobs[i].row * N) + jobs[i].start;
+        std::vector<cd> a(L);
+        for (int n = 0; n < L; n++) { const int m = (n + L / 2) % L; a[n] = cd(src[m].x, src[m].y) * cd(tables[jobs[i].tab_off + m].x, tables[jobs[i].tab_off + m].y); }
+        fft64(a, +1);
+        std::vector<cd> want(a.begin() + L / 4, a.end());
+        worst = std::max(worst, rel_err(want, out.data() + jobs[i].dst_off));
+    }
+    char name[128]; snprintf(name, sizeof name, "jobs L=%d N=%d njobs=%d", L, N, njobs);
+    report(name, worst, 3e-6);
+}
+
 int main()
 {
-    double w = 0;
-    w = std::max(w, check<2, 256, 1, false, false>());
-    w = std::max(w, check<4, 128, -1, false, false>());
-    w = std::max(w, check<8, 64, -1, false, false>());
-    w = std::max(w, check<16, 32, 1, false, false>());
-    w = std::max(w, check<32, 16, -1, false, false>());
-    w = std::max(w, check<64, 16, -1, false, false>());
-    w = std::max(w, check<128, 16, -1, false, false>());
-    w = std::max(w, check<256, 16, -1, false, false>());
-    w = std::max(w, check<256, 16, 1, true, true>());
-    w = std::max(w, check<256, 16, 1, false, true>());
-    w = std::max(w, check<512, 8, -1, false, false>());
-    w = std::max(w, check<512, 16, 1, true, true>());
-    w = std::max(w, check<1024, 4, 1, false, false>());
-    w = std::max(w, check<1024, 4, -1, false, false>());
-    w = std::max(w, check<2048, 2, 1, false, false>());
-    w = std::max(w, check<4096, 1, 1, false, false>());
-    w = std::max(w, check<4096, 1, -1, false, false>());
-    w = std::max(w, check<8192, 1, 1, false, false>());
-    w = std::max(w, check<16384, 1, 1, false, false>());
-    return w < 2e-6 ? 0 : 1;
+#define PL(LL) check_plain<LL, 1>(1); check_plain<LL, -1>(1); check_plain<LL, 1>(0); check_plain<LL, -1>(0);
+    PL(2) PL(4) PL(8) PL(16) PL(32) PL(64) PL(128) PL(256) PL(512) PL(1024) PL(2048) PL(4096) PL(8192) PL(16384)
+#undef PL
+    check_fwd_small<16>(4, 300); check_fwd_small<64>(16, 70); check_fwd_small<1024>(512, 9); check_fwd_small<4096>(1024, 3);
+    check_fwd_small<8192>(2048, 2); check_fwd_small<16384>(2048, 2); check_fwd_small<2048>(1536, 5);
+    check_fwd_big<128, 256>(8192, 2); check_fwd_big<256, 256>(16384, 2); check_fwd_big<256, 512>(32768, 1);
+    check_fwd_big<512, 512>(65536, 1); check_fwd_big<256, 256>(49152, 3);
+    check_extract<2>(64, 5, 3, 4); check_extract<8>(64, 7, 3, 4); check_extract<16>(256, 300, 2, 3); check_extract<64>(1024, 16, 5, 2);
+    check_extract<128>(4096, 70, 3, 4); check_extract<256>(8192, 64, 3, 4); check_extract<512>(8192, 19, 5, 4);
+    check_extract<1024>(4096, 5, 3, 4); check_extract<4096>(16384, 3, 2, 4); check_extract<8192>(16384, 2, 2, 8);
+    check_jobs<64>(1024, 70); check_jobs<512>(4096, 11); check_jobs<16>(256, 300);
+    printf("%s\n", g_fail ? "EMU FAILED" : "EMU OK");
+    return g_fail ? 1 : 0;
 }
