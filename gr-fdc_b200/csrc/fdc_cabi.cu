@@ -120,7 +120,7 @@ struct fdc_chan {
     cudaStream_t stream;
     /* device path: chunks alternate between NWORK worker streams, each with its own spectrum / intermediate ring, so
      * that the tail of one chunk's kernels overlaps the head of the next chunk's */
-    enum { NWORK = 2 };
+    enum { NWORK = 4 };
     cudaStream_t ws[NWORK];
     DevBuf w_spec[NWORK], w_mid[NWORK];
     cudaEvent_t ev_start, ev_done[NWORK];
@@ -339,7 +339,8 @@ int fdc_chan_work_device(fdc_chan* c, const void* d_in_v, long nblocks, void* d_
         if (e != cudaSuccess) return cuda_fail(e, "history staging copy");
     }
     /* worker streams (profiling serialises everything on the caller's stream so that the per-kernel events are clean) */
-    const int nw = (c->prof || tuning().streams < 2 || nblocks <= nh + c->chunk_blocks / 2) ? 1 : (int)fdc_chan::NWORK;
+    int nw = tuning().streams < 1 ? 1 : (tuning().streams > (int)fdc_chan::NWORK ? (int)fdc_chan::NWORK : tuning().streams);
+    if (c->prof || nblocks <= nh + c->chunk_blocks / 2) nw = 1;
     cudaStream_t wk[fdc_chan::NWORK];
     for (int i = 0; i < fdc_chan::NWORK; i++) wk[i] = nw == 1 ? s : c->ws[i];
     const long ring = std::min(nblocks, c->chunk_blocks);

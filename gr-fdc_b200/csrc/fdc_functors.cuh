@@ -108,25 +108,35 @@ template <int N1, int N2, int B> struct ColLoader {     /* signal = column n2, e
     template <int R, int STRIDE> FDC_HD float2 fetch(const Ctx& c, int t) const { return fdc_ldg(c + (long)t * STRIDE * N2); }
     template <int R, int STRIDE> FDC_HD float2 finish(const Ctx&, int, float2 raw) const { return raw; }
 };
+/* The four-step twiddles a column CTA needs are the same for every block (it keeps its column tile), so they are
+ * copied once into shared memory, laid out [t][butterfly] = exactly the order the last pass consumes them: every
+ * thread reads back only the 16 entries it wrote itself (conflict free, no barrier, nothing left in L1/L2 traffic). */
+template <int N1, int N2, int B> struct ColTwiddles {
+    template <int R, int NS> static FDC_HD void init_one(float2* tws, const float2* tw4, int ctile, int batch, int o)
+    {
+        const float2* src = tw4 + ((long)o * N2 + (ctile * B + batch));
+#pragma unroll
+        for (int t = 0; t < R; t++) tws[t * (NS * B) + o * B + batch] = fdc_ldg(src + (long)t * NS * N2);   /* NS * B butterflies per tile */
+    }
+};
 template <int N1, int N2, int B> struct ColStorer {
     struct Ctx { float2* col; const float2* tw; };
-    const BigParams& p; int ctile; long blk;
+    const BigParams& p; int ctile; long blk; const float2* tws;
     FDC_HD Ctx begin(int batch, int o) const
     {
-        const long off = (long)o * N2 + (ctile * B + batch);
-        Ctx c; c.col = p.mid + (blk * ((long)N1 * N2) + off); c.tw = p.tw4 + off;
+        Ctx c; c.col = p.mid + (blk * ((long)N1 * N2) + (long)o * N2 + (ctile * B + batch)); c.tw = tws + (o * B + batch);
         return c;
     }
     template <int R, int NS> FDC_HD void put(const Ctx& c, int t, float2 v) const
     {
-        c.col[(long)t * NS * N2] = cmul(v, fdc_ldg(c.tw + (long)t * NS * N2));
+        c.col[(long)t * NS * N2] = cmul(v, c.tw[t * (NS * B)]);
     }
 };
 template <int N1, int N2, int B> struct ColTiles {      /* tile = blk * (N2/B) + column tile */
-    const BigParams& p;
+    const BigParams& p; const float2* tws;
     FDC_HD int ninner() const { return N2 / B; }
     FDC_HD ColLoader<N1, N2, B> loader(TilePos t) const { return ColLoader<N1, N2, B>{p, t.inner, (long)t.outer}; }
-    FDC_HD ColStorer<N1, N2, B> storer(TilePos t) const { return ColStorer<N1, N2, B>{p, t.inner, (long)t.outer}; }
+    FDC_HD ColStorer<N1, N2, B> storer(TilePos t) const { return ColStorer<N1, N2, B>{p, t.inner, (long)t.outer, tws}; }
 };
 template <int N1, int N2, int B> struct RowLoader {     /* signal = row k1, element index = n2 */
     typedef const float2* Ctx;

@@ -24,13 +24,12 @@ template <int L, bool PF> static cudaError_t go_extract(const ExtractParams& p0,
 {
     constexpr int B = tile_batch(L);
     typedef TileFFT<L, B, -1, false, false> ENG;
-    FDC_CHECK(set_smem(k_extract<L, B, PF>, ENG::SMEM_BYTES));
     ExtractParams p = p0;
     p.ny = (p.nsel + B - 1) / B;
     const long ntiles = p.nb * p.ny;
     unsigned grid = 1;
-    FDC_CHECK(persistent_grid(k_extract<L, B, PF>, ENG::T, ENG::SMEM_BYTES, ntiles, 1, &grid));
-    k_extract<L, B, PF><<<grid, ENG::T, ENG::SMEM_BYTES, s>>>(p, twiddle_table(L), ntiles);
+    FDC_CHECK(persistent_grid(k_extract<L, B, PF>, ENG::T, tile_smem_bytes<ENG>(), ntiles, 1, &grid));
+    k_extract<L, B, PF><<<grid, ENG::T, tile_smem_bytes<ENG>(), s>>>(p, twiddle_table(L), ntiles);
     count_launch();
     return cudaGetLastError();
 }
@@ -45,11 +44,10 @@ template <int L> static cudaError_t go_jobs(const JobParams& p, cudaStream_t s)
 {
     constexpr int B = tile_batch(L);
     typedef TileFFT<L, B, -1, false, false> ENG;
-    FDC_CHECK(set_smem(k_jobs<L, B>, ENG::SMEM_BYTES));
     const long ntiles = ((long)p.njobs + B - 1) / B;
     unsigned grid = 1;
-    FDC_CHECK(persistent_grid(k_jobs<L, B>, ENG::T, ENG::SMEM_BYTES, ntiles, 1, &grid));
-    k_jobs<L, B><<<grid, ENG::T, ENG::SMEM_BYTES, s>>>(p, twiddle_table(L), ntiles);
+    FDC_CHECK(persistent_grid(k_jobs<L, B>, ENG::T, tile_smem_bytes<ENG>(), ntiles, 1, &grid));
+    k_jobs<L, B><<<grid, ENG::T, tile_smem_bytes<ENG>(), s>>>(p, twiddle_table(L), ntiles);
     count_launch();
     return cudaGetLastError();
 }

@@ -19,7 +19,11 @@ template <int N1, int N2, int B, bool PF>
 __global__ void __launch_bounds__((TileFFT<N1, B, 1, true, true>::T), min_ctas(TileFFT<N1, B, 1, true, true>::T, PF))
 k_fwd_cols(const BigParams p, const float2* __restrict__ tw, long ntiles)
 {
-    tile_kernel_body<TileFFT<N1, B, 1, true, true>, PF>(ColTiles<N1, N2, B>{p}, tw, ntiles);
+    typedef TileFFT<N1, B, 1, true, true> ENG;
+    /* the launcher rounds the grid to a multiple of the column tiles per block: this CTA keeps column tile blockIdx % (N2/B) */
+    float2* tws = reinterpret_cast<float2*>(fdc_smem_raw) + ENG::SMEM_ELEMS + tw_smem_elems(ENG::L);
+    ENG::template last_pass_init<ColTwiddles<N1, N2, B> >((int)threadIdx.x, tws, p.tw4, (int)(blockIdx.x % (N2 / B)));
+    tile_kernel_body<ENG, PF>(ColTiles<N1, N2, B>{p, tws}, tw, ntiles);
 }
 template <int N1, int N2, int B, bool PF>
 __global__ void __launch_bounds__((TileFFT<N2, B, 1, false, true>::T), min_ctas(TileFFT<N2, B, 1, false, true>::T, PF))
@@ -32,11 +36,10 @@ template <int N, bool PF> static cudaError_t go_small(const FwdParams& p, cudaSt
 {
     constexpr int B = tile_batch(N);
     typedef TileFFT<N, B, 1, false, false> ENG;
-    FDC_CHECK(set_smem(k_fwd_small<N, B, PF>, ENG::SMEM_BYTES));
     const long ntiles = (p.nblocks + B - 1) / B;
     unsigned grid = 1;
-    FDC_CHECK(persistent_grid(k_fwd_small<N, B, PF>, ENG::T, ENG::SMEM_BYTES, ntiles, 1, &grid));
-    k_fwd_small<N, B, PF><<<grid, ENG::T, ENG::SMEM_BYTES, s>>>(p, twiddle_table(N), ntiles);
+    FDC_CHECK(persistent_grid(k_fwd_small<N, B, PF>, ENG::T, tile_smem_bytes<ENG>(), ntiles, 1, &grid));
+    k_fwd_small<N, B, PF><<<grid, ENG::T, tile_smem_bytes<ENG>(), s>>>(p, twiddle_table(N), ntiles);
     count_launch();
     return cudaGetLastError();
 }
@@ -73,15 +76,14 @@ template <int N1, int N2, bool PF> static cudaError_t go_big(const BigParams& p,
     constexpr int BC = big_tile_batch(N1), BR = big_tile_batch(N2);
     typedef TileFFT<N1, BC, 1, true, true> CE;
     typedef TileFFT<N2, BR, 1, false, true> RE;
-    FDC_CHECK(set_smem(k_fwd_cols<N1, N2, BC, PF>, CE::SMEM_BYTES));
-    FDC_CHECK(set_smem(k_fwd_rows<N1, N2, BR, PF>, RE::SMEM_BYTES));
+    constexpr size_t csmem = tile_smem_bytes<CE>() + sizeof(float2) * 16 * CE::T;       /* exchange buffer + this CTA's four-step twiddles */
     const long ctiles = p.nblocks * (N2 / BC), rtiles = p.nblocks * (N1 / BR);
     unsigned gc = 1, gr = 1;
     /* a column CTA keeps its column tile: its slice of the four-step twiddle table stays in L1 */
-    FDC_CHECK(persistent_grid(k_fwd_cols<N1, N2, BC, PF>, CE::T, CE::SMEM_BYTES, ctiles, N2 / BC, &gc));
-    FDC_CHECK(persistent_grid(k_fwd_rows<N1, N2, BR, PF>, RE::T, RE::SMEM_BYTES, rtiles, 1, &gr));
-    k_fwd_cols<N1, N2, BC, PF><<<gc, CE::T, CE::SMEM_BYTES, s>>>(p, twiddle_table(N1), ctiles);
-    k_fwd_rows<N1, N2, BR, PF><<<gr, RE::T, RE::SMEM_BYTES, s>>>(p, twiddle_table(N2), rtiles);
+    FDC_CHECK(persistent_grid(k_fwd_cols<N1, N2, BC, PF>, CE::T, csmem, ctiles, N2 / BC, &gc));
+    FDC_CHECK(persistent_grid(k_fwd_rows<N1, N2, BR, PF>, RE::T, tile_smem_bytes<RE>(), rtiles, 1, &gr));
+    k_fwd_cols<N1, N2, BC, PF><<<gc, CE::T, csmem, s>>>(p, twiddle_table(N1), ctiles);
+    k_fwd_rows<N1, N2, BR, PF><<<gr, RE::T, tile_smem_bytes<RE>(), s>>>(p, twiddle_table(N2), rtiles);
     count_launch(2);
     return cudaGetLastError();
 }

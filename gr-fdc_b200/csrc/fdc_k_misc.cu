@@ -27,6 +27,28 @@ const Tuning& tuning()
     return t;
 }
 
+/* ---- launch geometry cache --------------------------------------------------------------------- */
+cudaError_t kernel_capacity(const void* kernel, int threads, size_t smem, int* capacity)
+{
+    static std::mutex m;
+    static std::map<std::pair<int, const void*>, int> cache;
+    int dev = 0;
+    FDC_CHECK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> g(m);
+    std::map<std::pair<int, const void*>, int>::iterator it = cache.find(std::make_pair(dev, kernel));
+    if (it != cache.end()) { *capacity = it->second; return cudaSuccess; }
+    int sms = 0, per_sm = 0;
+    if (smem > 48 * 1024) FDC_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FDC_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    FDC_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int lim = tuning().ctas_per_sm;
+    if (lim > 0 && per_sm > lim) per_sm = lim;
+    *capacity = sms * per_sm;
+    cache[std::make_pair(dev, kernel)] = *capacity;
+    return cudaSuccess;
+}
+
 /* ---- twiddle tables (per device, per length) ------------------------------------------------ */
 static std::mutex g_tw_mutex;
 static std::map<std::pair<int, long>, float2*> g_tw;      /* (device, key) -> device pointer */

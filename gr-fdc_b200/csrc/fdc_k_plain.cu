@@ -14,11 +14,10 @@ template <int L, int DIR> static cudaError_t go_plain(const PlainParams& p, cuda
 {
     constexpr int B = tile_batch(L);
     typedef TileFFT<L, B, DIR, false, false> ENG;
-    FDC_CHECK(set_smem(k_plain<L, B, DIR>, ENG::SMEM_BYTES));
     const long ntiles = (p.nvec + B - 1) / B;
     unsigned grid = 1;
-    FDC_CHECK(persistent_grid(k_plain<L, B, DIR>, ENG::T, ENG::SMEM_BYTES, ntiles, 1, &grid));
-    k_plain<L, B, DIR><<<grid, ENG::T, ENG::SMEM_BYTES, s>>>(p, twiddle_table(L), ntiles);
+    FDC_CHECK(persistent_grid(k_plain<L, B, DIR>, ENG::T, tile_smem_bytes<ENG>(), ntiles, 1, &grid));
+    k_plain<L, B, DIR><<<grid, ENG::T, tile_smem_bytes<ENG>(), s>>>(p, twiddle_table(L), ntiles);
     count_launch();
     return cudaGetLastError();
 }

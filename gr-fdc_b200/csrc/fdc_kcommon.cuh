@@ -20,28 +20,24 @@ constexpr bool can_prefetch(int threads) { return threads <= 512; }
 /* tile batch for a transform length: 4096-point tiles (256 threads), one signal per CTA above that */
 constexpr int tile_batch(int L) { return L >= 4096 ? 1 : 4096 / L; }
 
+/* dynamic shared memory of a tile kernel: exchange buffer + (small lengths) the twiddle table */
+template <class ENG> constexpr size_t tile_smem_bytes() { return sizeof(float2) * (size_t)(ENG::SMEM_ELEMS + tw_smem_elems(ENG::L)); }
+
 /* column / row tiles of the four-step kernels */
 constexpr int big_tile_batch(int L) { return L <= 256 ? 16 : 4096 / L; }
 
-template <class K> cudaError_t set_smem(K kernel, size_t bytes)
-{
-    if (bytes > 48 * 1024) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    return cudaSuccess;
-}
 #define FDC_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
 
 /* Persistent launch geometry: as many CTAs as are resident at once (occupancy x SM count), never more than there are
  * tiles; `multiple` > 1 rounds down to a multiple (a CTA then keeps the same inner tile index for its whole life). */
+/* resident CTAs of `kernel` on the current device (cached per device and kernel entry point; also opts the kernel in to
+ * its dynamic shared memory size).  Defined in fdc_k_misc.cu. */
+cudaError_t kernel_capacity(const void* kernel, int threads, size_t smem, int* capacity);
 template <class K> cudaError_t persistent_grid(K kernel, int threads, size_t smem, long ntiles, int multiple, unsigned* grid)
 {
-    int dev = 0, sms = 0, per_sm = 0;
-    FDC_CHECK(cudaGetDevice(&dev));
-    FDC_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    FDC_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
-    if (per_sm < 1) per_sm = 1;
-    const int cap = tuning().ctas_per_sm;
-    if (cap > 0 && per_sm > cap) per_sm = cap;
-    long g = (long)sms * per_sm;
+    int capacity = 0;
+    FDC_CHECK(kernel_capacity((const void*)kernel, threads, smem, &capacity));
+    long g = capacity;
     if (multiple > 1 && g >= multiple) g -= g % multiple;
     if (g > ntiles) g = ntiles;
     if (g < 1) g = 1;

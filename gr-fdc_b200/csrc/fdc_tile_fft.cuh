@@ -141,8 +141,21 @@ struct TileFFT {
         }
     }
 
+    /* per-CTA constants of the last pass (e.g. the four-step twiddles): Init::init_one<R, NS>(args..., batch, o) for every
+     * butterfly this thread owns in the last pass */
+    template <class Init, class... A> static FDC_HD void last_pass_init(int tid, A... args)
+    {
+        typedef Pass<NP - 1> PS;
+#pragma unroll
+        for (int u = 0; u < PS::U; u++) {
+            int batch, j; PS::map(tid, u, batch, j);
+            Init::template init_one<PS::R, PS::NS>(args..., batch, j);
+        }
+    }
+
     /* ---- butterflies ---------------------------------------------------------------------------------------- */
-    template <int P> static FDC_HD void twiddle_bfly(int tid, float2* v, const float2* tw)
+    /* TWS: tw points to a shared-memory copy of the table (plain loads); otherwise read-only global loads */
+    template <int P, bool TWS> static FDC_HD void twiddle_bfly(int tid, float2* v, const float2* tw)
     {
         typedef Pass<P> PS;
 #pragma unroll
@@ -152,7 +165,7 @@ struct TileFFT {
                 const float2* twp = tw + PS::TWOFF + (j % PS::NS);
 #pragma unroll
                 for (int t = 1; t < PS::R; t++) {
-                    const float2 w = fdc_ldg(twp + (t - 1) * PS::NS);
+                    const float2 w = TWS ? twp[(t - 1) * PS::NS] : fdc_ldg(twp + (t - 1) * PS::NS);
                     const float2 a = v[u * PS::R + t];
                     v[u * PS::R + t] = DIR > 0 ? make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x)
                                                : make_float2(a.x * w.x + a.y * w.y, a.y * w.x - a.x * w.y);
@@ -190,17 +203,17 @@ struct TileFFT {
     }
 
     /* one barrier-separated phase; v[16] is the calling thread's register tile and persists across phases.
-     * Phase 0 expects the raw fetched values in v. */
-    template <int PH, class Loader, class Storer>
-    static FDC_HD void phase(int tid, float2* v, float2* smem, const float2* tw, const Loader& ld, const Storer& st)
+     * Phase 0 expects the finished (fetch + finish) values in v. */
+    template <int PH, bool TWS, class Storer>
+    static FDC_HD void phase(int tid, float2* v, float2* smem, const float2* tw, const Storer& st)
     {
         if constexpr (NP == 1) {
-            finish(tid, v, ld); twiddle_bfly<0>(tid, v, tw); store_global<0>(tid, v, st);
+            twiddle_bfly<0, TWS>(tid, v, tw); store_global<0>(tid, v, st);
         } else if constexpr (PH == 0) {
-            finish(tid, v, ld); twiddle_bfly<0>(tid, v, tw); write_smem<0>(tid, v, smem);
+            twiddle_bfly<0, TWS>(tid, v, tw); write_smem<0>(tid, v, smem);
         } else if constexpr (PH % 2 == 1) {
             constexpr int P = (PH + 1) / 2;
-            read_smem<P>(tid, v, smem); twiddle_bfly<P>(tid, v, tw);
+            read_smem<P>(tid, v, smem); twiddle_bfly<P, TWS>(tid, v, tw);
             if constexpr (P == NP - 1) store_global<P>(tid, v, st);
         } else {
             constexpr int P = PH / 2;
@@ -210,22 +223,37 @@ struct TileFFT {
 };
 
 #if defined(__CUDACC__)
-/* device driver: run all phases of one tile with CTA barriers in between (v holds the fetched values) */
-template <class ENG, int PH, class Loader, class Storer>
-__device__ __forceinline__ void tile_fft_from(float2* v, float2* smem, const float2* tw, const Loader& ld, const Storer& st)
+/* twiddles are served from shared memory when the per-length table is small (<= 8 KB) */
+constexpr bool tw_in_smem(int L) { return fft_npasses(L) > 1 && fft_twsize(L) <= 1024; }
+constexpr int tw_smem_elems(int L) { return tw_in_smem(L) ? fft_twsize(L) : 0; }
+
+/* device driver: run all phases of one tile with CTA barriers in between (v holds the finished first-pass inputs) */
+template <class ENG, int PH, bool TWS, class Storer>
+__device__ __forceinline__ void tile_fft_from(float2* v, float2* smem, const float2* tw, const Storer& st)
 {
-    ENG::template phase<PH>(threadIdx.x, v, smem, tw, ld, st);
+    ENG::template phase<PH, TWS>(threadIdx.x, v, smem, tw, st);
     if constexpr (PH + 1 < ENG::NPH) {
         __syncthreads();
-        tile_fft_from<ENG, PH + 1, Loader, Storer>(v, smem, tw, ld, st);
+        tile_fft_from<ENG, PH + 1, TWS, Storer>(v, smem, tw, st);
     }
 }
 /* Persistent tile loop: the CTA walks tiles first, first + stride, ... < ntiles; with PF the global loads of tile
  * i+1 are issued before tile i is computed (register prefetch).  Tiles::loader(pos) / Tiles::storer(pos) make the
- * functors from the (inner, outer) split of the tile index, which is advanced without divisions. */
+ * functors from the (inner, outer) split of the tile index, which is advanced without divisions.
+ * Order inside an iteration: finish (the loader's own table loads + arithmetic) -> prefetch of the next tile ->
+ * butterflies.  The only global loads in flight during the butterflies are the prefetch: the twiddles come from
+ * shared memory, so no instruction waits on a scoreboard that it shares with a DRAM access. */
 template <class ENG, bool PF, class Tiles>
-__device__ __forceinline__ void tile_fft_loop(float2* smem, const float2* tw, const Tiles& tiles, long first, long stride, long ntiles)
+__device__ __forceinline__ void tile_fft_loop(float2* smem, const float2* tw_global, const Tiles& tiles, long first, long stride, long ntiles)
 {
+    constexpr bool TWS = tw_in_smem(ENG::L);
+    const float2* tw = tw_global;
+    if constexpr (TWS) {
+        float2* tws = smem + ENG::SMEM_ELEMS;
+        for (int i = threadIdx.x; i < fft_twsize(ENG::L); i += ENG::T) tws[i] = tw_global[i];
+        tw = tws;
+        __syncthreads();
+    }
     if (first >= ntiles) return;
     const int ninner = tiles.ninner();
     const TilePos step = tile_split(stride, ninner);
@@ -237,14 +265,18 @@ __device__ __forceinline__ void tile_fft_loop(float2* smem, const float2* tw, co
         const TilePos npos = tile_advance(pos, step, ninner);
         if constexpr (PF) {
             float2 nx[16];
+            ENG::finish(threadIdx.x, v, tiles.loader(pos));
+            asm volatile("" ::: "memory");
             if (next < ntiles) ENG::fetch(threadIdx.x, nx, tiles.loader(npos));
-            tile_fft_from<ENG, 0>(v, smem, tw, tiles.loader(pos), tiles.storer(pos));
+            asm volatile("" ::: "memory");
+            tile_fft_from<ENG, 0, TWS>(v, smem, tw, tiles.storer(pos));
             if (next >= ntiles) break;
 #pragma unroll
             for (int i = 0; i < 16; i++) v[i] = nx[i];
         } else {
             ENG::fetch(threadIdx.x, v, tiles.loader(pos));
-            tile_fft_from<ENG, 0>(v, smem, tw, tiles.loader(pos), tiles.storer(pos));
+            ENG::finish(threadIdx.x, v, tiles.loader(pos));
+            tile_fft_from<ENG, 0, TWS>(v, smem, tw, tiles.storer(pos));
             if (next >= ntiles) break;
         }
         tile = next; pos = npos;

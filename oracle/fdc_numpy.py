@@ -95,20 +95,23 @@ def psw_tables(blocksize, relinvovl, passbw, stopbw, wintype, exact=False):
     return t if exact else t.astype(np.complex64)
 
 
-def channelize(x, N, R, params, wintype, hist=None, counter0=None, want_spectrum=False):
+def channelize(x, N, R, params, wintype, hist=None, counter0=None, want_spectrum=False, ovl=None, shifts=None):
     """The hier block's chain for fixed channels (python/FrequencyDomainChannelizer.py:201-231, 284-315) in fp64.
 
     x: complex input stream; params: list of (f, l, lout, passbw, stopbw) from get_opt_channelparams.
     The table values are the reference's float32-rounded tables (they are inputs of the arithmetic, not results).
+    ovl / shifts generalise the hier block (which only wires ovl = N/R and shifts = f): a true sliding window of any
+    overlap with the per-block table advance given explicitly (used for the "true 75 % overlap" reading of config 4).
     Returns (list of per-channel output streams as complex128, spectrum[nblocks, N] or None)."""
-    ovl = N // R
+    ovl = N // R if ovl is None else int(ovl)
     blocks, _ = overlap_save(np.asarray(x, dtype=np.complex128), N, ovl, hist)
     spec = fft_vcc_forward_shift(blocks) / N
     nblocks = spec.shape[0]
     outs = []
     for ci, (f, l, lout, pb, sb) in enumerate(params):
         tables = psw_tables(l, R, pb, sb, wintype).astype(np.complex128)
-        shift = ((f % R) + R) % R                                            # shifts argument = f (:226), made positive (:58)
+        sh = f if shifts is None else shifts[ci]
+        shift = ((sh % R) + R) % R                                           # shifts argument = f (:226), made positive (:58)
         c0 = 0 if counter0 is None else counter0[ci]
         phase = (c0 + np.arange(nblocks) * shift) % R                         # counter = (counter + shift) % R (:82)
         seg = vector_cut(spec, f, l) * tables[phase]

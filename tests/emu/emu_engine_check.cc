@@ -50,7 +50,8 @@ static float frand() { return (float)rand() / RAND_MAX - 0.5f; }
 template <class ENG, int PH, class LD, class ST> struct Run {
     static void go(std::vector<std::array<float2, 16>>& regs, float2* smem, const float2* tw, const LD& ld, const ST& st)
     {
-        for (int tid = 0; tid < ENG::T; tid++) ENG::template phase<PH>(tid, regs[tid].data(), smem, tw, ld, st);
+        if (PH == 0) for (int tid = 0; tid < ENG::T; tid++) ENG::finish(tid, regs[tid].data(), ld);
+        for (int tid = 0; tid < ENG::T; tid++) ENG::template phase<PH, false>(tid, regs[tid].data(), smem, tw, st);
         if constexpr (PH + 1 < ENG::NPH) Run<ENG, PH + 1, LD, ST>::go(regs, smem, tw, ld, st);
     }
 };
@@ -154,7 +155,23 @@ template <int N1, int N2> static void check_fwd_big(int ovl, long nblocks)
     const std::vector<float2> twc = pass_twiddles(N1), twr = pass_twiddles(N2);
     BigParams p; p.in = buf.data() + ovl; p.mid = mid.data(); p.spec = spec.data(); p.tw4 = tw4.data(); p.nblocks = nblocks;
     p.hop = hop; p.ovl = ovl; p.scale = 1.0f / N;
-    run_tiles<CE>(ColTiles<N1, N2, BC>{p}, nblocks * (N2 / BC), twc.data());
+    /* a persistent column CTA keeps one column tile and its twiddle slice; the emulator walks all tiles with "one CTA",
+     * so the slice is rebuilt per column tile: run the tiles of one column tile at a time */
+    {
+        std::vector<float2> tws((size_t)16 * CE::T);
+        for (int ct = 0; ct < N2 / BC; ct++) {
+            for (int tid = 0; tid < CE::T; tid++) CE::template last_pass_init<ColTwiddles<N1, N2, BC> >(tid, tws.data(), (const float2*)tw4.data(), ct);
+            ColTiles<N1, N2, BC> tiles{p, tws.data()};
+            std::vector<float2> smem(CE::SMEM_ELEMS);
+            std::vector<std::array<float2, 16>> regs(CE::T);
+            for (long b = 0; b < nblocks; b++) {
+                TilePos pos; pos.inner = ct; pos.outer = (int)b;
+                auto ld = tiles.loader(pos); auto st = tiles.storer(pos);
+                for (int tid = 0; tid < CE::T; tid++) CE::fetch(tid, regs[tid].data(), ld);
+                Run<CE, 0, decltype(ld), decltype(st)>::go(regs, smem.data(), twc.data(), ld, st);
+            }
+        }
+    }
     run_tiles<RE>(RowTiles<N1, N2, BR>{p}, nblocks * (N1 / BR), twr.data());
     double worst = 0;
     for (long b = 0; b < nblocks; b++) {

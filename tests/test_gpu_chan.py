@@ -117,3 +117,66 @@ def test_device_path_equals_host_path(FDC):
     got = d_out.cpu().numpy().view(np.complex64)
     for i, (off, ln) in enumerate(g2.out_slices(nblocks)):
         assert np.array_equal(got[off:off + ln].view(np.uint8), outs[i].view(np.uint8))
+
+
+def test_golden_vectors_from_the_reference_build(FDC):
+    """committed outputs of the reference's own code (tests/golden, made by make_golden.py) -- no oracle library needed"""
+    import os
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    for name in ("chain_n1024_r4_hann", "chain_n512_r2_rect", "chain_n2048_r8_ramp"):
+        g = np.load(os.path.join(gold, name + ".npz"))
+        N, R, wintype, nblocks, seed = [int(v) for v in g["meta"]]
+        cfg = workloads.cfg_example(N, R, wintype)
+        assert [list(p[:3]) for p in cfg.params] == g["params"].tolist()
+        outs, spec = make_gpu_chain(FDC, cfg).work_host(g["x"], want_spectrum=True)
+        assert rel_l2(spec[:N], g["spectrum_first_block"]) < TOL and rel_l2(spec[-N:], g["spectrum_last_block"]) < TOL
+        for i, o in enumerate(outs):
+            assert rel_l2(o, g["out%d" % i]) < TOL, (name, i)
+
+
+@pytest.mark.parametrize("N,ovl", [(1024, 768), (1024, 640), (32768, 24576)])
+def test_sliding_window_overlap_above_half(FDC, N, ovl):
+    """overlap > 50 % (SURVEY 8d 'true 75 % overlap'): the reference's overlap_save cannot express it
+    (lib/overlap_save_impl.cc:74-78), the fp64 restatement with an explicit hop is the oracle"""
+    from oracle import fdc_numpy as fnp
+    cfg = workloads.ChanConfig("ovl_test", N, 4, workloads.example_channels(), workloads.HANN, ovl=ovl)
+    nblocks = 11
+    x = workloads.tones_input(cfg, nblocks * cfg.hop, seed=5)
+    want, wspec = fnp.channelize(x, cfg.N, cfg.R, cfg.params, cfg.windowtype, want_spectrum=True, ovl=ovl, shifts=cfg.shifts())
+    g = make_gpu_chain(FDC, cfg)
+    o1, s1 = g.work_host(x[:2 * cfg.hop], want_spectrum=True)        # fewer new samples than the overlap: history slides
+    o2, s2 = g.work_host(x[2 * cfg.hop:], want_spectrum=True)
+    assert rel_l2(np.concatenate([s1, s2]), wspec.reshape(-1)) < TOL
+    for i in range(cfg.nchan):
+        assert rel_l2(np.concatenate([o1[i], o2[i]]), want[i]) < TOL
+    # device path, same stream in three calls
+    import torch
+    g2 = make_gpu_chain(FDC, cfg)
+    d_in = torch.from_numpy(x.view(np.float32).copy()).cuda()
+    got = [[] for _ in range(cfg.nchan)]
+    pos = 0
+    for nb in (1, 3, nblocks - 4):
+        d_out = torch.empty(nb * cfg.out_per_block * 2, dtype=torch.float32, device="cuda")
+        g2.work_device(d_in.data_ptr() + 8 * pos * cfg.hop, nb, d_out.data_ptr(), 0, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        a = d_out.cpu().numpy().view(np.complex64)
+        for i, (off, ln) in enumerate(g2.out_slices(nb)):
+            got[i].append(a[off:off + ln])
+        pos += nb
+    for i in range(cfg.nchan):
+        assert rel_l2(np.concatenate(got[i]), want[i]) < TOL
+
+
+def test_time_sharded_equals_single_stream(FDC):
+    """SURVEY 8e on one GPU: the stream cut into per-rank runs (own halo, closed-form phase origin) gives bit-identical
+    channel outputs to one context fed the whole stream"""
+    from FDC import sharded
+    cfg = workloads.cfg2()
+    nblocks, world = 23, 4
+    x = workloads.tones_input(cfg, nblocks * cfg.hop, seed=9)
+    whole, _ = make_gpu_chain(FDC, cfg).work_host(x)
+    parts = [sharded.run_sharded(sharded.channelizer_worker(make_gpu_chain(FDC, cfg)), x, cfg.hop, cfg.ovl, nblocks, r, world)
+             for r in range(world)]
+    for i in range(cfg.nchan):
+        got = np.concatenate([p[i] for p in parts if p is not None])
+        assert np.array_equal(got.view(np.uint8), whole[i].view(np.uint8))
