@@ -241,11 +241,24 @@ def main():
     kern = {"forward_fft": {"ms": ms_fwd, "algorithmic_GB": in_bytes / 1e9, "GBps_algorithmic": in_bytes / ms_fwd / 1e6,
                             "GBps_incl_spectrum_write": (in_bytes + spec_bytes) / ms_fwd / 1e6},
             "channel_extract": {"ms": ms_ext, "algorithmic_GB": out_bytes / 1e9, "GBps_algorithmic": out_bytes / ms_ext / 1e6}}
-    dom = "forward_fft" if ms_fwd >= ms_ext else "channel_extract"
+    # forward_fft is ONE kernel for N <= 16384 and two (columns, rows) above; the dominant single kernel is the extract
+    # unless one forward kernel alone takes longer
+    fwd_kernels = 2 if cfg.N > 16384 else 1
+    dom = "forward_fft" if ms_fwd / fwd_kernels >= ms_ext else "channel_extract"
     ach = kern[dom]["GBps_algorithmic"]
+    kern[dom]["launches"] = int(chunks) * (fwd_kernels if dom == "forward_fft" else len(set(p[1] for p in cfg.params)))
+    kern[dom]["avg_launch_ms"] = kern[dom]["ms"] / max(1, kern[dom]["launches"])
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as fh:
+            tj = json.load(fh).get(cfg.name, {}).get(dom)
+        if tj:                                   # DRAM bytes of one launch = one chunk of blocks (ncu --set full capture, see profiles/)
+            traffic = tj["dram_bytes_per_block"] * min(nb, chan.chunk_blocks)
     path_gbs = value * 1e6 / world * cfg.bytes_per_sample() / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                "frac": ach / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": (out_bytes if dom == "channel_extract" else in_bytes) / max(1, int(chunks)),
                 "launches_per_step": launches / K, "kernels": kern,
                 "path": {"bytes_per_sample": cfg.bytes_per_sample(), "achieved": path_gbs, "frac": path_gbs / peaks["hbm_gbs"],
                          "frac_of_8TBps_nominal": path_gbs / 8000.0,

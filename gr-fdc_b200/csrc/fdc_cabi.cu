@@ -3,6 +3,7 @@
 #include "fdc_cabi_internal.h"
 #include <algorithm>
 #include <cstring>
+#include <cmath>
 #include <map>
 #include <string>
 
@@ -150,9 +151,9 @@ struct fdc_chan {
 
 static long pick_chunk_blocks(int N)
 {
-    /* spectrum ring of about 32 MiB per worker stream: with the (equally large) four-step intermediate the
+    /* spectrum ring of about 64 MiB per worker stream: with the (equally large) four-step intermediate the
      * K1 -> K2 hand-over mostly stays inside the 126 MB L2; never fewer than one wave of CTAs. */
-    long c = (32L << 20) / ((long)N * 8);
+    long c = (64L << 20) / ((long)N * 8);
     if (c < 8) c = 8;
     return c;
 }
@@ -200,7 +201,8 @@ fdc_chan* fdc_chan_create(int N, int ovl, int nphase, int nchan, const fdc_chan_
     cudaGetDevice(&c->dev);
     c->N = N; c->ovl = ovl; c->hop = N - ovl; c->nphase = nphase; c->nchan = nchan; c->blockcount = 0;
     c->big = false; c->N1 = c->N2 = 0;
-    if (!fwd_small_supported(N)) {
+    /* one CTA per block up to tuning().fwd_split (exclusive), the two-kernel four-step scheme from there on */
+    if (!fwd_small_supported(N) || (N >= tuning().fwd_split && fwd_big_supported(N, 0, 0))) {
         if (!fwd_big_supported(N, &c->N1, &c->N2)) { fail("fdc_chan_create: unsupported FFT length"); delete c; return 0; }
         c->big = true;
         c->tw4 = fourstep_table(c->N1, c->N2);
@@ -224,7 +226,13 @@ fdc_chan* fdc_chan_create(int N, int ovl, int nphase, int nchan, const fdc_chan_
         /* channels whose tables are bit-identical share one copy (equal-bandwidth channel plans have a single table,
          * which then lives in L1/L2 instead of being streamed once per channel) */
         const size_t tbytes = sizeof(float2) * (size_t)nphase * d.l;
-        const std::string key((const char*)d.table, tbytes);
+        /* a power-of-two gain (the hier block uses l) commutes exactly with every rounding of the chain, so it is folded
+         * into the device copy of the table and the kernel stores without a multiply */
+        int gexp = 0;
+        const bool fold = d.gain > 0.0f && std::frexp(d.gain, &gexp) == 0.5f && gexp > -60 && gexp < 60;
+        if (fold) cd.gain = 1.0f;
+        std::string key((const char*)d.table, tbytes);
+        key.append((const char*)&gexp, fold ? sizeof(gexp) : 0);
         std::map<std::string, long>::iterator hit = seen.find(key);
         if (hit != seen.end()) cd.tab_off = hit->second;
         else {
@@ -232,6 +240,7 @@ fdc_chan* fdc_chan_create(int N, int ovl, int nphase, int nchan, const fdc_chan_
             seen[key] = cd.tab_off;
             const float2* t = (const float2*)d.table;
             tables.insert(tables.end(), t, t + (size_t)nphase * d.l);
+            if (fold) for (size_t k = tables.size() - (size_t)nphase * d.l; k < tables.size(); k++) { tables[k].x *= d.gain; tables[k].y *= d.gain; }
         }
         c->chans.push_back(cd); c->l.push_back(d.l); by_l[d.l].push_back(i);
     }

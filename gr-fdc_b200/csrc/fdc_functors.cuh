@@ -207,9 +207,11 @@ template <int L, int B> struct ExtractLoader {
     }
     /* fft_vcc inverse+shift: FFT input n takes bin (n + l/2) mod l; n = j + t STRIDE, l/2 = (R/2) STRIDE */
     template <int R, int STRIDE> FDC_HD float2 fetch(const Ctx& c, int t) const { return fdc_ldg(c.x + ((t + R / 2) % R) * STRIDE); }
+    /* fused path: contracted complex multiply (2 FMUL + 2 FFMA); the stand-alone phase_shifting_windowing_vcc block and
+     * the activity-gated job path keep the VOLK-exact, uncontracted form */
     template <int R, int STRIDE> FDC_HD float2 finish(const Ctx& c, int t, float2 raw) const
     {
-        return cmul_exact(raw, fdc_ldg(c.w + ((t + R / 2) % R) * STRIDE));
+        return cmul(raw, fdc_ldg(c.w + ((t + R / 2) % R) * STRIDE));
     }
 };
 template <int L, int B> struct ExtractStorer {
@@ -225,9 +227,12 @@ template <int L, int B> struct ExtractStorer {
         c.dst = p.out + (p.call_blocks * ch.lout_prefix + (p.call_blk0 + b) * ch.lout - (L - ch.lout) + o);
         return c;
     }
-    template <int R, int NS> FDC_HD void put(const Ctx& c, int t, float2 v) const
+    /* gain 1 (a power-of-two gain is folded into the table at create time) skips the multiply: uniform branch per butterfly */
+    static constexpr bool HAS_VARIANT = true;
+    FDC_HD bool variant(const Ctx& c) const { return c.gain == 1.0f; }
+    template <int R, int NS, bool UNIT> FDC_HD void put(const Ctx& c, int t, float2 v) const
     {
-        if (t * NS >= c.skip) c.dst[t * NS] = make_float2(v.x * c.gain, v.y * c.gain);
+        if (t * NS >= c.skip) c.dst[t * NS] = UNIT ? v : make_float2(v.x * c.gain, v.y * c.gain);
     }
 };
 template <int L, int B> struct ExtractTiles {           /* tile = block * ny + channel tile */

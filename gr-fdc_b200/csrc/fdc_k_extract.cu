@@ -8,13 +8,21 @@
 namespace fdc {
 
 template <int L, int B, bool PF>
-__global__ void __launch_bounds__((TileFFT<L, B, -1, false, false>::T), min_ctas(TileFFT<L, B, -1, false, false>::T, PF))
+__global__ void __launch_bounds__((TileFFT<L, B, -1, false, false>::T), min_ctas(TileFFT<L, B, -1, false, false>::T, PF, L))
 k_extract(const ExtractParams p, const float2* __restrict__ tw, long ntiles)
 {
     tile_kernel_body<TileFFT<L, B, -1, false, false>, PF>(ExtractTiles<L, B>{p}, tw, ntiles);
 }
+/* 8 points per thread: tiles of 2048 points on 256 threads at <= 64 registers, four CTAs (32 warps) per SM instead of two
+ * CTAs (16 warps) -- the extract is latency bound, not bandwidth bound, so it is the warps in flight that count */
+template <int L, int B, bool PF>
+__global__ void __launch_bounds__(256, 4)
+k_extract8(const ExtractParams p, const float2* __restrict__ tw, long ntiles)
+{
+    tile_kernel_body<TileFFT<L, B, -1, false, false, 8>, PF>(ExtractTiles<L, B>{p}, tw, ntiles);
+}
 template <int L, int B>
-__global__ void __launch_bounds__((TileFFT<L, B, -1, false, false>::T), min_ctas(TileFFT<L, B, -1, false, false>::T, false))
+__global__ void __launch_bounds__((TileFFT<L, B, -1, false, false>::T), min_ctas(TileFFT<L, B, -1, false, false>::T, false, L))
 k_jobs(const JobParams p, const float2* __restrict__ tw, long ntiles)
 {
     tile_kernel_body<TileFFT<L, B, -1, false, false>, false>(JobTiles<L, B>{p}, tw, ntiles);
@@ -28,15 +36,31 @@ template <int L, bool PF> static cudaError_t go_extract(const ExtractParams& p0,
     p.ny = (p.nsel + B - 1) / B;
     const long ntiles = p.nb * p.ny;
     unsigned grid = 1;
-    FDC_CHECK(persistent_grid(k_extract<L, B, PF>, ENG::T, tile_smem_bytes<ENG>(), ntiles, 1, &grid));
-    k_extract<L, B, PF><<<grid, ENG::T, tile_smem_bytes<ENG>(), s>>>(p, twiddle_table(L), ntiles);
-    count_launch();
-    return cudaGetLastError();
+    FDC_CHECK(persistent_grid(k_extract<L, B, PF>, ENG::T, tile_smem_bytes<ENG>(), ntiles, 1, &grid, tuning().ctas_ext));
+    return launch_tile_kernel(k_extract<L, B, PF>, grid, ENG::T, tile_smem_bytes<ENG>(), s, p, twiddle_table(L), ntiles);
+}
+template <int L, bool PF> static cudaError_t go_extract8(const ExtractParams& p0, cudaStream_t s)
+{
+    constexpr int B = 2048 / L;
+    typedef TileFFT<L, B, -1, false, false, 8> ENG;
+    static_assert(ENG::T == 256, "2048-point tiles");
+    ExtractParams p = p0;
+    p.ny = (p.nsel + B - 1) / B;
+    const long ntiles = p.nb * p.ny;
+    unsigned grid = 1;
+    FDC_CHECK(persistent_grid(k_extract8<L, B, PF>, ENG::T, tile_smem_bytes<ENG>(), ntiles, 1, &grid));
+    return launch_tile_kernel(k_extract8<L, B, PF>, grid, ENG::T, tile_smem_bytes<ENG>(), s, p, twiddle_table(L, 8), ntiles);
 }
 template <int L> static cudaError_t go_extract_pf(const ExtractParams& p, cudaStream_t s)
 {
+    if constexpr (L >= 64 && L <= 2048) {
+        /* short slices have many signals per tile and little work per signal: twice the warps wins there (measured: l = 64
+         * 1.5x faster, l >= 256 10-20 % slower); FDC_EXTRACT_E8 = 0 / 1 forces either engine */
+        const int e8 = tuning().extract_e8;
+        if (e8 > 0 || (e8 < 0 && L <= 128)) return (tuning().prefetch & 2) ? go_extract8<L, true>(p, s) : go_extract8<L, false>(p, s);
+    }
     if constexpr (can_prefetch(TileFFT<L, tile_batch(L), -1, false, false>::T)) {
-        if (tuning().prefetch) return go_extract<L, true>(p, s);
+        if (tuning().prefetch & 2) return go_extract<L, true>(p, s);
     }
     return go_extract<L, false>(p, s);
 }
@@ -47,9 +71,7 @@ template <int L> static cudaError_t go_jobs(const JobParams& p, cudaStream_t s)
     const long ntiles = ((long)p.njobs + B - 1) / B;
     unsigned grid = 1;
     FDC_CHECK(persistent_grid(k_jobs<L, B>, ENG::T, tile_smem_bytes<ENG>(), ntiles, 1, &grid));
-    k_jobs<L, B><<<grid, ENG::T, tile_smem_bytes<ENG>(), s>>>(p, twiddle_table(L), ntiles);
-    count_launch();
-    return cudaGetLastError();
+    return launch_tile_kernel(k_jobs<L, B>, grid, ENG::T, tile_smem_bytes<ENG>(), s, p, twiddle_table(L), ntiles);
 }
 bool tile_len_supported(int L) { return L >= 2 && L <= 16384 && (L & (L - 1)) == 0; }
 

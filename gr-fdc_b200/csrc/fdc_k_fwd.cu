@@ -9,24 +9,24 @@
 namespace fdc {
 
 template <int N, int B, bool PF>
-__global__ void __launch_bounds__((TileFFT<N, B, 1, false, false>::T), min_ctas(TileFFT<N, B, 1, false, false>::T, PF))
+__global__ void __launch_bounds__((TileFFT<N, B, 1, false, false>::T), min_ctas(TileFFT<N, B, 1, false, false>::T, PF, N))
 k_fwd_small(const FwdParams p, const float2* __restrict__ tw, long ntiles)
 {
     tile_kernel_body<TileFFT<N, B, 1, false, false>, PF>(FwdTiles<N, B>{p}, tw, ntiles);
 }
 
 template <int N1, int N2, int B, bool PF>
-__global__ void __launch_bounds__((TileFFT<N1, B, 1, true, true>::T), min_ctas(TileFFT<N1, B, 1, true, true>::T, PF))
+__global__ void __launch_bounds__((TileFFT<N1, B, 1, true, true>::T), min_ctas(TileFFT<N1, B, 1, true, true>::T, PF, N1))
 k_fwd_cols(const BigParams p, const float2* __restrict__ tw, long ntiles)
 {
     typedef TileFFT<N1, B, 1, true, true> ENG;
     /* the launcher rounds the grid to a multiple of the column tiles per block: this CTA keeps column tile blockIdx % (N2/B) */
-    float2* tws = reinterpret_cast<float2*>(fdc_smem_raw) + ENG::SMEM_ELEMS + tw_smem_elems(ENG::L);
+    float2* tws = reinterpret_cast<float2*>(fdc_smem_raw) + ENG::SMEM_ELEMS + tw_smem_elems(ENG::L, ENG::E);
     ENG::template last_pass_init<ColTwiddles<N1, N2, B> >((int)threadIdx.x, tws, p.tw4, (int)(blockIdx.x % (N2 / B)));
     tile_kernel_body<ENG, PF>(ColTiles<N1, N2, B>{p, tws}, tw, ntiles);
 }
 template <int N1, int N2, int B, bool PF>
-__global__ void __launch_bounds__((TileFFT<N2, B, 1, false, true>::T), min_ctas(TileFFT<N2, B, 1, false, true>::T, PF))
+__global__ void __launch_bounds__((TileFFT<N2, B, 1, false, true>::T), min_ctas(TileFFT<N2, B, 1, false, true>::T, PF, N2))
 k_fwd_rows(const BigParams p, const float2* __restrict__ tw, long ntiles)
 {
     tile_kernel_body<TileFFT<N2, B, 1, false, true>, PF>(RowTiles<N1, N2, B>{p}, tw, ntiles);
@@ -39,14 +39,12 @@ template <int N, bool PF> static cudaError_t go_small(const FwdParams& p, cudaSt
     const long ntiles = (p.nblocks + B - 1) / B;
     unsigned grid = 1;
     FDC_CHECK(persistent_grid(k_fwd_small<N, B, PF>, ENG::T, tile_smem_bytes<ENG>(), ntiles, 1, &grid));
-    k_fwd_small<N, B, PF><<<grid, ENG::T, tile_smem_bytes<ENG>(), s>>>(p, twiddle_table(N), ntiles);
-    count_launch();
-    return cudaGetLastError();
+    return launch_tile_kernel(k_fwd_small<N, B, PF>, grid, ENG::T, tile_smem_bytes<ENG>(), s, p, twiddle_table(N), ntiles);
 }
 template <int N> static cudaError_t go_small_pf(const FwdParams& p, cudaStream_t s)
 {
     if constexpr (can_prefetch(TileFFT<N, tile_batch(N), 1, false, false>::T)) {
-        if (tuning().prefetch) return go_small<N, true>(p, s);
+        if (tuning().prefetch & 1) return go_small<N, true>(p, s);
     }
     return go_small<N, false>(p, s);
 }
@@ -80,17 +78,18 @@ template <int N1, int N2, bool PF> static cudaError_t go_big(const BigParams& p,
     const long ctiles = p.nblocks * (N2 / BC), rtiles = p.nblocks * (N1 / BR);
     unsigned gc = 1, gr = 1;
     /* a column CTA keeps its column tile: its slice of the four-step twiddle table stays in L1 */
-    FDC_CHECK(persistent_grid(k_fwd_cols<N1, N2, BC, PF>, CE::T, csmem, ctiles, N2 / BC, &gc));
-    FDC_CHECK(persistent_grid(k_fwd_rows<N1, N2, BR, PF>, RE::T, tile_smem_bytes<RE>(), rtiles, 1, &gr));
-    k_fwd_cols<N1, N2, BC, PF><<<gc, CE::T, csmem, s>>>(p, twiddle_table(N1), ctiles);
-    k_fwd_rows<N1, N2, BR, PF><<<gr, RE::T, tile_smem_bytes<RE>(), s>>>(p, twiddle_table(N2), rtiles);
-    count_launch(2);
-    return cudaGetLastError();
+    FDC_CHECK(persistent_grid(k_fwd_cols<N1, N2, BC, PF>, CE::T, csmem, ctiles, N2 / BC, &gc, tuning().ctas_fwd));
+    FDC_CHECK(persistent_grid(k_fwd_rows<N1, N2, BR, PF>, RE::T, tile_smem_bytes<RE>(), rtiles, 1, &gr, tuning().ctas_fwd));
+    FDC_CHECK(launch_tile_kernel(k_fwd_cols<N1, N2, BC, PF>, gc, CE::T, csmem, s, p, twiddle_table(N1), ctiles));
+    return launch_tile_kernel(k_fwd_rows<N1, N2, BR, PF>, gr, RE::T, tile_smem_bytes<RE>(), s, p, twiddle_table(N2), rtiles);
 }
 bool fwd_big_supported(int N, int* N1, int* N2)
 {
     int a = 0, b = 0;
     switch (N) {
+    case 4096: a = 64; b = 64; break;
+    case 8192: a = 64; b = 128; break;
+    case 16384: a = 128; b = 128; break;
     case 32768: a = 128; b = 256; break;
     case 65536: a = 256; b = 256; break;
     case 131072: a = 256; b = 512; break;
@@ -106,10 +105,10 @@ bool fwd_big_supported(int N, int* N1, int* N2)
 cudaError_t launch_fwd_big(const BigParams& p, int N, cudaStream_t s)
 {
     if (p.nblocks <= 0) return cudaSuccess;
-    const bool pf = tuning().prefetch != 0;
+    const bool pf = (tuning().prefetch & 1) != 0;
     switch (N) {
 #define X(NN, A, BB) case NN: return pf ? go_big<A, BB, true>(p, s) : go_big<A, BB, false>(p, s);
-    X(32768, 128, 256) X(65536, 256, 256) X(131072, 256, 512) X(262144, 512, 512) X(524288, 512, 1024) X(1048576, 1024, 1024)
+    X(4096, 64, 64) X(8192, 64, 128) X(16384, 128, 128) X(32768, 128, 256) X(65536, 256, 256) X(131072, 256, 512) X(262144, 512, 512) X(524288, 512, 1024) X(1048576, 1024, 1024)
 #undef X
     }
     return cudaErrorInvalidValue;

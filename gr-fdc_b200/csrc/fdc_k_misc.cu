@@ -23,12 +23,12 @@ static int env_int(const char* name, int dflt)
 }
 const Tuning& tuning()
 {
-    static const Tuning t = { env_int("FDC_PREFETCH", 1), env_int("FDC_CTAS_PER_SM", 0), env_int("FDC_STREAMS", 2) };
+    static const Tuning t = { env_int("FDC_PREFETCH", 1), env_int("FDC_CTAS_PER_SM", 0), env_int("FDC_STREAMS", 3), env_int("FDC_EXTRACT_E8", -1), env_int("FDC_CTAS_FWD", 0), env_int("FDC_CTAS_EXT", 0), env_int("FDC_PDL", 1), env_int("FDC_FWD_SPLIT", 32768) };
     return t;
 }
 
 /* ---- launch geometry cache --------------------------------------------------------------------- */
-cudaError_t kernel_capacity(const void* kernel, int threads, size_t smem, int* capacity)
+cudaError_t kernel_capacity(const void* kernel, int threads, size_t smem, int* capacity, int limit)
 {
     static std::mutex m;
     static std::map<std::pair<int, const void*>, int> cache;
@@ -42,7 +42,8 @@ cudaError_t kernel_capacity(const void* kernel, int threads, size_t smem, int* c
     FDC_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     FDC_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
     if (per_sm < 1) per_sm = 1;
-    const int lim = tuning().ctas_per_sm;
+    int lim = tuning().ctas_per_sm;
+    if (limit > 0 && (lim <= 0 || limit < lim)) lim = limit;
     if (lim > 0 && per_sm > lim) per_sm = lim;
     *capacity = sms * per_sm;
     cache[std::make_pair(dev, kernel)] = *capacity;
@@ -65,22 +66,22 @@ static float2* upload(const std::vector<float2>& h)
     if (cudaMemcpy(d, h.data(), sizeof(float2) * h.size(), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return 0; }
     return d;
 }
-static void host_pass_twiddles(int L, std::vector<float2>& h)
+static void host_pass_twiddles(int L, int E, std::vector<float2>& h)
 {
-    h.assign((size_t)fft_twsize(L), make_float2(1.f, 0.f));
-    const int np = fft_npasses(L);
+    h.assign((size_t)fft_twsize(L, E), make_float2(1.f, 0.f));
+    const int np = fft_npasses(L, E);
     for (int p = 1; p < np; p++) {
-        const int R = fft_radix(L, p), NS = fft_ns(L, p), off = fft_twoff(L, p);
+        const int R = fft_radix(L, p, E), NS = fft_ns(L, p, E), off = fft_twoff(L, p, E);
         for (int t = 1; t < R; t++)
             for (int k = 0; k < NS; k++) h[(size_t)(off + (t - 1) * NS + k)] = root((long)k * t, (long)NS * R);
     }
 }
-const float2* twiddle_table(int L)
+const float2* twiddle_table(int L, int E)
 {
     int dev = 0; cudaGetDevice(&dev);
     std::lock_guard<std::mutex> g(g_tw_mutex);
-    float2*& p = g_tw[std::make_pair(dev, (long)L)];
-    if (!p) { std::vector<float2> h; host_pass_twiddles(L < 1 ? 1 : L, h); p = upload(h); }
+    float2*& p = g_tw[std::make_pair(dev, (long)L * 64 + E)];
+    if (!p) { std::vector<float2> h; host_pass_twiddles(L < 1 ? 1 : L, E, h); p = upload(h); }
     return p;
 }
 const float2* fourstep_table(int N1, int N2)

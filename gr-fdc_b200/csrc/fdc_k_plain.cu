@@ -5,7 +5,7 @@
 namespace fdc {
 
 template <int L, int B, int DIR>
-__global__ void __launch_bounds__((TileFFT<L, B, DIR, false, false>::T), min_ctas(TileFFT<L, B, DIR, false, false>::T, false))
+__global__ void __launch_bounds__((TileFFT<L, B, DIR, false, false>::T), min_ctas(TileFFT<L, B, DIR, false, false>::T, false, L))
 k_plain(const PlainParams p, const float2* __restrict__ tw, long ntiles)
 {
     tile_kernel_body<TileFFT<L, B, DIR, false, false>, false>(PlainTiles<L, B, DIR>{p}, tw, ntiles);
@@ -17,9 +17,7 @@ template <int L, int DIR> static cudaError_t go_plain(const PlainParams& p, cuda
     const long ntiles = (p.nvec + B - 1) / B;
     unsigned grid = 1;
     FDC_CHECK(persistent_grid(k_plain<L, B, DIR>, ENG::T, tile_smem_bytes<ENG>(), ntiles, 1, &grid));
-    k_plain<L, B, DIR><<<grid, ENG::T, tile_smem_bytes<ENG>(), s>>>(p, twiddle_table(L), ntiles);
-    count_launch();
-    return cudaGetLastError();
+    return launch_tile_kernel(k_plain<L, B, DIR>, grid, ENG::T, tile_smem_bytes<ENG>(), s, p, twiddle_table(L), ntiles);
 }
 cudaError_t launch_plain_fft(const PlainParams& p, int L, int forward, cudaStream_t s)
 {

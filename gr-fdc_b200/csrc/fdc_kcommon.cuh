@@ -9,10 +9,11 @@ namespace fdc {
 extern __shared__ __align__(16) unsigned char fdc_smem_raw[];
 
 /* resident CTAs per SM the register allocator should aim for.  Prefetching kernels hold two register tiles
- * (32 + 32 floats) and get 128 registers: 2 CTAs of 256 threads or 1 of 512; kernels without prefetch 3 / 2 / 1. */
-constexpr int min_ctas(int threads, bool prefetch)
+ * (32 + 32 floats) and get 128 registers: 2 CTAs of 256 threads or 1 of 512; kernels without prefetch 4 / 2 / 1 (the 16-point register tile fits 64 registers). */
+constexpr int min_ctas(int threads, bool prefetch, int L = 0)
 {
-    return prefetch ? (threads <= 128 ? 4 : (threads <= 256 ? 2 : 1)) : (threads <= 256 ? 3 : (threads <= 512 ? 2 : 1));
+    return prefetch ? (threads <= 128 ? 4 : (threads <= 256 ? 2 : 1))
+                    : (L <= 1024 ? 4 : (threads <= 256 ? 2 : 1));       /* 3 passes fit 64 registers; 4 passes get 128 */
 }
 /* a 1024-thread CTA has 64 registers per thread: no room for a second register tile */
 constexpr bool can_prefetch(int threads) { return threads <= 512; }
@@ -21,10 +22,10 @@ constexpr bool can_prefetch(int threads) { return threads <= 512; }
 constexpr int tile_batch(int L) { return L >= 4096 ? 1 : 4096 / L; }
 
 /* dynamic shared memory of a tile kernel: exchange buffer + (small lengths) the twiddle table */
-template <class ENG> constexpr size_t tile_smem_bytes() { return sizeof(float2) * (size_t)(ENG::SMEM_ELEMS + tw_smem_elems(ENG::L)); }
+template <class ENG> constexpr size_t tile_smem_bytes() { return sizeof(float2) * (size_t)(ENG::SMEM_ELEMS + tw_smem_elems(ENG::L, ENG::E)); }
 
 /* column / row tiles of the four-step kernels */
-constexpr int big_tile_batch(int L) { return L <= 256 ? 16 : 4096 / L; }
+constexpr int big_tile_batch(int L) { return L < 256 ? 4096 / L : (L == 256 ? 16 : 4096 / L); }
 
 #define FDC_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
 
@@ -32,17 +33,33 @@ constexpr int big_tile_batch(int L) { return L <= 256 ? 16 : 4096 / L; }
  * tiles; `multiple` > 1 rounds down to a multiple (a CTA then keeps the same inner tile index for its whole life). */
 /* resident CTAs of `kernel` on the current device (cached per device and kernel entry point; also opts the kernel in to
  * its dynamic shared memory size).  Defined in fdc_k_misc.cu. */
-cudaError_t kernel_capacity(const void* kernel, int threads, size_t smem, int* capacity);
-template <class K> cudaError_t persistent_grid(K kernel, int threads, size_t smem, long ntiles, int multiple, unsigned* grid)
+cudaError_t kernel_capacity(const void* kernel, int threads, size_t smem, int* capacity, int limit);
+template <class K> cudaError_t persistent_grid(K kernel, int threads, size_t smem, long ntiles, int multiple, unsigned* grid, int limit = 0)
 {
     int capacity = 0;
-    FDC_CHECK(kernel_capacity((const void*)kernel, threads, smem, &capacity));
+    FDC_CHECK(kernel_capacity((const void*)kernel, threads, smem, &capacity, limit));
     long g = capacity;
     if (multiple > 1 && g >= multiple) g -= g % multiple;
     if (g > ntiles) g = ntiles;
     if (g < 1) g = 1;
     *grid = (unsigned)g;
     return cudaSuccess;
+}
+
+/* Launch of a tile kernel.  With programmatic dependent launch (sm_90+) the kernel may start while its predecessor in the
+ * stream is still draining: its prologue (twiddle tables into shared memory) overlaps the predecessor's tail and the
+ * launch latency; tile_fft_loop waits for the predecessor's results with cudaGridDependencySynchronize(). */
+template <class... KA, class... A>
+cudaError_t launch_tile_kernel(void (*kernel)(KA...), unsigned grid, int threads, size_t smem, cudaStream_t s, A... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = tuning().pdl ? 1 : 0;
+    count_launch();
+    return cudaLaunchKernelEx(&cfg, kernel, KA(args)...);
 }
 
 /* the body shared by all tile kernels: persistent loop with or without register prefetch */

@@ -10,13 +10,13 @@ namespace fdc {
 void count_launch(int n = 1);
 unsigned long long launch_count();
 
-/* run-time switches for measurements (environment: FDC_PREFETCH=0|1, FDC_CTAS_PER_SM=n, FDC_STREAMS=1|2) */
-struct Tuning { int prefetch; int ctas_per_sm; int streams; };
+/* run-time switches for measurements (environment: FDC_PREFETCH=bit 0 forward kernels | bit 1 extract kernels, FDC_CTAS_FWD / FDC_CTAS_EXT=n, FDC_CTAS_PER_SM=n, FDC_STREAMS=1..4, FDC_EXTRACT_E8=-1 (auto: slices <= 128) | 0 | 1, FDC_PDL=0|1, FDC_FWD_SPLIT=N) */
+struct Tuning { int prefetch; int ctas_per_sm; int streams; int extract_e8; int ctas_fwd; int ctas_ext; int pdl; int fwd_split; };
 const Tuning& tuning();
 
 /* per-pass Stockham twiddles of a length-L tile FFT (layout of fdc_tile_fft.cuh: pass p at fft_twoff(L, p), entry
  * [(t-1)*Ns + k] = exp(-2 pi i k t / (Ns R))), on the current device (cached per device and L) */
-const float2* twiddle_table(int L);
+const float2* twiddle_table(int L, int E = 16);
 /* four-step twiddles W_N^{n2 k1} laid out [k1][n2] (N = N1*N2 entries) */
 const float2* fourstep_table(int N1, int N2);
 

@@ -1,7 +1,7 @@
 /* fdc_tile_fft.cuh -- CTA-level batched complex-fp32 FFT ("tile FFT").
  *
- * One CTA transforms a tile of B independent length-L signals (B*L = 16*T elements, T threads,
- * 16 elements per thread held in registers).  Stockham autosort passes with register radix-16/8/4/2
+ * One CTA transforms a tile of B independent length-L signals (B*L = E*T elements, T threads,
+ * E = 16 (or 8) elements per thread held in registers).  Stockham autosort passes with register radix-16/8/4/2
  * butterflies; between passes the tile is exchanged through shared memory (in place: read all ->
  * barrier -> write all -> barrier).  The first pass takes its operands from global memory through a
  * Loader functor (overlap-save addressing, table multiply, half swap ... are fused there), the last
@@ -31,65 +31,75 @@
 
 namespace fdc {
 
-constexpr int fft_npasses(int L)
+/* Radix plan of a length-L transform with E points per thread: the first pass has radix E (the thread's whole register
+ * tile is one butterfly), the rest of L/E is split into radices <= E with the larger radix last (fewer store contexts per
+ * thread in the pass that talks to global memory). */
+constexpr int fft_next_radix(int rem, int E)
 {
-    if (L <= 16) return 1;
-    int n = 1, rem = L / 16;
-    while (rem > 1) {
-        if (rem >= 64 || rem == 16) rem /= 16;
-        else if (rem == 32) rem /= 4;
-        else rem = 1;
-        n++;
-    }
+    if (rem >= 64 || rem == E) return E;
+    if (rem == 32) return 4;                            /* 32 = 4 * 8 */
+    if (rem == 16) return 4;                            /* only reached for E = 8: 16 = 4 * 4 */
+    return rem;
+}
+constexpr int fft_npasses(int L, int E = 16)
+{
+    if (L <= E) return 1;
+    int n = 1, rem = L / E;
+    while (rem > 1) { rem /= fft_next_radix(rem, E); n++; }
     return n;
 }
-constexpr int fft_radix(int L, int p)
+constexpr int fft_radix(int L, int p, int E = 16)
 {
-    if (L <= 16) return L;
-    if (p == 0) return 16;
-    int rem = L / 16, q = 1, r = 1;
+    if (L <= E) return L;
+    if (p == 0) return E;
+    int rem = L / E, q = 1, r = 1;
     while (true) {
-        if (rem >= 64 || rem == 16) r = 16;
-        else if (rem == 32) r = 4;                    /* 32 = 4 * 8: the larger radix last, fewer store contexts per thread */
-        else r = rem;
+        r = fft_next_radix(rem, E);
         if (q == p) return r;
         rem /= r; q++;
     }
 }
-constexpr int fft_ns(int L, int p)
+constexpr int fft_ns(int L, int p, int E = 16)
 {
     int ns = 1;
-    for (int q = 0; q < p; q++) ns *= fft_radix(L, q);
+    for (int q = 0; q < p; q++) ns *= fft_radix(L, q, E);
     return ns;
 }
 /* offset of pass p's twiddles inside the per-length table, and the table's size (float2 units) */
-constexpr int fft_twoff(int L, int p)
+constexpr int fft_twoff(int L, int p, int E = 16)
 {
     int off = 0;
-    for (int q = 1; q < p; q++) off += (fft_radix(L, q) - 1) * fft_ns(L, q);
+    for (int q = 1; q < p; q++) off += (fft_radix(L, q, E) - 1) * fft_ns(L, q, E);
     return off;
 }
-constexpr int fft_twsize(int L) { const int n = fft_twoff(L, fft_npasses(L)); return n < 1 ? 1 : n; }
+constexpr int fft_twsize(int L, int E = 16) { const int n = fft_twoff(L, fft_npasses(L, E), E); return n < 1 ? 1 : n; }
 constexpr int ilog2(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
 
-template <int L_, int B_, int DIR, bool LOAD_BF, bool STORE_BF>
+/* storers may offer two code paths for a whole butterfly (e.g. unit gain): detected by a HAS_VARIANT member */
+template <class S, class = void> struct storer_has_variant { static constexpr bool value = false; };
+template <class S> struct storer_has_variant<S, decltype((void)S::HAS_VARIANT)> { static constexpr bool value = S::HAS_VARIANT; };
+
+template <int L_, int B_, int DIR, bool LOAD_BF, bool STORE_BF, int E_ = 16>
 struct TileFFT {
-    static constexpr int L = L_, B = B_, E = 16;
+    static constexpr int L = L_, B = B_, E = E_;               /* E points per thread (16, or 8 for twice the warps) */
     static constexpr int T = L * B / E;                       /* threads per CTA */
-    static constexpr int NP = fft_npasses(L);
+    static constexpr int NP = fft_npasses(L, E);
     static constexpr int NPH = NP == 1 ? 1 : 2 * NP - 2;       /* barrier-separated phases */
-    static constexpr int LP = L >= 32 ? ((L + L / 16) | 1) : L;
+    static constexpr int PADW = L < E ? L : E;                 /* first-pass radix = run a thread writes in exchange 0 */
+    static constexpr int LP = L >= 2 * E ? ((L + L / PADW) | 1) : L;
     static constexpr int SMEM_ELEMS = NP == 1 ? 1 : B * LP;    /* float2 units */
     static constexpr size_t SMEM_BYTES = sizeof(float2) * SMEM_ELEMS;
-    static_assert(L * B >= 16 * 32 && (L * B) % (16 * 32) == 0, "tile must fill whole warps");
+    static constexpr int TWSIZE = fft_twsize(L, E);
+    static_assert(E == 16 || E == 8, "8 or 16 points per thread");
+    static_assert(L * B >= E * 32 && (L * B) % (E * 32) == 0, "tile must fill whole warps");
     static_assert(T <= 1024, "tile too large for one CTA");
 
     template <int P> struct Pass {
-        static constexpr int R = fft_radix(L, P);
-        static constexpr int NS = fft_ns(L, P);
+        static constexpr int R = fft_radix(L, P, E);
+        static constexpr int NS = fft_ns(L, P, E);
         static constexpr int NBF = L / R;                     /* butterflies per signal */
         static constexpr int U = E / R;                       /* butterflies per thread */
-        static constexpr int TWOFF = fft_twoff(L, P);
+        static constexpr int TWOFF = fft_twoff(L, P, E);
         static constexpr bool BF = (P == 0 && LOAD_BF) || (P == NP - 1 && STORE_BF);
         static FDC_HD void map(int tid, int u, int& batch, int& j)
         {
@@ -99,10 +109,10 @@ struct TileFFT {
         }
     };
     /* physical smem slot of logical position pos of signal batch in exchange e (= written by pass e) */
-    template <int EX> static FDC_HD int phys(int batch, int pos) { return batch * LP + pos + (EX == 0 ? (pos >> 4) : 0); }
-    /* the same for pos + c with a compile-time c: returns the constant to add to phys(batch, pos) (c % 16 == 0 or EX > 0,
-     * or pos % 16 == 0 and c < 16) */
-    template <int EX> static constexpr int phys_step(int c) { return c + (EX == 0 ? c / 16 : 0); }
+    template <int EX> static FDC_HD int phys(int batch, int pos) { return batch * LP + pos + (EX == 0 ? (pos >> ilog2(PADW)) : 0); }
+    /* the same for pos + c with a compile-time c: returns the constant to add to phys(batch, pos) (c % PADW == 0 or EX > 0,
+     * or pos % PADW == 0 and c < PADW) */
+    template <int EX> static constexpr int phys_step(int c) { return c + (EX == 0 ? c / PADW : 0); }
 
     /* ---- global side --------------------------------------------------------------------------------------- */
     template <class Loader> static FDC_HD void fetch(int tid, float2* raw, const Loader& ld)
@@ -136,8 +146,18 @@ struct TileFFT {
             int batch, j; PS::map(tid, u, batch, j);
             /* last pass: NS * R == L, hence k == j and the outputs are j + t*NS */
             const typename Storer::Ctx c = st.begin(batch, j);
+            if constexpr (storer_has_variant<Storer>::value) {
+                if (st.variant(c)) {
 #pragma unroll
-            for (int t = 0; t < PS::R; t++) st.template put<PS::R, PS::NS>(c, t, v[u * PS::R + t]);
+                    for (int t = 0; t < PS::R; t++) st.template put<PS::R, PS::NS, true>(c, t, v[u * PS::R + t]);
+                } else {
+#pragma unroll
+                    for (int t = 0; t < PS::R; t++) st.template put<PS::R, PS::NS, false>(c, t, v[u * PS::R + t]);
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < PS::R; t++) st.template put<PS::R, PS::NS>(c, t, v[u * PS::R + t]);
+            }
         }
     }
 
@@ -179,7 +199,7 @@ struct TileFFT {
     template <int P> static FDC_HD void read_smem(int tid, float2* v, const float2* smem)
     {
         typedef Pass<P> PS;
-        static_assert(PS::NBF % 16 == 0, "exchange reads need a 16-aligned butterfly stride");
+        static_assert(P > 1 || PS::NBF % PADW == 0, "reads of the padded first exchange need a PADW-aligned butterfly stride");
 #pragma unroll
         for (int u = 0; u < PS::U; u++) {
             int batch, j; PS::map(tid, u, batch, j);
@@ -224,8 +244,8 @@ struct TileFFT {
 
 #if defined(__CUDACC__)
 /* twiddles are served from shared memory when the per-length table is small (<= 8 KB) */
-constexpr bool tw_in_smem(int L) { return fft_npasses(L) > 1 && fft_twsize(L) <= 1024; }
-constexpr int tw_smem_elems(int L) { return tw_in_smem(L) ? fft_twsize(L) : 0; }
+constexpr bool tw_in_smem(int L, int E = 16) { return fft_npasses(L, E) > 1 && fft_twsize(L, E) <= 1024; }
+constexpr int tw_smem_elems(int L, int E = 16) { return tw_in_smem(L, E) ? fft_twsize(L, E) : 0; }
 
 /* device driver: run all phases of one tile with CTA barriers in between (v holds the finished first-pass inputs) */
 template <class ENG, int PH, bool TWS, class Storer>
@@ -246,25 +266,29 @@ __device__ __forceinline__ void tile_fft_from(float2* v, float2* smem, const flo
 template <class ENG, bool PF, class Tiles>
 __device__ __forceinline__ void tile_fft_loop(float2* smem, const float2* tw_global, const Tiles& tiles, long first, long stride, long ntiles)
 {
-    constexpr bool TWS = tw_in_smem(ENG::L);
+    constexpr bool TWS = tw_in_smem(ENG::L, ENG::E);
     const float2* tw = tw_global;
+    /* programmatic dependent launch: let the next kernel of the stream start its prologue now, run ours (constant tables
+     * only), then wait until the previous kernel's results are complete and visible */
+    cudaTriggerProgrammaticLaunchCompletion();
     if constexpr (TWS) {
         float2* tws = smem + ENG::SMEM_ELEMS;
-        for (int i = threadIdx.x; i < fft_twsize(ENG::L); i += ENG::T) tws[i] = tw_global[i];
+        for (int i = threadIdx.x; i < ENG::TWSIZE; i += ENG::T) tws[i] = tw_global[i];
         tw = tws;
         __syncthreads();
     }
+    cudaGridDependencySynchronize();
     if (first >= ntiles) return;
     const int ninner = tiles.ninner();
     const TilePos step = tile_split(stride, ninner);
     TilePos pos = tile_split(first, ninner);
-    float2 v[16];
+    float2 v[ENG::E];
     if (PF) ENG::fetch(threadIdx.x, v, tiles.loader(pos));
     for (long tile = first;;) {
         const long next = tile + stride;
         const TilePos npos = tile_advance(pos, step, ninner);
         if constexpr (PF) {
-            float2 nx[16];
+            float2 nx[ENG::E];
             ENG::finish(threadIdx.x, v, tiles.loader(pos));
             asm volatile("" ::: "memory");
             if (next < ntiles) ENG::fetch(threadIdx.x, nx, tiles.loader(npos));
@@ -272,7 +296,7 @@ __device__ __forceinline__ void tile_fft_loop(float2* smem, const float2* tw_glo
             tile_fft_from<ENG, 0, TWS>(v, smem, tw, tiles.storer(pos));
             if (next >= ntiles) break;
 #pragma unroll
-            for (int i = 0; i < 16; i++) v[i] = nx[i];
+            for (int i = 0; i < ENG::E; i++) v[i] = nx[i];
         } else {
             ENG::fetch(threadIdx.x, v, tiles.loader(pos));
             ENG::finish(threadIdx.x, v, tiles.loader(pos));

@@ -12,11 +12,11 @@
 using namespace fdc;
 typedef std::complex<double> cd;
 
-static std::vector<float2> pass_twiddles(int L)
+static std::vector<float2> pass_twiddles(int L, int E = 16)
 {
-    std::vector<float2> h((size_t)fft_twsize(L), make_float2(1.f, 0.f));
-    for (int p = 1; p < fft_npasses(L); p++) {
-        const int R = fft_radix(L, p), NS = fft_ns(L, p), off = fft_twoff(L, p);
+    std::vector<float2> h((size_t)fft_twsize(L, E), make_float2(1.f, 0.f));
+    for (int p = 1; p < fft_npasses(L, E); p++) {
+        const int R = fft_radix(L, p, E), NS = fft_ns(L, p, E), off = fft_twoff(L, p, E);
         for (int t = 1; t < R; t++)
             for (int k = 0; k < NS; k++) {
                 const double a = -2.0 * M_PI * (double)(((long)k * t) % ((long)NS * R)) / ((double)NS * R);
@@ -141,7 +141,7 @@ template <int N> static void check_fwd_small(int ovl, long nblocks)
 template <int N1, int N2> static void check_fwd_big(int ovl, long nblocks)
 {
     constexpr int N = N1 * N2;
-    constexpr int BC = N1 <= 256 ? 16 : 4096 / N1, BR = N2 <= 256 ? 16 : 4096 / N2;
+    constexpr int BC = N1 == 256 ? 16 : 4096 / N1, BR = N2 == 256 ? 16 : 4096 / N2;
     typedef TileFFT<N1, BC, 1, true, true> CE;
     typedef TileFFT<N2, BR, 1, false, true> RE;
     const int hop = N - ovl;
@@ -187,10 +187,10 @@ template <int N1, int N2> static void check_fwd_big(int ovl, long nblocks)
 }
 
 /* ---- K2: channel tiles, shared tables, phase selection, overlap discard, gain ---- */
-template <int L> static void check_extract(int N, int nchan, long nb, int nphase)
+template <int L, int E = 16> static void check_extract(int N, int nchan, long nb, int nphase)
 {
-    constexpr int B = L >= 4096 ? 1 : 4096 / L;
-    typedef TileFFT<L, B, -1, false, false> ENG;
+    constexpr int B = E == 8 ? 2048 / L : (L >= 4096 ? 1 : 4096 / L);
+    typedef TileFFT<L, B, -1, false, false, E> ENG;
     std::vector<float2> spec((size_t)nb * N), tables((size_t)2 * nphase * L);
     for (auto& v : spec) { v.x = frand(); v.y = frand(); }
     for (auto& v : tables) { v.x = frand(); v.y = frand(); }
@@ -204,7 +204,7 @@ template <int L> static void check_extract(int N, int nchan, long nb, int nphase
         prefix += c.lout;
     }
     std::vector<float2> out((size_t)(call_blocks * prefix), make_float2(-9.f, -9.f));
-    const std::vector<float2> tw = pass_twiddles(L);
+    const std::vector<float2> tw = pass_twiddles(L, E);
     ExtractParams p; p.spec = spec.data(); p.spec_stride = N; p.tables = tables.data(); p.chans = chans.data();
     p.nsel = nchan; p.ny = (nchan + B - 1) / B; p.out = out.data(); p.nb = nb; p.call_blocks = call_blocks; p.call_blk0 = call_blk0;
     p.glob_phase0 = glob_phase0; p.nphase = nphase;
@@ -233,7 +233,7 @@ template <int L> static void check_extract(int N, int nchan, long nb, int nphase
             const float2* r = out.data() + (size_t)(call_blocks * chans[i].lout_prefix + b * chans[i].lout);
             for (int k = 0; k < chans[i].lout; k++) if (r[k].x != -9.f) stray++;
         }
-    char name[128]; snprintf(name, sizeof name, "extract L=%d N=%d nchan=%d nb=%ld nphase=%d stray=%ld", L, N, nchan, nb, nphase, stray);
+    char name[128]; snprintf(name, sizeof name, "extract L=%d E=%d N=%d nchan=%d nb=%ld nphase=%d stray=%ld", L, E, N, nchan, nb, nphase, stray);
     report(name, stray ? 1.0 : worst, 3e-6);
 }
 
@@ -277,11 +277,14 @@ int main()
 #undef PL
     check_fwd_small<16>(4, 300); check_fwd_small<64>(16, 70); check_fwd_small<1024>(512, 9); check_fwd_small<4096>(1024, 3);
     check_fwd_small<8192>(2048, 2); check_fwd_small<16384>(2048, 2); check_fwd_small<2048>(1536, 5);
+    check_fwd_big<64, 64>(1024, 3); check_fwd_big<64, 128>(2048, 3); check_fwd_big<128, 128>(4096, 2);
     check_fwd_big<128, 256>(8192, 2); check_fwd_big<256, 256>(16384, 2); check_fwd_big<256, 512>(32768, 1);
     check_fwd_big<512, 512>(65536, 1); check_fwd_big<256, 256>(49152, 3);
     check_extract<2>(64, 5, 3, 4); check_extract<8>(64, 7, 3, 4); check_extract<16>(256, 300, 2, 3); check_extract<64>(1024, 16, 5, 2);
     check_extract<128>(4096, 70, 3, 4); check_extract<256>(8192, 64, 3, 4); check_extract<512>(8192, 19, 5, 4);
     check_extract<1024>(4096, 5, 3, 4); check_extract<4096>(16384, 3, 2, 4); check_extract<8192>(16384, 2, 2, 8);
+    check_extract<64, 8>(1024, 16, 5, 2); check_extract<128, 8>(4096, 70, 3, 4); check_extract<256, 8>(8192, 64, 3, 4);
+    check_extract<512, 8>(8192, 19, 5, 4); check_extract<1024, 8>(4096, 5, 3, 4); check_extract<2048, 8>(8192, 3, 2, 4);
     check_jobs<64>(1024, 70); check_jobs<512>(4096, 11); check_jobs<16>(256, 300);
     printf("%s\n", g_fail ? "EMU FAILED" : "EMU OK");
     return g_fail ? 1 : 0;

@@ -1,0 +1,30 @@
+"""GPU parity of the kernel variants behind the run-time switches (FDC_PREFETCH, FDC_EXTRACT_E8, FDC_FWD_SPLIT, FDC_STREAMS,
+FDC_PDL).  The switches are read once per process, so every variant runs the parity tests of test_gpu_chan.py in a
+subprocess with its environment."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+VARIANTS = {
+    "no_prefetch_one_stream_no_pdl": {"FDC_PREFETCH": "0", "FDC_STREAMS": "1", "FDC_PDL": "0"},
+    "prefetch_everywhere_four_streams": {"FDC_PREFETCH": "3", "FDC_STREAMS": "4"},
+    "extract_8_points_per_thread": {"FDC_EXTRACT_E8": "1"},
+    "extract_8_points_per_thread_prefetch": {"FDC_EXTRACT_E8": "1", "FDC_PREFETCH": "3"},
+    "four_step_from_4096": {"FDC_FWD_SPLIT": "4096"},
+    "one_cta_per_sm": {"FDC_CTAS_PER_SM": "1"},
+}
+
+
+@pytest.mark.parametrize("name", sorted(VARIANTS))
+def test_variant_parity(name):
+    env = dict(os.environ); env.update(VARIANTS[name])
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_chan.py"), "-m", "gpu", "-x", "-q",
+                        "-k", "golden or chain_matches or sliding or device_path or time_sharded"],
+                       env=env, capture_output=True, text=True, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+    assert " passed" in r.stdout
