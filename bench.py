@@ -171,6 +171,8 @@ def main():
     torch.cuda.set_device(local)
     FDC._cabi.check(FDC._cabi.lib().fdc_set_device(local))
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"            # keep NCCL's version banner off stdout: ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     L = FDC._cabi.lib()
@@ -267,7 +269,7 @@ def main():
     # ---- e2e: host buffers through the C ABI ----
     e2e = None
     if not args.no_e2e:
-        nb_e = min(nb, max(64, int((64 << 20) / (8.0 * cfg.hop))))            # 64 MiB of input per step
+        nb_e = nb                                                              # the same batch as the device-resident step
         nbytes_in = 8 * nb_e * cfg.hop; nbytes_out = 8 * nb_e * cfg.out_per_block
         import ctypes
         h_in = L.fdc_host_alloc(nbytes_in); h_out = L.fdc_host_alloc(nbytes_out)
@@ -294,7 +296,7 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * EK * nb_e * cfg.hop / float(tt.item()) / 1e6, "unit": "Msamples/s",
                "h2d_bytes_per_step": nbytes_in, "d2h_bytes_per_step": nbytes_out, "steps": EK, "blocks_per_step": nb_e,
-               "api": "fdc_chan_work_host (pinned host in/out, 3-slot H2D/compute/D2H pipeline)"}
+               "api": "fdc_chan_work_host (pinned host in/out, 4-slot H2D/compute/D2H pipeline)"}
         L.fdc_host_free(h_in); L.fdc_host_free(h_out)
 
     # ---- optional: NCCL gather of the channel outputs to the sink rank ----

@@ -126,7 +126,7 @@ struct fdc_chan {
     DevBuf w_spec[NWORK], w_mid[NWORK];
     cudaEvent_t ev_start, ev_done[NWORK];
     /* host path: NSLOT pipelined chunk slots */
-    enum { NSLOT = 3 };
+    enum { NSLOT = 4 };
     cudaStream_t hs[NSLOT];
     DevBuf h_in[NSLOT], h_out[NSLOT], h_spec[NSLOT], h_mid[NSLOT];
     long host_chunk;
@@ -436,7 +436,11 @@ int fdc_chan_work_host(fdc_chan* c, const void* in_v, long nblocks, void* const*
     if (nblocks < 0) return fail("nblocks < 0");
     if (nblocks == 0) return 0;
     const float2* in = (const float2*)in_v; float2* spectrum = (float2*)spectrum_v;
-    const long chunk = std::min(nblocks, c->chunk_blocks);
+    /* PCIe is the bound here, not the kernels: small chunks (about tuning().host_chunk_mb MiB of input each) keep the copy
+     * engines of both directions busy from the first to the last millisecond of the call */
+    long chunk = ((long)tuning().host_chunk_mb << 20) / ((long)c->hop * (long)sizeof(float2));
+    if (chunk < 4) chunk = 4;
+    chunk = std::min(nblocks, std::min(chunk, c->chunk_blocks));
     cudaError_t e = cudaSuccess;
     for (int i = 0; i < fdc_chan::NSLOT; i++) {
         if (!c->hs[i] && (e = cudaStreamCreateWithFlags(&c->hs[i], cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "stream");

@@ -64,7 +64,7 @@ def cfg4(true_overlap=False):
 
 def cfg5_fixed():
     """FFT 262144, 4096 narrow channels (all active) -- throughput reading of config 5."""
-    ch = [((i + 0.5) / 4096.0 - 0.5, 40.0 / 262144.0) for i in range(4096)]
+    ch = [((i + 0.5) / 4096.0 - 0.5, 1.0 / 4096.0) for i in range(4096)]          # 64-bin raster: l = 128, lout = 96 (SURVEY 8a)
     return ChanConfig("cfg5_fft262144_r4_4096ch", 262144, 4, ch, HANN)
 
 
