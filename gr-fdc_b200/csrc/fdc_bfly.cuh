@@ -84,11 +84,35 @@ template <int DIR> FDC_HD void dft16(float2* x)
 #undef FDC_SWAP
 }
 
+/* radix 32 = two radix-16 transforms of the even / odd inputs, recombined with W32^k (decimation in time) */
+template <int DIR> FDC_HD void dft32(float2* x)
+{
+    float2 e[16], o[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) { e[i] = x[2 * i]; o[i] = x[2 * i + 1]; }
+    dft16<DIR>(e); dft16<DIR>(o);
+    /* cos / sin of 2 pi k / 32, k = 1..7 */
+    const float c[8] = { 1.0f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f, 0.70710678118654752440f,
+                         0.55557023301960222474f, 0.38268343236508977173f, 0.19509032201612826785f };
+    const float sn[8] = { 0.0f, 0.19509032201612826785f, 0.38268343236508977173f, 0.55557023301960222474f, 0.70710678118654752440f,
+                          0.83146961230254523708f, 0.92387953251128675613f, 0.98078528040323044913f };
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        float2 t;
+        if (k == 0) t = o[0];
+        else if (k == 8) t = rot4<DIR>(o[8]);
+        else if (k < 8) t = mulc<DIR>(o[k], c[k], sn[k]);                  /* W32^k = c -/+ j s */
+        else t = mulc<DIR>(o[k], -sn[k - 8], c[k - 8]);                      /* W32^k, k > 8: cos = -sin(k-8), sin = cos(k-8) */
+        x[k] = cadd(e[k], t); x[k + 16] = csub(e[k], t);
+    }
+}
+
 template <int R, int DIR> struct Bfly;
 template <int DIR> struct Bfly<2, DIR> { static FDC_HD void run(float2* x) { dft2<DIR>(x[0], x[1]); } };
 template <int DIR> struct Bfly<4, DIR> { static FDC_HD void run(float2* x) { dft4<DIR>(x[0], x[1], x[2], x[3]); } };
 template <int DIR> struct Bfly<8, DIR> { static FDC_HD void run(float2* x) { dft8<DIR>(x); } };
 template <int DIR> struct Bfly<16, DIR> { static FDC_HD void run(float2* x) { dft16<DIR>(x); } };
+template <int DIR> struct Bfly<32, DIR> { static FDC_HD void run(float2* x) { dft32<DIR>(x); } };
 
 }  // namespace fdc
 #endif

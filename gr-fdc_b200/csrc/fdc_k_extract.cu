@@ -21,6 +21,14 @@ k_extract8(const ExtractParams p, const float2* __restrict__ tw, long ntiles)
 {
     tile_kernel_body<TileFFT<L, B, -1, false, false, 8>, PF>(ExtractTiles<L, B>{p}, tw, ntiles);
 }
+/* 32 points per thread (512 = 16 * 32, 1024 = 32 * 32): one shared-memory exchange instead of two; the extract is limited by
+ * the L1/shared-memory pipe, so the exchange it does not do is the saving.  128 threads, 4 CTAs per SM. */
+template <int L, int B>
+__global__ void __launch_bounds__(128, 4)
+k_extract32(const ExtractParams p, const float2* __restrict__ tw, long ntiles)
+{
+    tile_kernel_body<TileFFT<L, B, -1, false, false, 32>, false>(ExtractTiles<L, B>{p}, tw, ntiles);
+}
 template <int L, int B>
 __global__ void __launch_bounds__((TileFFT<L, B, -1, false, false>::T), min_ctas(TileFFT<L, B, -1, false, false>::T, false, L))
 k_jobs(const JobParams p, const float2* __restrict__ tw, long ntiles)
@@ -51,8 +59,23 @@ template <int L, bool PF> static cudaError_t go_extract8(const ExtractParams& p0
     FDC_CHECK(persistent_grid(k_extract8<L, B, PF>, ENG::T, tile_smem_bytes<ENG>(), ntiles, 1, &grid));
     return launch_tile_kernel(k_extract8<L, B, PF>, grid, ENG::T, tile_smem_bytes<ENG>(), s, p, twiddle_table(L, 8), ntiles);
 }
+template <int L> static cudaError_t go_extract32(const ExtractParams& p0, cudaStream_t s)
+{
+    constexpr int B = 4096 / L;
+    typedef TileFFT<L, B, -1, false, false, 32> ENG;
+    static_assert(ENG::T == 128, "4096-point tiles on 128 threads");
+    ExtractParams p = p0;
+    p.ny = (p.nsel + B - 1) / B;
+    const long ntiles = p.nb * p.ny;
+    unsigned grid = 1;
+    FDC_CHECK(persistent_grid(k_extract32<L, B>, ENG::T, tile_smem_bytes<ENG>(), ntiles, 1, &grid, tuning().ctas_ext));
+    return launch_tile_kernel(k_extract32<L, B>, grid, ENG::T, tile_smem_bytes<ENG>(), s, p, twiddle_table(L, 32), ntiles);
+}
 template <int L> static cudaError_t go_extract_pf(const ExtractParams& p, cudaStream_t s)
 {
+    if constexpr (L == 512 || L == 1024) {
+        if (tuning().extract_e32) return go_extract32<L>(p, s);
+    }
     if constexpr (L >= 64 && L <= 2048) {
         /* short slices have many signals per tile and little work per signal: twice the warps wins there (measured: l = 64
          * 1.5x faster, l >= 256 10-20 % slower); FDC_EXTRACT_E8 = 0 / 1 forces either engine */

@@ -15,23 +15,40 @@ k_fwd_small(const FwdParams p, const float2* __restrict__ tw, long ntiles)
     tile_kernel_body<TileFFT<N, B, 1, false, false>, PF>(FwdTiles<N, B>{p}, tw, ntiles);
 }
 
-template <int N1, int N2, int B, bool PF>
-__global__ void __launch_bounds__((TileFFT<N1, B, 1, true, true>::T), min_ctas(TileFFT<N1, B, 1, true, true>::T, PF, N1))
+/* E = 32 (lengths 512 / 1024: two passes instead of three) runs without prefetch on 128 threads, four CTAs per SM */
+template <int N1, int N2, int B, bool PF, int E>
+__global__ void __launch_bounds__((TileFFT<N1, B, 1, true, true, E>::T), E == 32 ? 4 : min_ctas(TileFFT<N1, B, 1, true, true, E>::T, PF, N1))
 k_fwd_cols(const BigParams p, const float2* __restrict__ tw, long ntiles)
 {
-    typedef TileFFT<N1, B, 1, true, true> ENG;
+    typedef TileFFT<N1, B, 1, true, true, E> ENG;
     /* the launcher rounds the grid to a multiple of the column tiles per block: this CTA keeps column tile blockIdx % (N2/B) */
     float2* tws = reinterpret_cast<float2*>(fdc_smem_raw) + ENG::SMEM_ELEMS + tw_smem_elems(ENG::L, ENG::E);
     ENG::template last_pass_init<ColTwiddles<N1, N2, B> >((int)threadIdx.x, tws, p.tw4, (int)(blockIdx.x % (N2 / B)));
     tile_kernel_body<ENG, PF>(ColTiles<N1, N2, B>{p, tws}, tw, ntiles);
 }
-template <int N1, int N2, int B, bool PF>
-__global__ void __launch_bounds__((TileFFT<N2, B, 1, false, true>::T), min_ctas(TileFFT<N2, B, 1, false, true>::T, PF, N2))
+template <int N1, int N2, int B, bool PF, int E>
+__global__ void __launch_bounds__((TileFFT<N2, B, 1, false, true, E>::T), E == 32 ? 4 : min_ctas(TileFFT<N2, B, 1, false, true, E>::T, PF, N2))
 k_fwd_rows(const BigParams p, const float2* __restrict__ tw, long ntiles)
 {
-    tile_kernel_body<TileFFT<N2, B, 1, false, true>, PF>(RowTiles<N1, N2, B>{p}, tw, ntiles);
+    tile_kernel_body<TileFFT<N2, B, 1, false, true, E>, PF>(RowTiles<N1, N2, B>{p}, tw, ntiles);
 }
 
+/* 32 points per thread where that saves a pass: 512 / 1024 (two instead of three), 8192 / 16384 (three instead of four) */
+template <int N, int B>
+__global__ void __launch_bounds__(N * B / 32, N * B / 32 <= 128 ? 4 : (N * B / 32 <= 256 ? 2 : 1))
+k_fwd_small32(const FwdParams p, const float2* __restrict__ tw, long ntiles)
+{
+    tile_kernel_body<TileFFT<N, B, 1, false, false, 32>, false>(FwdTiles<N, B>{p}, tw, ntiles);
+}
+template <int N> static cudaError_t go_small32(const FwdParams& p, cudaStream_t s)
+{
+    constexpr int B = tile_batch(N);
+    typedef TileFFT<N, B, 1, false, false, 32> ENG;
+    const long ntiles = (p.nblocks + B - 1) / B;
+    unsigned grid = 1;
+    FDC_CHECK(persistent_grid(k_fwd_small32<N, B>, ENG::T, tile_smem_bytes<ENG>(), ntiles, 1, &grid, tuning().ctas_fwd));
+    return launch_tile_kernel(k_fwd_small32<N, B>, grid, ENG::T, tile_smem_bytes<ENG>(), s, p, twiddle_table(N, 32), ntiles);
+}
 template <int N, bool PF> static cudaError_t go_small(const FwdParams& p, cudaStream_t s)
 {
     constexpr int B = tile_batch(N);
@@ -58,30 +75,38 @@ cudaError_t launch_fwd_small(const FwdParams& p, cudaStream_t s)
     case 64: return go_small_pf<64>(p, s);
     case 128: return go_small_pf<128>(p, s);
     case 256: return go_small_pf<256>(p, s);
-    case 512: return go_small_pf<512>(p, s);
-    case 1024: return go_small_pf<1024>(p, s);
+    case 512: return tuning().fwd_e32 > 1 ? go_small32<512>(p, s) : go_small_pf<512>(p, s);     /* measured: no gain at 1024 */
+    case 1024: return tuning().fwd_e32 > 1 ? go_small32<1024>(p, s) : go_small_pf<1024>(p, s);
     case 2048: return go_small_pf<2048>(p, s);
     case 4096: return go_small_pf<4096>(p, s);
-    case 8192: return go_small_pf<8192>(p, s);
-    case 16384: return go_small_pf<16384>(p, s);
+    case 8192: return tuning().fwd_e32 ? go_small32<8192>(p, s) : go_small_pf<8192>(p, s);
+    case 16384: return tuning().fwd_e32 ? go_small32<16384>(p, s) : go_small_pf<16384>(p, s);
     }
     return cudaErrorInvalidValue;
 }
 
-template <int N1, int N2, bool PF> static cudaError_t go_big(const BigParams& p, cudaStream_t s)
+constexpr int big_points(int L, bool e32) { return (e32 && (L == 512 || L == 1024)) ? 32 : 16; }     /* points per thread of a column / row transform */
+template <int N1, int N2, bool PF, bool E32 = true> static cudaError_t go_big(const BigParams& p, cudaStream_t s)
 {
+    if constexpr (E32 && (N1 >= 512 || N2 >= 512)) {
+        /* measured on cfg5 (512 x 512): 16 points + prefetch 60 Gsample/s, 32 points without prefetch 52: these kernels
+         * are bandwidth bound, the prefetch counts for more than the saved pass.  FDC_FWD_E32=2 selects the 32-point form. */
+        if (tuning().fwd_e32 < 2) return go_big<N1, N2, PF, false>(p, s);
+    }
     /* 16 adjacent columns / rows (128-byte lines) while the tile fits 256 threads, narrower tiles above that */
     constexpr int BC = big_tile_batch(N1), BR = big_tile_batch(N2);
-    typedef TileFFT<N1, BC, 1, true, true> CE;
-    typedef TileFFT<N2, BR, 1, false, true> RE;
-    constexpr size_t csmem = tile_smem_bytes<CE>() + sizeof(float2) * 16 * CE::T;       /* exchange buffer + this CTA's four-step twiddles */
+    constexpr int EC = big_points(N1, E32), ER = big_points(N2, E32);
+    constexpr bool PFC = PF && EC == 16, PFR = PF && ER == 16;
+    typedef TileFFT<N1, BC, 1, true, true, EC> CE;
+    typedef TileFFT<N2, BR, 1, false, true, ER> RE;
+    constexpr size_t csmem = tile_smem_bytes<CE>() + sizeof(float2) * (size_t)N1 * BC;   /* exchange buffer + this CTA's four-step twiddles */
     const long ctiles = p.nblocks * (N2 / BC), rtiles = p.nblocks * (N1 / BR);
     unsigned gc = 1, gr = 1;
-    /* a column CTA keeps its column tile: its slice of the four-step twiddle table stays in L1 */
-    FDC_CHECK(persistent_grid(k_fwd_cols<N1, N2, BC, PF>, CE::T, csmem, ctiles, N2 / BC, &gc, tuning().ctas_fwd));
-    FDC_CHECK(persistent_grid(k_fwd_rows<N1, N2, BR, PF>, RE::T, tile_smem_bytes<RE>(), rtiles, 1, &gr, tuning().ctas_fwd));
-    FDC_CHECK(launch_tile_kernel(k_fwd_cols<N1, N2, BC, PF>, gc, CE::T, csmem, s, p, twiddle_table(N1), ctiles));
-    return launch_tile_kernel(k_fwd_rows<N1, N2, BR, PF>, gr, RE::T, tile_smem_bytes<RE>(), s, p, twiddle_table(N2), rtiles);
+    /* a column CTA keeps its column tile and with it its slice of the four-step twiddle table */
+    FDC_CHECK(persistent_grid(k_fwd_cols<N1, N2, BC, PFC, EC>, CE::T, csmem, ctiles, N2 / BC, &gc, tuning().ctas_fwd));
+    FDC_CHECK(persistent_grid(k_fwd_rows<N1, N2, BR, PFR, ER>, RE::T, tile_smem_bytes<RE>(), rtiles, 1, &gr, tuning().ctas_fwd));
+    FDC_CHECK(launch_tile_kernel(k_fwd_cols<N1, N2, BC, PFC, EC>, gc, CE::T, csmem, s, p, twiddle_table(N1, EC), ctiles));
+    return launch_tile_kernel(k_fwd_rows<N1, N2, BR, PFR, ER>, gr, RE::T, tile_smem_bytes<RE>(), s, p, twiddle_table(N2, ER), rtiles);
 }
 bool fwd_big_supported(int N, int* N1, int* N2)
 {

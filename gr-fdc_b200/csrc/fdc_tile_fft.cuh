@@ -41,8 +41,15 @@ constexpr int fft_next_radix(int rem, int E)
     if (rem == 16) return 4;                            /* only reached for E = 8: 16 = 4 * 4 */
     return rem;
 }
+/* E = 32 saves one pass (= one shared-memory exchange) where the length allows it:
+ * 512 = 16 * 32, 1024 = 32 * 32 (2 passes instead of 3), 8192 = 32 * 16 * 16, 16384 = 32 * 16 * 32 (3 instead of 4) */
+constexpr int fft_radix32(int L, int p)
+{
+    return L == 512 ? (p == 0 ? 16 : 32) : L == 1024 ? 32 : L == 8192 ? (p == 0 ? 32 : 16) : (p == 1 ? 16 : 32);
+}
 constexpr int fft_npasses(int L, int E = 16)
 {
+    if (E == 32) return L <= 1024 ? 2 : 3;
     if (L <= E) return 1;
     int n = 1, rem = L / E;
     while (rem > 1) { rem /= fft_next_radix(rem, E); n++; }
@@ -50,6 +57,7 @@ constexpr int fft_npasses(int L, int E = 16)
 }
 constexpr int fft_radix(int L, int p, int E = 16)
 {
+    if (E == 32) return fft_radix32(L, p);
     if (L <= E) return L;
     if (p == 0) return E;
     int rem = L / E, q = 1, r = 1;
@@ -85,12 +93,12 @@ struct TileFFT {
     static constexpr int T = L * B / E;                       /* threads per CTA */
     static constexpr int NP = fft_npasses(L, E);
     static constexpr int NPH = NP == 1 ? 1 : 2 * NP - 2;       /* barrier-separated phases */
-    static constexpr int PADW = L < E ? L : E;                 /* first-pass radix = run a thread writes in exchange 0 */
-    static constexpr int LP = L >= 2 * E ? ((L + L / PADW) | 1) : L;
+    static constexpr int PADW = fft_radix(L, 0, E);            /* first-pass radix = run a thread writes in exchange 0 */
+    static constexpr int LP = NP > 1 ? ((L + L / PADW) | 1) : L;
     static constexpr int SMEM_ELEMS = NP == 1 ? 1 : B * LP;    /* float2 units */
     static constexpr size_t SMEM_BYTES = sizeof(float2) * SMEM_ELEMS;
     static constexpr int TWSIZE = fft_twsize(L, E);
-    static_assert(E == 16 || E == 8, "8 or 16 points per thread");
+    static_assert(E == 16 || E == 8 || (E == 32 && (L == 512 || L == 1024 || L == 8192 || L == 16384)), "8, 16 or (selected lengths) 32 points per thread");
     static_assert(L * B >= E * 32 && (L * B) % (E * 32) == 0, "tile must fill whole warps");
     static_assert(T <= 1024, "tile too large for one CTA");
 

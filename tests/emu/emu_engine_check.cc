@@ -48,7 +48,7 @@ static float frand() { return (float)rand() / RAND_MAX - 0.5f; }
 
 /* run one tile through all phases */
 template <class ENG, int PH, class LD, class ST> struct Run {
-    static void go(std::vector<std::array<float2, 16>>& regs, float2* smem, const float2* tw, const LD& ld, const ST& st)
+    static void go(std::vector<std::array<float2, 32>>& regs, float2* smem, const float2* tw, const LD& ld, const ST& st)
     {
         if (PH == 0) for (int tid = 0; tid < ENG::T; tid++) ENG::finish(tid, regs[tid].data(), ld);
         for (int tid = 0; tid < ENG::T; tid++) ENG::template phase<PH, false>(tid, regs[tid].data(), smem, tw, st);
@@ -58,7 +58,7 @@ template <class ENG, int PH, class LD, class ST> struct Run {
 template <class ENG, class Tiles> static void run_tiles(const Tiles& tiles, long ntiles, const float2* tw)
 {
     std::vector<float2> smem(ENG::SMEM_ELEMS);
-    std::vector<std::array<float2, 16>> regs(ENG::T);
+    std::vector<std::array<float2, 32>> regs(ENG::T);
     /* walk the tiles like a persistent CTA does: a stride that is not a multiple of ninner exercises tile_advance */
     const int ninner = tiles.ninner();
     const long stride = 3;
@@ -114,14 +114,14 @@ template <int L, int DIR> static void check_plain(int shift)
 }
 
 /* ---- K1 small: overlap addressing, shift, scale ---- */
-template <int N> static void check_fwd_small(int ovl, long nblocks)
+template <int N, int E = 16> static void check_fwd_small(int ovl, long nblocks)
 {
     constexpr int B = N >= 4096 ? 1 : 4096 / N;
-    typedef TileFFT<N, B, 1, false, false> ENG;
+    typedef TileFFT<N, B, 1, false, false, E> ENG;
     const int hop = N - ovl;
     std::vector<float2> buf((size_t)ovl + (size_t)nblocks * hop), spec((size_t)nblocks * N);
     for (auto& v : buf) { v.x = frand(); v.y = frand(); }
-    const std::vector<float2> tw = pass_twiddles(N);
+    const std::vector<float2> tw = pass_twiddles(N, E);
     FwdParams p; p.in = buf.data() + ovl; p.spec = spec.data(); p.nblocks = nblocks; p.hop = hop; p.ovl = ovl; p.N = N; p.scale = 1.0f / N;
     run_tiles<ENG>(FwdTiles<N, B>{p}, (nblocks + B - 1) / B, tw.data());
     double worst = 0;
@@ -133,7 +133,7 @@ template <int N> static void check_fwd_small(int ovl, long nblocks)
         for (int k = 0; k < N; k++) want[k ^ (N / 2)] = a[k] / (double)N;
         worst = std::max(worst, rel_err(want, spec.data() + (size_t)b * N));
     }
-    char name[128]; snprintf(name, sizeof name, "fwd_small N=%d ovl=%d nblocks=%ld", N, ovl, nblocks);
+    char name[128]; snprintf(name, sizeof name, "fwd_small N=%d E=%d ovl=%d nblocks=%ld", N, E, ovl, nblocks);
     report(name, worst, 2e-6);
 }
 
@@ -142,8 +142,9 @@ template <int N1, int N2> static void check_fwd_big(int ovl, long nblocks)
 {
     constexpr int N = N1 * N2;
     constexpr int BC = N1 == 256 ? 16 : 4096 / N1, BR = N2 == 256 ? 16 : 4096 / N2;
-    typedef TileFFT<N1, BC, 1, true, true> CE;
-    typedef TileFFT<N2, BR, 1, false, true> RE;
+    constexpr int EC = (N1 == 512 || N1 == 1024) ? 32 : 16, ER = (N2 == 512 || N2 == 1024) ? 32 : 16;    /* as fdc_k_fwd.cu big_points() */
+    typedef TileFFT<N1, BC, 1, true, true, EC> CE;
+    typedef TileFFT<N2, BR, 1, false, true, ER> RE;
     const int hop = N - ovl;
     std::vector<float2> buf((size_t)ovl + (size_t)nblocks * hop), mid((size_t)nblocks * N), spec((size_t)nblocks * N), tw4((size_t)N);
     for (auto& v : buf) { v.x = frand(); v.y = frand(); }
@@ -152,18 +153,18 @@ template <int N1, int N2> static void check_fwd_big(int ovl, long nblocks)
             const double a = -2.0 * M_PI * (double)((k1 * n2) % N) / N;
             tw4[(size_t)(k1 * N2 + n2)] = make_float2((float)cos(a), (float)sin(a));
         }
-    const std::vector<float2> twc = pass_twiddles(N1), twr = pass_twiddles(N2);
+    const std::vector<float2> twc = pass_twiddles(N1, EC), twr = pass_twiddles(N2, ER);
     BigParams p; p.in = buf.data() + ovl; p.mid = mid.data(); p.spec = spec.data(); p.tw4 = tw4.data(); p.nblocks = nblocks;
     p.hop = hop; p.ovl = ovl; p.scale = 1.0f / N;
     /* a persistent column CTA keeps one column tile and its twiddle slice; the emulator walks all tiles with "one CTA",
      * so the slice is rebuilt per column tile: run the tiles of one column tile at a time */
     {
-        std::vector<float2> tws((size_t)16 * CE::T);
+        std::vector<float2> tws((size_t)N1 * BC);
         for (int ct = 0; ct < N2 / BC; ct++) {
             for (int tid = 0; tid < CE::T; tid++) CE::template last_pass_init<ColTwiddles<N1, N2, BC> >(tid, tws.data(), (const float2*)tw4.data(), ct);
             ColTiles<N1, N2, BC> tiles{p, tws.data()};
             std::vector<float2> smem(CE::SMEM_ELEMS);
-            std::vector<std::array<float2, 16>> regs(CE::T);
+            std::vector<std::array<float2, 32>> regs(CE::T);
             for (long b = 0; b < nblocks; b++) {
                 TilePos pos; pos.inner = ct; pos.outer = (int)b;
                 auto ld = tiles.loader(pos); auto st = tiles.storer(pos);
@@ -191,6 +192,7 @@ template <int L, int E = 16> static void check_extract(int N, int nchan, long nb
 {
     constexpr int B = E == 8 ? 2048 / L : (L >= 4096 ? 1 : 4096 / L);
     typedef TileFFT<L, B, -1, false, false, E> ENG;
+    static_assert(ENG::E <= 32, "emulator register tile");
     std::vector<float2> spec((size_t)nb * N), tables((size_t)2 * nphase * L);
     for (auto& v : spec) { v.x = frand(); v.y = frand(); }
     for (auto& v : tables) { v.x = frand(); v.y = frand(); }
@@ -277,14 +279,17 @@ int main()
 #undef PL
     check_fwd_small<16>(4, 300); check_fwd_small<64>(16, 70); check_fwd_small<1024>(512, 9); check_fwd_small<4096>(1024, 3);
     check_fwd_small<8192>(2048, 2); check_fwd_small<16384>(2048, 2); check_fwd_small<2048>(1536, 5);
+    check_fwd_small<512, 32>(128, 20); check_fwd_small<1024, 32>(512, 9);
+    check_fwd_small<8192, 32>(2048, 2); check_fwd_small<16384, 32>(4096, 2);
     check_fwd_big<64, 64>(1024, 3); check_fwd_big<64, 128>(2048, 3); check_fwd_big<128, 128>(4096, 2);
     check_fwd_big<128, 256>(8192, 2); check_fwd_big<256, 256>(16384, 2); check_fwd_big<256, 512>(32768, 1);
-    check_fwd_big<512, 512>(65536, 1); check_fwd_big<256, 256>(49152, 3);
+    check_fwd_big<512, 512>(65536, 1); check_fwd_big<512, 1024>(131072, 1); check_fwd_big<256, 256>(49152, 3);
     check_extract<2>(64, 5, 3, 4); check_extract<8>(64, 7, 3, 4); check_extract<16>(256, 300, 2, 3); check_extract<64>(1024, 16, 5, 2);
     check_extract<128>(4096, 70, 3, 4); check_extract<256>(8192, 64, 3, 4); check_extract<512>(8192, 19, 5, 4);
     check_extract<1024>(4096, 5, 3, 4); check_extract<4096>(16384, 3, 2, 4); check_extract<8192>(16384, 2, 2, 8);
     check_extract<64, 8>(1024, 16, 5, 2); check_extract<128, 8>(4096, 70, 3, 4); check_extract<256, 8>(8192, 64, 3, 4);
     check_extract<512, 8>(8192, 19, 5, 4); check_extract<1024, 8>(4096, 5, 3, 4); check_extract<2048, 8>(8192, 3, 2, 4);
+    check_extract<512, 32>(8192, 19, 5, 4); check_extract<1024, 32>(4096, 5, 3, 4); check_extract<512, 32>(65536, 256, 2, 4);
     check_jobs<64>(1024, 70); check_jobs<512>(4096, 11); check_jobs<16>(256, 300);
     printf("%s\n", g_fail ? "EMU FAILED" : "EMU OK");
     return g_fail ? 1 : 0;

@@ -78,7 +78,11 @@ CASES = {
     "cfg2": (workloads.cfg2, 6),
     "example32768": (lambda: workloads.cfg_example(32768, 4, workloads.HANN), 5),
     "cfg4": (workloads.cfg4, 4),
+    # narrow channels on long transforms (slices 128 .. 2048 bins): 256 x 512 and 512 x 512 four-step, 32 points per thread
+    "narrow131072": (lambda: workloads.ChanConfig("narrow131072", 131072, 4, NARROW, workloads.HANN), 3),
+    "narrow262144_r8": (lambda: workloads.ChanConfig("narrow262144", 262144, 8, NARROW, workloads.RAMP), 3),
 }
+NARROW = [(0.12, 0.001), (0.22, 0.004), (-0.14, 0.0005), (0.0, 0.002), (-0.4991, 0.0003), (0.4993, 0.0003)]
 
 
 @pytest.mark.parametrize("case", sorted(CASES))

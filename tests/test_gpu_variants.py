@@ -15,6 +15,8 @@ VARIANTS = {
     "prefetch_everywhere_four_streams": {"FDC_PREFETCH": "3", "FDC_STREAMS": "4"},
     "extract_8_points_per_thread": {"FDC_EXTRACT_E8": "1"},
     "extract_8_points_per_thread_prefetch": {"FDC_EXTRACT_E8": "1", "FDC_PREFETCH": "3"},
+    "extract_16_points_per_thread": {"FDC_EXTRACT_E32": "0"},
+    "forward_32_points_per_thread": {"FDC_FWD_E32": "1"},
     "four_step_from_4096": {"FDC_FWD_SPLIT": "4096"},
     "one_cta_per_sm": {"FDC_CTAS_PER_SM": "1"},
 }
