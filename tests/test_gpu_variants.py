@@ -16,7 +16,8 @@ VARIANTS = {
     "extract_8_points_per_thread": {"FDC_EXTRACT_E8": "1"},
     "extract_8_points_per_thread_prefetch": {"FDC_EXTRACT_E8": "1", "FDC_PREFETCH": "3"},
     "extract_16_points_per_thread": {"FDC_EXTRACT_E32": "0"},
-    "forward_32_points_per_thread": {"FDC_FWD_E32": "1"},
+    "forward_16_points_per_thread": {"FDC_FWD_E32": "0"},
+    "forward_32_points_everywhere": {"FDC_FWD_E32": "2"},
     "four_step_from_4096": {"FDC_FWD_SPLIT": "4096"},
     "one_cta_per_sm": {"FDC_CTAS_PER_SM": "1"},
 }
@@ -26,7 +27,7 @@ VARIANTS = {
 def test_variant_parity(name):
     env = dict(os.environ); env.update(VARIANTS[name])
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_chan.py"), "-m", "gpu", "-x", "-q",
-                        "-k", "golden or chain_matches or sliding or device_path or time_sharded"],
+                        "-k", "golden or chain_matches or sliding or device_path or time_sharded or fft_vcc"],
                        env=env, capture_output=True, text=True, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
     assert " passed" in r.stdout
