@@ -113,6 +113,7 @@ struct fdc_chan {
     std::vector<ChanDev> chans;
     std::vector<int> l;
     std::vector<std::pair<int, std::pair<int, int> > > groups;    /* (l, (first index in d_chans, count)) */
+    std::vector<int> group_even_f;     /* every slice of the group starts on an even bin (16-byte aligned: TMA bulk copies) */
     long lout_total;
     long blockcount;
     long chunk_blocks;                 /* blocks per K1->K2 round trip: spectrum ring sized to stay in L2 */
@@ -180,6 +181,7 @@ static int chan_enqueue_chunk(fdc_chan* c, const float2* d_in, long nb, float2* 
         ExtractParams q; q.spec = d_spec; q.spec_stride = c->N; q.tables = (const float2*)c->d_tables.p;
         q.chans = (const ChanDev*)c->d_chans.p + c->groups[g].second.first;
         q.nsel = c->groups[g].second.second; q.ny = 0; q.out = d_out;
+        q.tma_ok = ((uintptr_t)d_spec % 16 == 0) && (c->N % 2 == 0) && c->group_even_f[g];
         q.nb = nb; q.call_blocks = call_blocks; q.call_blk0 = call_blk0; q.glob_phase0 = (int)(glob_blk0 % c->nphase); q.nphase = c->nphase;
         e = launch_extract(q, c->groups[g].first, s);
         if (e != cudaSuccess) return cuda_fail(e, "channel extract launch");
@@ -249,6 +251,9 @@ fdc_chan* fdc_chan_create(int N, int ovl, int nphase, int nchan, const fdc_chan_
     for (std::map<int, std::vector<int> >::iterator it = by_l.begin(); it != by_l.end(); ++it) {
         c->groups.push_back(std::make_pair(it->first, std::make_pair((int)sel.size(), (int)it->second.size())));
         /* neighbours in frequency share a CTA tile: their slices overlap in the spectrum */
+        int even = 1;
+        for (size_t k = 0; k < it->second.size(); k++) if (c->chans[(size_t)it->second[k]].f & 1) even = 0;
+        c->group_even_f.push_back(even);
         std::vector<int> order(it->second);
         std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return c->chans[a].f < c->chans[b].f; });
         sel.insert(sel.end(), order.begin(), order.end());
