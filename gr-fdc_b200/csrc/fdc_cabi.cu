@@ -386,6 +386,36 @@ int fdc_chan_work_device(fdc_chan* c, const void* d_in_v, long nblocks, void* d_
     return 0;
 }
 
+/* inpveclen > 1 mode of the hier block (python/FrequencyDomainChannelizer.py:284-290): the input items are already
+ * fft-shifted, unnormalised spectra; only normalize_input (x 1/N, :216) and the per-channel chains run. */
+int fdc_chan_work_spectrum_device(fdc_chan* c, const void* d_spec_in_v, long nblocks, void* d_out_v, void* d_spectrum_v, void* stream)
+{
+    if (!c) return fail("null context");
+    if (nblocks < 0) return fail("nblocks < 0");
+    if (nblocks == 0) return 0;
+    const float2* d_spec_in = (const float2*)d_spec_in_v; float2* d_out = (float2*)d_out_v; float2* d_spectrum = (float2*)d_spectrum_v;
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    const long ring = std::min(nblocks, c->chunk_blocks);
+    if (!d_spectrum && !c->w_spec[0].reserve(sizeof(float2) * (size_t)ring * c->N)) return cuda_fail(cudaGetLastError(), "spectrum ring");
+    for (long b0 = 0; b0 < nblocks; b0 += ring) {
+        const long nb = std::min(ring, nblocks - b0);
+        float2* spec = d_spectrum ? d_spectrum + b0 * c->N : (float2*)c->w_spec[0].p;
+        cudaError_t e = launch_scale(d_spec_in + b0 * c->N, spec, nb * c->N, 1.0f / (float)c->N, s);
+        if (e != cudaSuccess) return cuda_fail(e, "normalize_input launch");
+        if (!d_out) continue;
+        for (size_t g = 0; g < c->groups.size(); g++) {
+            ExtractParams q; q.spec = spec; q.spec_stride = c->N; q.tables = (const float2*)c->d_tables.p;
+            q.chans = (const ChanDev*)c->d_chans.p + c->groups[g].second.first; q.nsel = c->groups[g].second.second; q.ny = 0; q.out = d_out;
+            q.tma_ok = ((uintptr_t)spec % 16 == 0) && (c->N % 2 == 0) && c->group_even_f[g];
+            q.nb = nb; q.call_blocks = nblocks; q.call_blk0 = b0; q.glob_phase0 = (int)((c->blockcount + b0) % c->nphase); q.nphase = c->nphase;
+            e = launch_extract(q, c->groups[g].first, s);
+            if (e != cudaSuccess) return cuda_fail(e, "channel extract launch");
+        }
+    }
+    c->blockcount += nblocks;
+    return 0;
+}
+
 int fdc_chan_set_profiling(fdc_chan* c, int enable)
 {
     if (!c) return fail("null context");

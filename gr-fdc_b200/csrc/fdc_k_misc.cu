@@ -160,6 +160,25 @@ cudaError_t launch_psw(const float2* in, float2* out, const float2* table, long 
     return cudaGetLastError();
 }
 
+/* ---- blocks.multiply_const_cc(k) with a real constant (the hier block's normalize_input, python/FrequencyDomainChannelizer.py:216),
+ * for spectra that arrive already transformed (inpveclen > 1, :284-290) ---- */
+__global__ void __launch_bounds__(256) k_scale(const float4* __restrict__ in, float4* __restrict__ out, long n4, float k)
+{
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+        const float4 v = in[i];
+        out[i] = make_float4(fdc_mul(v.x, k), fdc_mul(v.y, k), fdc_mul(v.z, k), fdc_mul(v.w, k));
+    }
+}
+cudaError_t launch_scale(const float2* in, float2* out, long n, float k, cudaStream_t s)
+{
+    if (n <= 0) return cudaSuccess;
+    if ((n & 1) || ((uintptr_t)in & 15) || ((uintptr_t)out & 15)) return cudaErrorInvalidValue;
+    long blocks = (n / 2 + 255) / 256; if (blocks > 148L * 16) blocks = 148L * 16;
+    k_scale<<<(unsigned)blocks, 256, 0, s>>>((const float4*)in, (float4*)out, n / 2, k);
+    count_launch();
+    return cudaGetLastError();
+}
+
 /* ---- K3 ------------------------------------------------------------------------------------------ */
 /* one thread per (block, power bin): D sequential |x|^2 additions, the order of the generic VOLK accumulator.
  * A warp covers 32 adjacent power bins = 32*D contiguous spectrum bins; the tile is staged through shared

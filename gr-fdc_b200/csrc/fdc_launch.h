@@ -39,6 +39,9 @@ cudaError_t launch_rowcopy(const void* src, const void* hist, long hist_bytes, v
 cudaError_t launch_psw(const float2* in, float2* out, const float2* table, long nblocks, int l, int nphase,
                        int counter, int shift, cudaStream_t s);
 
+/* out = in * k (real constant), n complex items (n even, 16-byte aligned pointers) */
+cudaError_t launch_scale(const float2* in, float2* out, long n, float k, cudaStream_t s);
+
 /* ---- K3: power / threshold / edges ---------------------------------------------------------- */
 /* P[b*M + i] = sum_{k<D} |X_b[start + i*D + k]|^2, strictly sequential fp32 (generic VOLK order,
  * lib/SegmentDetection_impl.cc:185-190); mean != 0 multiplies by 1/D afterwards

@@ -90,9 +90,10 @@ class FrequencyDomainChannelizer(object):
         self.relinvovl = nextpow2(relinvovl)
         self.ovllen = self.blocksize // self.relinvovl
         self.inpblocklen = self.blocksize - self.ovllen
-        if self.inpveclen != 1:
-            raise NotImplementedError('inpveclen > 1 (already transformed input, python/FrequencyDomainChannelizer.py:284-290) '
-                                      'is not part of the GPU hot path yet')
+        if self.inpveclen != 1 and self.inpveclen != self.blocksize:
+            # the reference wires the input straight into multiply_const_cc(1/N, blocksize) (:284-290): any other vector
+            # length makes GNU Radio refuse the connection
+            raise ValueError('inpveclen must be 1 (sample stream) or blocksize (already transformed input vectors)')
         if self.itemsize != 8:
             raise ValueError('Unknown input type. ')           # the reference's float branch is dead code (:205-210)
 
@@ -230,11 +231,12 @@ class FrequencyDomainChannelizer(object):
 
     def work(self, samples):
         x = np.ascontiguousarray(samples, dtype=np.complex64)
-        nblocks = x.size // self.inpblocklen
-        if nblocks * self.inpblocklen != x.size:
-            raise ValueError('input must be a whole number of blocks of {} samples'.format(self.inpblocklen))
+        per_item = self.inpblocklen if self.inpveclen == 1 else self.blocksize
+        nblocks = x.size // per_item
+        if nblocks * per_item != x.size:
+            raise ValueError('input must be a whole number of blocks of {} samples'.format(per_item))
         need_spec = self.debug or self.PowerActChans or self.SegmentDetectionChans
-        if not need_spec:
+        if not need_spec and self.inpveclen == 1:
             outs, _ = self.front.work_host(x)
             return outs
         N = self.blocksize
@@ -243,7 +245,10 @@ class FrequencyDomainChannelizer(object):
         nout = int(self.front.lout_prefix[-1]) * nblocks
         d_out = self._dev('out', 8 * max(nout, 1))
         check(lib().fdc_memcpy_h2d(d_in, x.ctypes.data, 8 * x.size))
-        self.front.work_device(d_in, nblocks, d_out if nout else 0, d_spec, 0)
+        if self.inpveclen == 1:
+            self.front.work_device(d_in, nblocks, d_out if nout else 0, d_spec, 0)
+        else:                                          # already transformed input vectors, :284-290
+            self.front.work_spectrum_device(d_in, nblocks, d_out if nout else 0, d_spec, 0)
         self.front.sync()
         for b in self.PowerActChans:
             b.work_device(nblocks, d_spec)

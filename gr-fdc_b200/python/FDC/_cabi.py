@@ -53,6 +53,7 @@ SIGNATURES = {
     "fdc_chan_set_history": (_i, [_vp, _vp]),
     "fdc_chan_work_host": (_i, [_vp, _vp, _l, _vp, _vp]),
     "fdc_chan_work_device": (_i, [_vp, _vp, _l, _vp, _vp, _vp]),
+    "fdc_chan_work_spectrum_device": (_i, [_vp, _vp, _l, _vp, _vp, _vp]),
     "fdc_chan_sync": (_i, [_vp]),
     "fdc_chan_set_profiling": (_i, [_vp, _i]),
     "fdc_chan_get_profile": (_i, [_vp, _dp, _dp, C.POINTER(C.c_long)]),

@@ -226,6 +226,12 @@ class Channelizer(object):
                                          C.c_void_p(d_spectrum) if d_spectrum else None, C.c_void_p(stream) if stream else None),
               "fdc_chan_work_device")
 
+    def work_spectrum_device(self, d_spectra, nblocks, d_out, d_spectrum=0, stream=0):
+        """inpveclen > 1 mode: already transformed (fft-shifted, unnormalised) spectra in, channel outputs out."""
+        check(lib().fdc_chan_work_spectrum_device(self._h, C.c_void_p(d_spectra), int(nblocks), C.c_void_p(d_out) if d_out else None,
+                                                  C.c_void_p(d_spectrum) if d_spectrum else None, C.c_void_p(stream) if stream else None),
+              "fdc_chan_work_spectrum_device")
+
     def sync(self):
         check(lib().fdc_chan_sync(self._h))
 

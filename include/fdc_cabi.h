@@ -94,6 +94,11 @@ int fdc_chan_work_host(fdc_chan* c, const void* in, long nblocks, void* const* o
  * sum_{j<i} nblocks*lout_j ("channel-major slabs").  d_spectrum may be NULL (an internal L2-sized
  * ring is used then).  Only enqueues on `stream`; history/counters are advanced. */
 int fdc_chan_work_device(fdc_chan* c, const void* d_in, long nblocks, void* d_out, void* d_spectrum, void* stream);
+/* The hier block's inpveclen > 1 mode (python/FrequencyDomainChannelizer.py:284-290): the input items are vectors that are
+ * already transformed (fft-shifted, unnormalised spectra of N bins).  Runs normalize_input (x 1/N, :216) and the
+ * per-channel chains; overlap-save and the forward FFT are skipped.  d_spectrum (optional) receives the normalised
+ * spectra for the activity-gated blocks / the debug port. */
+int fdc_chan_work_spectrum_device(fdc_chan* c, const void* d_spectra, long nblocks, void* d_out, void* d_spectrum, void* stream);
 int fdc_chan_sync(fdc_chan* c);
 /* Measurement hooks.  Profiling records CUDA events around the forward-FFT and the channel-extract kernels of every
  * chunk; get_profile synchronises and returns the summed kernel times (ms) since the last call.  chunk_blocks is

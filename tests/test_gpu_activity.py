@@ -190,3 +190,29 @@ def test_hier_block_against_reference_flowgraph(FDC, ref):
     got = blk.messages()
     assert len(got) == len(ref_msgs) and len(got) > 8
     compare_messages(ref_msgs, got, ordered=False)
+
+
+def test_hier_block_transformed_input_mode(FDC, ref):
+    """inpveclen = blocksize (python/FrequencyDomainChannelizer.py:284-290): the input items are fft-shifted, unnormalised
+    spectra; oracle = the reference blocks chained by hand behind the restated multiply_const / inverse fft_vcc stages"""
+    N, R = 2048, 4
+    chans = [(0.12, 0.05), (-0.2, 0.02), (0.31, 0.1)]
+    rng = np.random.default_rng(17)
+    nblocks = 9
+    X = (rng.standard_normal((nblocks, N)) + 1j * rng.standard_normal((nblocks, N))).astype(np.complex64) * np.float32(30.0)
+    blk = FDC.FrequencyDomainChannelizer(8, N, N, R, chans, [], 6.0, 1.0, 0.0, "normalized", 1, False, False, "", False, [], 10.0, 0.01,
+                                         1, 0.2, 0, 1, 4, 4, True)
+    o1 = blk.work(X[:4].reshape(-1)); o2 = blk.work(X[4:].reshape(-1))
+    spec = np.concatenate([o1[0], o2[0]])
+    want_spec = (X * np.float32(1.0 / N)).astype(np.complex64)                    # multiply_const_cc(1/N): exact (power of two)
+    assert np.array_equal(spec.view(np.uint32), want_spec.view(np.uint32))
+    for i, (fq, bw) in enumerate(chans):
+        f, l, lout, pb, sb = geometry.get_opt_channelparams(N, R, geometry.get_freq(fq), geometry.get_bw(bw))
+        cut0 = ref.vector_cut_vxx(8, N, f, l); psw = ref.phase_shifting_windowing_vcc(l, R, f, pb, sb, 1); cut3 = ref.vector_cut_vxx(8, l, l - lout, lout)
+        y = cut0.work(want_spec.reshape(-1)).view(np.complex64)
+        y = psw.work(y).view(np.complex64)
+        y = ref.fft_vcc(y, l, False, True)
+        y = cut3.work(y).view(np.complex64) * np.float32(l)
+        got = np.concatenate([o1[1 + i], o2[1 + i]])
+        assert got.size == y.size == nblocks * lout
+        assert rel_l2(got, y) < 1e-5

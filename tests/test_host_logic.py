@@ -276,3 +276,26 @@ def test_actdet_state_machine_vs_oracle(FDC, ref, threads):
     assert a.segments() == b.segments()
     for i in range(len(segs)):
         assert np.array_equal(a.power(i), b.power(i))
+
+
+# ------------------------------------------------------------------------------------------------ GRC descriptors
+def test_grc_yaml_descriptors_match_the_block_api():
+    """GNU Radio >= 3.8 descriptors (gr-fdc_b200/grc): ids and make templates are the reference's keys / make strings
+    (grc/FDC_*.xml), every make argument is a declared parameter"""
+    import glob
+    import yaml
+    files = sorted(glob.glob(os.path.join(ROOT, "gr-fdc_b200", "grc", "*.block.yml")))
+    assert len(files) == 7
+    want = {"FDC_overlap_save": ("FDC.overlap_save", 3), "FDC_vector_cut_vxx": ("FDC.vector_cut_vxx", 4),
+            "FDC_phase_shifting_windowing_vcc": ("FDC.phase_shifting_windowing_vcc", 6), "FDC_PowerActivationChannel": ("FDC.PowerActivationChannel", 12),
+            "FDC_SegmentDetection": ("FDC.SegmentDetection", 15), "FDC_activity_detection_channelizer_vcm": ("FDC.activity_detection_channelizer_vcm", 13),
+            "FDC_FrequencyDomainChannelizer": ("FDC.FrequencyDomainChannelizer", 25)}
+    for f in files:
+        d = yaml.safe_load(open(f))
+        fn, nargs = want[d["id"]]
+        make = d["templates"]["make"]
+        assert make.startswith(fn + "(")
+        args = re.findall(r"\$\{\s*([A-Za-z_][A-Za-z0-9_]*)", make)
+        assert len(args) == nargs, (d["id"], args)
+        ids = {p["id"] for p in d["parameters"]}
+        assert set(args) <= ids, (d["id"], set(args) - ids)
