@@ -22,9 +22,10 @@ k_extract8(const ExtractParams p, const float2* __restrict__ tw, long ntiles)
     tile_kernel_body<TileFFT<L, B, -1, false, false, 8>, PF>(ExtractTiles<L, B>{p}, tw, ntiles);
 }
 /* 32 points per thread (512 = 16 * 32, 1024 = 32 * 32): one shared-memory exchange instead of two; the extract is limited by
- * the L1/shared-memory pipe, so the exchange it does not do is the saving.  128 threads, 4 CTAs per SM. */
+ * the L1/shared-memory pipe, so the exchange it does not do is the saving.  128 threads at 96 registers, 5 CTAs per SM (measured: 4 CTAs / 127 registers
+ * 79.1 Gsample/s, 5 CTAs 80.4, 6 CTAs with the twiddles left in global memory to fit the shared memory 69). */
 template <int L, int B>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, 5)
 k_extract32(const ExtractParams p, const float2* __restrict__ tw, long ntiles)
 {
     tile_kernel_body<TileFFT<L, B, -1, false, false, 32>, false>(ExtractTiles<L, B>{p}, tw, ntiles);

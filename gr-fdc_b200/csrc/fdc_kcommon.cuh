@@ -63,10 +63,10 @@ cudaError_t launch_tile_kernel(void (*kernel)(KA...), unsigned grid, int threads
 }
 
 /* the body shared by all tile kernels: persistent loop with or without register prefetch */
-template <class ENG, bool PF, class Tiles>
+template <class ENG, bool PF, class Tiles, bool TW_SMEM = true>
 __device__ __forceinline__ void tile_kernel_body(const Tiles& tiles, const float2* tw, long ntiles)
 {
-    tile_fft_loop<ENG, PF>(reinterpret_cast<float2*>(fdc_smem_raw), tw, tiles, (long)blockIdx.x, (long)gridDim.x, ntiles);
+    tile_fft_loop<ENG, PF, Tiles, TW_SMEM>(reinterpret_cast<float2*>(fdc_smem_raw), tw, tiles, (long)blockIdx.x, (long)gridDim.x, ntiles);
 }
 
 }  // namespace fdc

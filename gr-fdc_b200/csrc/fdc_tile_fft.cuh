@@ -273,10 +273,10 @@ __device__ __forceinline__ void tile_fft_from(float2* v, float2* smem, const flo
  * Order inside an iteration: finish (the loader's own table loads + arithmetic) -> prefetch of the next tile ->
  * butterflies.  The only global loads in flight during the butterflies are the prefetch: the twiddles come from
  * shared memory, so no instruction waits on a scoreboard that it shares with a DRAM access. */
-template <class ENG, bool PF, class Tiles>
+template <class ENG, bool PF, class Tiles, bool TW_SMEM = true>
 __device__ __forceinline__ void tile_fft_loop(float2* smem, const float2* tw_global, const Tiles& tiles, long first, long stride, long ntiles)
 {
-    constexpr bool TWS = tw_in_smem(ENG::L, ENG::E);
+    constexpr bool TWS = TW_SMEM && tw_in_smem(ENG::L, ENG::E);       /* TW_SMEM = false: twiddles stay in global memory / L1 (saves 4 KB per CTA) */
     const float2* tw = tw_global;
     /* programmatic dependent launch: let the next kernel of the stream start its prologue now, run ours (constant tables
      * only), then wait until the previous kernel's results are complete and visible */
