@@ -317,6 +317,35 @@ def main():
         gather = {"value": world * GK * nb * cfg.hop / (float(tg.item()) * 1e-3) / 1e6, "unit": "Msamples/s",
                   "note": "compute + NCCL gather of every rank's output slab to rank 0 (sink ingest bound)"}
 
+    # ---- gather fused into the extract kernel: every rank stores its outputs straight into the sink rank's buffer (peer
+    # memory over NVLink, CUDA IPC), nothing is staged locally and no collective follows ----
+    if world > 1:
+        from FDC import sharded
+        try:
+            sink = sharded.PeerSink(cfg.out_per_block, nb, rank, world, dst=0)
+
+            def fstep():
+                chan.work_device_slab(d_in.data_ptr(), nb, sink.ptr, sink.slab_blocks, sink.first_block(), 0, stream)
+
+            for _ in range(3):
+                fstep()
+            bracket()
+            f0 = torch.cuda.Event(enable_timing=True); f1 = torch.cuda.Event(enable_timing=True)
+            FK = max(5, min(K, 20))
+            f0.record()
+            for _ in range(FK):
+                fstep()
+            f1.record(); bracket()
+            tf = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device=dev)
+            dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+            gather["fused_peer_store"] = {"value": world * FK * nb * cfg.hop / (float(tf.item()) * 1e-3) / 1e6, "unit": "Msamples/s",
+                                          "note": "extract kernels of all ranks store into rank 0's buffer (fdc_chan_work_device_slab on IPC-mapped "
+                                                  "peer memory): compute and transfer overlap, no NCCL call on the path"}
+            bracket()
+            sink.close()
+        except Exception as exc:                          # peer access not available on this box: keep the NCCL number
+            gather["fused_peer_store"] = {"unavailable": str(exc)[:200]}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_reference_run(cfg)

@@ -336,8 +336,15 @@ static int chan_save_history(fdc_chan* c, const float2* d_in, long nblocks, cuda
 
 int fdc_chan_work_device(fdc_chan* c, const void* d_in_v, long nblocks, void* d_out_v, void* d_spectrum_v, void* stream)
 {
+    return fdc_chan_work_device_slab(c, d_in_v, nblocks, d_out_v, nblocks, 0, d_spectrum_v, stream);
+}
+
+int fdc_chan_work_device_slab(fdc_chan* c, const void* d_in_v, long nblocks, void* d_out_v, long slab_blocks, long slab_first_block,
+                              void* d_spectrum_v, void* stream)
+{
     if (!c) return fail("null context");
     if (nblocks < 0) return fail("nblocks < 0");
+    if (slab_first_block < 0 || slab_first_block + nblocks > slab_blocks) return fail("fdc_chan_work_device_slab: blocks outside the slab");
     if (nblocks == 0) return 0;
     const float2* d_in = (const float2*)d_in_v; float2* d_out = (float2*)d_out_v; float2* d_spectrum = (float2*)d_spectrum_v;
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
@@ -372,7 +379,7 @@ int fdc_chan_work_device(fdc_chan* c, const void* d_in_v, long nblocks, void* d_
         const long nb = head ? nh : std::min(c->chunk_blocks, nblocks - b0);
         const float2* in = head ? (const float2*)c->d_stage.p + c->ovl : d_in + b0 * c->hop;
         float2* spec = d_spectrum ? d_spectrum + b0 * c->N : (float2*)c->w_spec[w].p;
-        if (chan_enqueue_chunk(c, in, nb, spec, (float2*)c->w_mid[w].p, d_out, nblocks, b0, c->blockcount + b0, wk[w])) return -1;
+        if (chan_enqueue_chunk(c, in, nb, spec, (float2*)c->w_mid[w].p, d_out, slab_blocks, slab_first_block + b0, c->blockcount + b0, wk[w])) return -1;
         b0 += nb;
     }
     if (nw > 1) {
@@ -414,6 +421,33 @@ int fdc_chan_work_spectrum_device(fdc_chan* c, const void* d_spec_in_v, long nbl
     }
     c->blockcount += nblocks;
     return 0;
+}
+
+/* ---- peer memory (one process per GPU): the sink rank exports its output buffer, the other ranks map it and let their
+ * extract kernels store straight into it over NVLink (fdc_chan_work_device_slab) -- the gather is fused into the kernel */
+int fdc_ipc_export(const void* d_ptr, void* handle64)
+{
+    if (!d_ptr || !handle64) return fail("fdc_ipc_export: bad arguments");
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, const_cast<void*>(d_ptr));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaIpcGetMemHandle");
+    static_assert(sizeof(h) == 64, "CUDA IPC handles are 64 bytes");
+    memcpy(handle64, &h, sizeof(h));
+    return 0;
+}
+void* fdc_ipc_open(const void* handle64)
+{
+    if (!handle64) { fail("fdc_ipc_open: bad arguments"); return 0; }
+    cudaIpcMemHandle_t h; memcpy(&h, handle64, sizeof(h));
+    void* p = 0;
+    const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { cuda_fail(e, "cudaIpcOpenMemHandle"); return 0; }
+    return p;
+}
+int fdc_ipc_close(void* d_ptr)
+{
+    const cudaError_t e = cudaIpcCloseMemHandle(d_ptr);
+    return e == cudaSuccess ? 0 : cuda_fail(e, "cudaIpcCloseMemHandle");
 }
 
 int fdc_chan_set_profiling(fdc_chan* c, int enable)

@@ -53,6 +53,10 @@ SIGNATURES = {
     "fdc_chan_set_history": (_i, [_vp, _vp]),
     "fdc_chan_work_host": (_i, [_vp, _vp, _l, _vp, _vp]),
     "fdc_chan_work_device": (_i, [_vp, _vp, _l, _vp, _vp, _vp]),
+    "fdc_chan_work_device_slab": (_i, [_vp, _vp, _l, _vp, _l, _l, _vp, _vp]),
+    "fdc_ipc_export": (_i, [_vp, _vp]),
+    "fdc_ipc_open": (_vp, [_vp]),
+    "fdc_ipc_close": (_i, [_vp]),
     "fdc_chan_work_spectrum_device": (_i, [_vp, _vp, _l, _vp, _vp, _vp]),
     "fdc_chan_sync": (_i, [_vp]),
     "fdc_chan_set_profiling": (_i, [_vp, _i]),

@@ -226,6 +226,13 @@ class Channelizer(object):
                                          C.c_void_p(d_spectrum) if d_spectrum else None, C.c_void_p(stream) if stream else None),
               "fdc_chan_work_device")
 
+    def work_device_slab(self, d_in, nblocks, d_out, slab_blocks, slab_first_block, d_spectrum=0, stream=0):
+        """work_device with explicit output placement (rows [slab_first_block, +nblocks) of slabs of slab_blocks rows);
+        d_out may be peer memory of the sink rank (FDC.sharded.PeerSink)."""
+        check(lib().fdc_chan_work_device_slab(self._h, C.c_void_p(d_in), int(nblocks), C.c_void_p(d_out) if d_out else None, int(slab_blocks),
+                                              int(slab_first_block), C.c_void_p(d_spectrum) if d_spectrum else None,
+                                              C.c_void_p(stream) if stream else None), "fdc_chan_work_device_slab")
+
     def work_spectrum_device(self, d_spectra, nblocks, d_out, d_spectrum=0, stream=0):
         """inpveclen > 1 mode: already transformed (fft-shifted, unnormalised) spectra in, channel outputs out."""
         check(lib().fdc_chan_work_spectrum_device(self._h, C.c_void_p(d_spectra), int(nblocks), C.c_void_p(d_out) if d_out else None,

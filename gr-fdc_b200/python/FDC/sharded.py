@@ -86,3 +86,44 @@ def gather_objects(obj, rank, world, dst=0, group=None):
     res = [None] * world if rank == dst else None
     dist.gather_object(obj, res, dst=dst, group=group)
     return res
+
+
+class PeerSink(object):
+    """One stream-ordered output buffer on the sink rank that every rank's extract kernel stores into directly (peer memory
+    over NVLink, CUDA IPC between the per-GPU processes): the gather is fused into the kernel, nothing is staged locally and
+    no collective runs afterwards.  Layout: channel-major slabs of world * blocks_per_rank rows; rank r owns rows
+    [r * blocks_per_rank, (r + 1) * blocks_per_rank) of every slab (Channelizer.work_device_slab)."""
+
+    def __init__(self, out_per_block, blocks_per_rank, rank, world, dst=0, group=None):
+        import ctypes as C
+        import torch.distributed as dist
+        from ._cabi import lib, check, handle
+        self.rank, self.world, self.dst, self.blocks_per_rank = rank, world, dst, int(blocks_per_rank)
+        self.slab_blocks = world * self.blocks_per_rank
+        self.nbytes = 8 * self.slab_blocks * int(out_per_block)
+        self._local = None
+        box = [None]
+        if rank == dst:
+            self._local = lib().fdc_dev_alloc(self.nbytes)
+            if not self._local:
+                raise RuntimeError("sink allocation failed")
+            h = C.create_string_buffer(64)
+            check(lib().fdc_ipc_export(C.c_void_p(self._local), h), "fdc_ipc_export")
+            box[0] = bytes(h.raw)
+        dist.broadcast_object_list(box, src=dst, group=group)
+        if rank == dst:
+            self.ptr = self._local
+        else:
+            self._hbuf = C.create_string_buffer(box[0], 64)
+            self.ptr = handle(lib().fdc_ipc_open(self._hbuf), "fdc_ipc_open").value
+
+    def first_block(self):
+        return self.rank * self.blocks_per_rank
+
+    def close(self):
+        from ._cabi import lib
+        if self.ptr and self.rank != self.dst:
+            lib().fdc_ipc_close(self.ptr)
+        if self._local:
+            lib().fdc_dev_free(self._local)
+        self.ptr = self._local = None

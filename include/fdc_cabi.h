@@ -94,6 +94,17 @@ int fdc_chan_work_host(fdc_chan* c, const void* in, long nblocks, void* const* o
  * sum_{j<i} nblocks*lout_j ("channel-major slabs").  d_spectrum may be NULL (an internal L2-sized
  * ring is used then).  Only enqueues on `stream`; history/counters are advanced. */
 int fdc_chan_work_device(fdc_chan* c, const void* d_in, long nblocks, void* d_out, void* d_spectrum, void* stream);
+/* The same with an explicit placement of the outputs: channel i occupies slab_blocks * lout_i items starting at item offset
+ * slab_blocks * sum_{j<i} lout_j, and this call's blocks go to rows [slab_first_block, slab_first_block + nblocks) of every
+ * channel's slab.  With d_out in ANOTHER GPU's memory (fdc_ipc_open) the extract kernel's stores travel over NVLink: the
+ * time-sharded ranks write one stream-ordered buffer on the sink rank and no separate gather is needed. */
+int fdc_chan_work_device_slab(fdc_chan* c, const void* d_in, long nblocks, void* d_out, long slab_blocks, long slab_first_block,
+                              void* d_spectrum, void* stream);
+/* CUDA IPC plumbing for that (one process per GPU): export a buffer made by fdc_dev_alloc as a 64-byte handle, map it in
+ * another process (peer access is enabled on demand), unmap. */
+int fdc_ipc_export(const void* d_ptr, void* handle64);
+void* fdc_ipc_open(const void* handle64);
+int fdc_ipc_close(void* d_ptr);
 /* The hier block's inpveclen > 1 mode (python/FrequencyDomainChannelizer.py:284-290): the input items are vectors that are
  * already transformed (fft-shifted, unnormalised spectra of N bins).  Runs normalize_input (x 1/N, :216) and the
  * per-channel chains; overlap-save and the forward FFT are skipped.  d_spectrum (optional) receives the normalised

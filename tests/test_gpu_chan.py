@@ -184,3 +184,32 @@ def test_time_sharded_equals_single_stream(FDC):
     for i in range(cfg.nchan):
         got = np.concatenate([p[i] for p in parts if p is not None])
         assert np.array_equal(got.view(np.uint8), whole[i].view(np.uint8))
+
+
+def test_slab_placement_builds_one_stream_ordered_buffer(FDC):
+    """fdc_chan_work_device_slab: two "ranks" (contexts positioned with seek + halo) write their runs into ONE buffer laid
+    out for the whole stream -- what the ranks do into the sink rank's peer memory (FDC.sharded.PeerSink); bit identical
+    to a single context fed the whole stream"""
+    import torch
+    from FDC import sharded
+    cfg = workloads.cfg2()
+    per, world = 11, 3
+    nblocks = per * world
+    x = workloads.tones_input(cfg, nblocks * cfg.hop, seed=19)
+    whole, _ = make_gpu_chain(FDC, cfg).work_host(x)
+    d_all = torch.zeros(nblocks * cfg.out_per_block * 2, dtype=torch.float32, device="cuda")
+    for r in range(world):
+        g = make_gpu_chain(FDC, cfg)
+        halo, new = sharded.shard_input(x, cfg.hop, cfg.ovl, r * per, per)
+        g.seek(r * per, halo)
+        d_in = torch.from_numpy(np.ascontiguousarray(new).view(np.float32).copy()).cuda()
+        g.work_device_slab(d_in.data_ptr(), per, d_all.data_ptr(), nblocks, r * per, 0, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+    got = d_all.cpu().numpy().view(np.complex64)
+    off = 0
+    for i in range(cfg.nchan):
+        n = nblocks * cfg.params[i][2]
+        assert np.array_equal(got[off:off + n].view(np.uint32), whole[i].view(np.uint32)), i
+        off += n
+    with pytest.raises(FDC.FDCError, match="outside the slab"):
+        make_gpu_chain(FDC, cfg).work_device_slab(d_in.data_ptr(), per, d_all.data_ptr(), per, 1)
