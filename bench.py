@@ -88,6 +88,24 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Best effort: run this rank on the CPUs NVML reports as local to its GPU, so that first-touch places the pinned host
+    buffers on that NUMA node (with 8 ranks the host<->device copies otherwise cross the socket interconnect)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [w * 64 + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1 and w * 64 + b < ncpu]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "%d cpus local to gpu %d" % (len(cpus), index)
+    except Exception as exc:
+        return "not bound (%s)" % str(exc)[:80]
+    return "not bound"
+
+
 def blocks_per_step(cfg):
     """batch whose input alone (>= 256 MiB) exceeds the 126 MB L2, so consecutive steps cannot hit in cache"""
     return max(64, int(np.ceil((256 << 20) / (8.0 * cfg.hop))))
@@ -170,6 +188,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
     torch.cuda.set_device(local)
     FDC._cabi.check(FDC._cabi.lib().fdc_set_device(local))
+    numa = bind_to_gpu_numa_node(local)        # pinned staging buffers of the e2e leg land on the GPU's own NUMA node
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"            # keep NCCL's version banner off stdout: ONE JSON line
@@ -296,7 +315,7 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * EK * nb_e * cfg.hop / float(tt.item()) / 1e6, "unit": "Msamples/s",
                "h2d_bytes_per_step": nbytes_in, "d2h_bytes_per_step": nbytes_out, "steps": EK, "blocks_per_step": nb_e,
-               "api": "fdc_chan_work_host (pinned host in/out, 4-slot H2D/compute/D2H pipeline)"}
+               "api": "fdc_chan_work_host (pinned host in/out, 4-slot H2D/compute/D2H pipeline)", "cpu_affinity": numa}
         L.fdc_host_free(h_in); L.fdc_host_free(h_out)
 
     # ---- optional: NCCL gather of the channel outputs to the sink rank ----
