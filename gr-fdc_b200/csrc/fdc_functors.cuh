@@ -24,8 +24,6 @@
 
 namespace fdc {
 
-FDC_HD float2 fdc_zero2() { return make_float2(0.f, 0.f); }
-
 /* tile index = outer * ninner + inner (inner runs fastest).  Persistent loops split their first tile and their stride
  * once and then advance the pair without dividing. */
 struct TilePos { int inner; int outer; };

@@ -44,8 +44,6 @@ template <class T> FDC_HD T fdc_ldg(const T* p) { return *p; }
 FDC_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 FDC_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 FDC_HD float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-FDC_HD float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
-FDC_HD float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
 /* VOLK-generic complex multiply: (ar*br - ai*bi, ar*bi + ai*br), four products and two sums
  * each rounded on its own (volk_32fc_x2_multiply_32fc generic kernel; reference call sites
  * lib/phase_shifting_windowing_vcc_impl.cc:81, lib/PowerActivationChannel_impl.cc:267,
