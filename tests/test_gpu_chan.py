@@ -213,3 +213,27 @@ def test_slab_placement_builds_one_stream_ordered_buffer(FDC):
         off += n
     with pytest.raises(FDC.FDCError, match="outside the slab"):
         make_gpu_chain(FDC, cfg).work_device_slab(d_in.data_ptr(), per, d_all.data_ptr(), per, 1)
+
+
+def test_empty_and_ragged_calls(FDC, ref):
+    """edge cases of the work() contract: zero items, a context without channels (spectrum only), calls of one block, and
+    outputs independent of how the same stream is cut into calls (the reference keeps history and counters across calls)"""
+    cfg = workloads.cfg_example(1024, 4, workloads.RAMP)
+    x = workloads.tones_input(cfg, 7 * cfg.hop, seed=23)
+    g = make_gpu_chain(FDC, cfg)
+    o0, s0 = g.work_host(x[:0], want_spectrum=True)
+    assert all(o.size == 0 for o in o0) and s0.size == 0 and g.blockcount == 0
+    want, wspec = make_ref_chain(ref, cfg).run(x, nthreads=1, want_spectrum=True)
+    parts = [g.work_host(x[a * cfg.hop:b * cfg.hop], want_spectrum=True) for a, b in ((0, 1), (1, 2), (2, 2), (2, 7))]
+    for i in range(cfg.nchan):
+        assert rel_l2(np.concatenate([p[0][i] for p in parts]), want[i]) < TOL
+    assert rel_l2(np.concatenate([p[1] for p in parts]), wspec) < TOL
+    # no channels: the front end alone (debug spectrum port)
+    g0 = FDC.Channelizer(cfg.N, cfg.ovl, cfg.R, [])
+    outs, spec = g0.work_host(x, want_spectrum=True)
+    assert outs == [] and rel_l2(spec, wspec) < TOL
+    # constructor errors of the C ABI surface as FDCError with the reason
+    with pytest.raises(FDC.FDCError, match="power of two"):
+        FDC.Channelizer(1000, 250, 4, [])
+    with pytest.raises(FDC.FDCError, match="outside the spectrum"):
+        FDC.Channelizer(1024, 256, 4, [(1000, 64, 48, 0, 64.0, FDC.psw_tables(64, 4, 0.5, 0.75, 1))])
