@@ -95,8 +95,12 @@ struct TileFFT {
     static constexpr int T = L * B / E;                       /* threads per CTA */
     static constexpr int NP = fft_npasses(L, E);
     static constexpr int NPH = NP == 1 ? 1 : 2 * NP - 2;       /* barrier-separated phases */
-    static constexpr int PADW = fft_radix(L, 0, E);            /* first-pass radix = run a thread writes in exchange 0 */
-    static constexpr int LP = NP > 1 ? ((L + L / PADW) | 1) : L;
+    /* exchange 0 is padded by one slot per PADW points.  16 (32 for a radix-32 first pass) keeps both the first pass's
+     * writes (a thread stores R0 <= PADW consecutive points) and the second pass's reads (lanes walk consecutive points)
+     * on 32 distinct banks per 16-lane phase of the 64-bit accesses; the per-signal stride is odd only for the batch-fast
+     * mappings, where lanes walk over signals (bank model: tests/emu/bank_model.py) */
+    static constexpr int PADW = fft_radix(L, 0, E) > 16 ? 32 : 16;
+    static constexpr int LP = NP > 1 ? ((LOAD_BF || STORE_BF) ? ((L + L / PADW) | 1) : (L + L / PADW)) : L;
     static constexpr int SMEM_ELEMS = NP == 1 ? 1 : B * LP;    /* float2 units */
     static constexpr size_t SMEM_BYTES = sizeof(float2) * SMEM_ELEMS;
     static constexpr int TWSIZE = fft_twsize(L, E);
@@ -209,7 +213,7 @@ struct TileFFT {
     template <int P> static FDC_HD void read_smem(int tid, float2* v, const float2* smem)
     {
         typedef Pass<P> PS;
-        static_assert(P > 1 || PS::NBF % PADW == 0, "reads of the padded first exchange need a PADW-aligned butterfly stride");
+        static_assert(P > 1 || PS::NBF % PADW == 0 || 2 * PS::NBF == PADW, "reads of the padded first exchange need a PADW-aligned butterfly stride");
 #pragma unroll
         for (int u = 0; u < PS::U; u++) {
             int batch, j; PS::map(tid, u, batch, j);
