@@ -124,7 +124,8 @@ struct fdc_chan {
      * that the tail of one chunk's kernels overlaps the head of the next chunk's */
     enum { NWORK = 4 };
     cudaStream_t ws[NWORK];
-    DevBuf w_spec[NWORK], w_mid[NWORK];
+    DevBuf w_spec[NWORK], w_mid[NWORK], w_ring[NWORK];   /* w_ring: mid | spectrum in one allocation when L2 persistence is on */
+    size_t l2_window[NWORK];
     cudaEvent_t ev_start, ev_done[NWORK];
     /* host path: NSLOT pipelined chunk slots */
     enum { NSLOT = 4 };
@@ -138,7 +139,7 @@ struct fdc_chan {
     fdc_chan() : tw4(0), stream(0), ev_start(0), host_chunk(0), prof(false)
     {
         for (int i = 0; i < NSLOT; i++) hs[i] = 0;
-        for (int i = 0; i < NWORK; i++) { ws[i] = 0; ev_done[i] = 0; }
+        for (int i = 0; i < NWORK; i++) { ws[i] = 0; ev_done[i] = 0; l2_window[i] = 0; }
     }
     cudaEvent_t ev()
     {
@@ -365,9 +366,29 @@ int fdc_chan_work_device_slab(fdc_chan* c, const void* d_in_v, long nblocks, voi
     cudaStream_t wk[fdc_chan::NWORK];
     for (int i = 0; i < fdc_chan::NWORK; i++) wk[i] = nw == 1 ? s : c->ws[i];
     const long ring = std::min(nblocks, c->chunk_blocks);
+    const bool l2pin = tuning().l2_persist_mb > 0 && !d_spectrum && c->big;
+    float2* ring_spec[fdc_chan::NWORK]; float2* ring_mid[fdc_chan::NWORK];
     for (int i = 0; i < nw; i++) {
-        if (!d_spectrum && !c->w_spec[i].reserve(sizeof(float2) * (size_t)ring * c->N)) return cuda_fail(cudaGetLastError(), "spectrum ring");
-        if (c->big && !c->w_mid[i].reserve(sizeof(float2) * (size_t)ring * c->N)) return cuda_fail(cudaGetLastError(), "four-step intermediate");
+        const size_t rb = sizeof(float2) * (size_t)ring * c->N;
+        if (l2pin) {
+            /* experiment: keep the K1 -> K2 hand-over (intermediate + spectrum rings) in the persisting part of L2 */
+            if (!c->w_ring[i].reserve(2 * rb)) return cuda_fail(cudaGetLastError(), "hand-over ring");
+            ring_mid[i] = (float2*)c->w_ring[i].p; ring_spec[i] = ring_mid[i] + (size_t)ring * c->N;
+            if (c->l2_window[i] != 2 * rb) {
+                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)tuning().l2_persist_mb << 20);
+                cudaStreamAttrValue av; memset(&av, 0, sizeof(av));
+                av.accessPolicyWindow.base_ptr = c->w_ring[i].p; av.accessPolicyWindow.num_bytes = 2 * rb;
+                av.accessPolicyWindow.hitRatio = 1.0f; av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                const cudaError_t pe = cudaStreamSetAttribute(wk[i], cudaStreamAttributeAccessPolicyWindow, &av);
+                if (pe != cudaSuccess) return cuda_fail(pe, "L2 access policy window");
+                c->l2_window[i] = 2 * rb;
+            }
+            continue;
+        }
+        if (!d_spectrum && !c->w_spec[i].reserve(rb)) return cuda_fail(cudaGetLastError(), "spectrum ring");
+        if (c->big && !c->w_mid[i].reserve(rb)) return cuda_fail(cudaGetLastError(), "four-step intermediate");
+        ring_spec[i] = (float2*)c->w_spec[i].p; ring_mid[i] = (float2*)c->w_mid[i].p;
     }
     if (nw > 1) {
         if ((e = cudaEventRecord(c->ev_start, s)) != cudaSuccess) return cuda_fail(e, "event record");
@@ -378,8 +399,8 @@ int fdc_chan_work_device_slab(fdc_chan* c, const void* d_in_v, long nblocks, voi
         const bool head = b0 < nh;
         const long nb = head ? nh : std::min(c->chunk_blocks, nblocks - b0);
         const float2* in = head ? (const float2*)c->d_stage.p + c->ovl : d_in + b0 * c->hop;
-        float2* spec = d_spectrum ? d_spectrum + b0 * c->N : (float2*)c->w_spec[w].p;
-        if (chan_enqueue_chunk(c, in, nb, spec, (float2*)c->w_mid[w].p, d_out, slab_blocks, slab_first_block + b0, c->blockcount + b0, wk[w])) return -1;
+        float2* spec = d_spectrum ? d_spectrum + b0 * c->N : ring_spec[w];
+        if (chan_enqueue_chunk(c, in, nb, spec, ring_mid[w], d_out, slab_blocks, slab_first_block + b0, c->blockcount + b0, wk[w])) return -1;
         b0 += nb;
     }
     if (nw > 1) {
