@@ -19,3 +19,23 @@ def test_host_emulation_of_all_kernels():
     lines = r.stdout.strip().splitlines()
     assert r.returncode == 0 and lines[-1] == "EMU OK", "\n".join(l for l in lines if not l.endswith(" ok"))
     assert len(lines) > 100
+
+
+def test_host_emulation_under_address_sanitizer():
+    """the same program with -fsanitize=address,undefined: every loader / storer address of every emulated kernel stays
+    inside its (exactly sized) buffer, including ragged last tiles and clamped signals (compute-sanitizer is not
+    available on the GPU pool, this is the bounds check of the kernels' index arithmetic)"""
+    out_dir = os.path.join(ROOT, "tests", "emu", "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    exe = os.path.join(out_dir, "emu_check_asan")
+    r = subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-ffp-contract=off",
+                        "-DFDC_HOST_EMU", "-I" + os.path.join(ROOT, "gr-fdc_b200", "csrc"),
+                        os.path.join(ROOT, "tests", "emu", "emu_engine_check.cc"), "-o", exe], capture_output=True, text=True)
+    if r.returncode != 0 and "sanitize" in r.stderr:
+        import pytest
+        pytest.skip("sanitizer runtime not installed")
+    assert r.returncode == 0, r.stderr[-3000:]
+    env = dict(os.environ); env["ASAN_OPTIONS"] = "detect_leaks=0"
+    r = subprocess.run([exe], capture_output=True, text=True, env=env)
+    assert r.returncode == 0 and r.stdout.strip().splitlines()[-1] == "EMU OK", (r.stdout[-1500:] + r.stderr[-3000:])
+    assert "runtime error" not in r.stderr and "AddressSanitizer" not in r.stderr
