@@ -198,13 +198,21 @@ def run_cfg3(args, rank, world, local):
     d_spec = torch.empty(nb * N * 2, dtype=torch.float32, device=d_in.device)
     stats = {"pdus": 0, "samples": 0}
 
+    # GNU Radio runs every block in its own thread (thread-per-block scheduler): the 18 sink blocks work concurrently, each
+    # single threaded.  Same here for both arms: one worker thread per block (the C ABI contexts are independent).
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(max_workers=min(len(sd) + len(pc), os.cpu_count() or 1))
+
+    def one(b):
+        b.work_device(nb, d_spec.data_ptr())
+        ms = b.messages()
+        return len(ms), sum(m["nsamples"] for m in ms)
+
     def step():
         front.work_device(d_in.data_ptr(), nb, 0, d_spec.data_ptr(), 0)
         front.sync()
-        for b in sd + pc:
-            b.work_device(nb, d_spec.data_ptr())
-            for m in b.messages():
-                stats["pdus"] += 1; stats["samples"] += m["nsamples"]
+        for n, smp in pool.map(one, sd + pc):
+            stats["pdus"] += n; stats["samples"] += smp
 
     for _ in range(W):
         step()
@@ -233,14 +241,13 @@ def run_cfg3(args, rank, world, local):
         t1 = time.perf_counter(); reps = 0
         while time.perf_counter() - t1 < 10.0 and reps < 16:
             _, sp = chain.run(x, nthreads=cores, want_spectrum=True, want_outputs=False)
-            for b in rsd + rpc:
-                b.work(sp); b.messages()
+            list(pool.map(lambda b: (b.work(sp), b.messages()), rsd + rpc))
             reps += 1
         dtc = time.perf_counter() - t1
         ref.set_fft_mode(0)
         cpu = {"value": reps * nb * hop / dtc / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "reference",
                "sample": "%d x %d blocks, reference overlap_save + restated fft_vcc on all cores, then the unmodified SegmentDetection x2 and "
-                         "PowerActivationChannel x16 blocks (single threaded, as GNU Radio runs one work() per block), %.1f s" % (reps, nb, dtc)}
+                         "PowerActivationChannel x16 blocks, one thread per block as under GNU Radio's thread-per-block scheduler, %.1f s" % (reps, nb, dtc)}
     line = {"metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": dt / K * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "cfg3_fft16384_r4_activity", "fft": N, "overlap": N // R, "hop": hop, "segments": segs,

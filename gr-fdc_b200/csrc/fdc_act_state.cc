@@ -128,17 +128,19 @@ static bool fipair_desc(fipair& a, fipair& b) { return a.first > b.first; }
 
 void SegmentState::candidates(const EdgeBlock& e, std::deque<std::array<long, 2> >& poss) const
 {
-    /* lib/SegmentDetection_impl.cc:195-244; the same containers and std::sort call so that ties between equal
-     * ratios resolve identically */
-    std::deque<fipair> rise;
-    std::deque<size_t> fall;
+    /* lib/SegmentDetection_impl.cc:195-244.  Same order of operations as the reference: rising edges sorted by ratio with
+     * the same std::sort call (introsort makes the same comparisons and moves on any random-access range, so ties between
+     * equal ratios resolve as in the reference's deque), then walked from the strongest down.  The scratch vectors live for
+     * the thread's lifetime: no allocation per block. */
+    static thread_local std::vector<fipair> rise;
+    static thread_local std::vector<size_t> fall;
+    rise.clear(); fall.clear();
     for (size_t n = 0; n < e.rise.size(); n++) rise.push_back(fipair(e.rise[n].first, (size_t)e.rise[n].second * (size_t)g.D + (size_t)g.start));
     for (size_t n = 0; n < e.fall.size(); n++) fall.push_back(((size_t)e.fall[n] + 1) * (size_t)g.D + (size_t)g.start);
     std::sort(rise.begin(), rise.end(), fipair_desc);
-    while (rise.size()) {
-        const size_t poss_start = rise.front().second;
-        rise.pop_front();
-        std::deque<size_t>::iterator next_end = std::upper_bound(fall.begin(), fall.end(), poss_start);
+    for (size_t r = 0; r < rise.size(); r++) {
+        const size_t poss_start = rise[r].second;
+        std::vector<size_t>::iterator next_end = std::upper_bound(fall.begin(), fall.end(), poss_start);
         if (next_end == fall.end()) continue;
         bool overlapping = false;
         for (size_t k = 0; k < poss.size(); k++)
@@ -230,7 +232,7 @@ void SegmentState::emit_final(ActiveChannel& c, long blockcount, std::vector<Act
 {
     /* emit_channel, lib/SegmentDetection_impl.cc:437-482: everything buffered, even nothing */
     ActOp o; o.kind = ActOp::EMIT; o.uid = c.uid; o.job = -1; o.ntake = -1; o.blocksamples = c.outputsamples;
-    o.meta = meta(c, blockcount, true);
+    o.meta = std::make_shared<MsgMeta>(meta(c, blockcount, true));
     ops.push_back(o);
     c.ndata = 0;
 }
@@ -242,7 +244,7 @@ void SegmentState::emit_partial(ActiveChannel& c, long blockcount, std::vector<A
     const int ntx = maxblocks == 0 ? c.ndata : maxblocks;
     if (ntx <= 0) return;
     ActOp o; o.kind = ActOp::EMIT; o.uid = c.uid; o.job = -1; o.ntake = ntx; o.blocksamples = c.outputsamples;
-    o.meta = meta(c, blockcount, false);
+    o.meta = std::make_shared<MsgMeta>(meta(c, blockcount, false));
     ops.push_back(o);
     c.ndata -= ntx;
     c.part++;
@@ -336,7 +338,8 @@ void PacState::emit(bool fin, std::vector<ActOp>& ops)
 {
     /* emit_data, lib/PowerActivationChannel_impl.cc:212-258 */
     ActOp o; o.kind = ActOp::EMIT; o.uid = uid; o.job = -1; o.ntake = -1; o.blocksamples = output_len;
-    MsgMeta& m = o.meta;
+    o.meta = std::make_shared<MsgMeta>();
+    MsgMeta& m = *o.meta;
     m.id = msgID + (fin ? std::string(".fin") : std::string(".part"));
     m.finalized = fin; m.part = part;
     m.rel_cfreq = (double)(extract_start + extract_stop) / 2.0 / (double)blocklen;

@@ -14,6 +14,7 @@
 #include <array>
 #include <complex>
 #include <deque>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -45,7 +46,7 @@ struct ActOp {
     int job;                      /* PUSH: index into the call's job list */
     int ntake;                    /* EMIT: number of buffered blocks to publish, -1 = all */
     int blocksamples;             /* EMIT: samples per buffered block */
-    MsgMeta meta;
+    std::shared_ptr<MsgMeta> meta;  /* EMIT only: PUSH / DROP ops (one per extracted block) stay small and string free */
 };
 
 std::string current_time_string();            /* "%Y-%m-%d-%H-%M-%S" */

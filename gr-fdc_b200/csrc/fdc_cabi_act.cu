@@ -43,7 +43,22 @@ struct ActEngine {
     cudaStream_t s;
     DevBuf d_in, d_hist, d_tab, d_jobs, d_out, d_P, d_cnt, d_rr, d_ri, d_fi, d_pw;
     PinBuf h_out, h_misc;
-    std::map<long, std::deque<std::vector<cfloat> > > pending;
+    /* buffered output blocks of one active channel (the reference's `data` deque of vectors): one contiguous, append-only
+     * run of samples + the number of blocks in it; EMIT takes blocks from the front */
+    struct Pending {
+        std::vector<cfloat> data; size_t head; size_t nblocks;
+        Pending() : head(0), nblocks(0) {}
+        void push(const cfloat* p, size_t n) { data.insert(data.end(), p, p + n); nblocks++; }
+        void take(size_t nb, size_t blocksamples, std::vector<cfloat>* out)
+        {
+            const size_t n = nb * blocksamples;
+            if (out) out->assign(data.begin() + head, data.begin() + head + n);
+            head += n; nblocks -= nb;
+            if (nblocks == 0) { data.clear(); head = 0; }
+            else if (head > (1u << 20)) { data.erase(data.begin(), data.begin() + head); head = 0; }
+        }
+    };
+    std::map<long, Pending> pending;
     std::vector<OutMsg> msgs;
     long uid_counter;
     bool logic_only;               /* host-logic hooks: no device, messages carry metadata and sample counts only */
@@ -66,13 +81,13 @@ struct ActEngine {
         if (logic_only) {
             for (size_t i = 0; i < ops.size(); i++) {
                 const ActOp& o = ops[i];
-                if (o.kind == ActOp::PUSH) pending[o.uid].push_back(std::vector<cfloat>());
+                if (o.kind == ActOp::PUSH) pending[o.uid].nblocks++;
                 else if (o.kind == ActOp::DROP) pending.erase(o.uid);
                 else {
-                    std::deque<std::vector<cfloat> >& q = pending[o.uid];
-                    const size_t ntake = o.ntake < 0 ? q.size() : std::min((size_t)o.ntake, q.size());
-                    OutMsg m; m.meta = o.meta; m.logic_samples = (long)(ntake * (size_t)o.blocksamples);
-                    q.erase(q.begin(), q.begin() + ntake);
+                    Pending& q = pending[o.uid];
+                    const size_t ntake = o.ntake < 0 ? q.nblocks : std::min((size_t)o.ntake, q.nblocks);
+                    OutMsg m; m.meta = *o.meta; m.logic_samples = (long)(ntake * (size_t)o.blocksamples);
+                    q.nblocks -= ntake;
                     if (m.meta.publish) msgs.push_back(m);
                 }
             }
@@ -114,16 +129,14 @@ struct ActEngine {
             const ActOp& o = ops[i];
             if (o.kind == ActOp::PUSH) {
                 const ActJob& j = jobs[o.job];
-                pending[o.uid].push_back(std::vector<cfloat>(res + dst[o.job], res + dst[o.job] + (j.L - j.skip)));
+                pending[o.uid].push(res + dst[o.job], (size_t)(j.L - j.skip));
             } else if (o.kind == ActOp::DROP) {
                 pending.erase(o.uid);
             } else {
-                std::deque<std::vector<cfloat> >& q = pending[o.uid];
-                const size_t ntake = o.ntake < 0 ? q.size() : std::min((size_t)o.ntake, q.size());
-                OutMsg m; m.meta = o.meta;
-                m.data.reserve(ntake * (size_t)o.blocksamples);
-                for (size_t b = 0; b < ntake; b++) m.data.insert(m.data.end(), q[b].begin(), q[b].end());
-                q.erase(q.begin(), q.begin() + ntake);
+                Pending& q = pending[o.uid];
+                const size_t ntake = o.ntake < 0 ? q.nblocks : std::min((size_t)o.ntake, q.nblocks);
+                OutMsg m; m.meta = *o.meta;
+                q.take(ntake, (size_t)o.blocksamples, &m.data);
                 if (!m.meta.filename.empty()) {
                     FILE* fh = fopen(m.meta.filename.c_str(), "wb");
                     if (!fh) std::cerr << "Cannot write to file " << m.meta.filename << std::endl;
@@ -256,6 +269,7 @@ int fdc_pac_logic_work(fdc_pac* b, int n, const float* pwr)
 {
     if (!b || !b->e.logic_only || n < 0) return fail("fdc_pac_logic_work: needs a context from fdc_pac_create_logic");
     std::vector<ActJob> jobs; std::vector<ActOp> ops;
+    jobs.reserve((size_t)n * 16 + 16); ops.reserve((size_t)n * 18 + 16);     /* no reallocation (and op copies) while the blocks are walked */
     for (int i = 0; i < n; i++) b->st.block(i, pwr[i], b->e.uid_counter, jobs, ops);
     return b->e.finish(0, jobs, ops, 0) ? -1 : n;
 }
@@ -272,6 +286,7 @@ int fdc_pac_work_device(fdc_pac* b, int n, const void* d_in, void* stream)
     if (ce != cudaSuccess) return cuda_fail(ce, "band power");
     const float* pw = (const float*)b->e.h_misc.p;
     std::vector<ActJob> jobs; std::vector<ActOp> ops;
+    jobs.reserve((size_t)n * 16 + 16); ops.reserve((size_t)n * 18 + 16);     /* no reallocation (and op copies) while the blocks are walked */
     for (int i = 0; i < n; i++) b->st.block(i, pw[i], b->e.uid_counter, jobs, ops);
     if (b->e.finish(rows, jobs, ops, st)) return -1;
     if (b->e.save_hist(rows, n, st)) return -1;
@@ -371,6 +386,7 @@ int fdc_segdet_logic_work(fdc_segdet* b, int n, const float* P)
     std::vector<EdgeBlock> edges;
     classify_rows(P, n, (int)b->st.g.M, b->thresh, 0, edges);
     std::vector<ActJob> jobs; std::vector<ActOp> ops;
+    jobs.reserve((size_t)n * 16 + 16); ops.reserve((size_t)n * 18 + 16);     /* no reallocation (and op copies) while the blocks are walked */
     for (int i = 0; i < n; i++) { b->st.block(i, edges[(size_t)i], b->blockcount, b->e.uid_counter, jobs, ops); b->blockcount++; }
     if (n > 0) b->det.last_power.assign(P + (size_t)(n - 1) * b->st.g.M, P + (size_t)n * b->st.g.M);
     return b->e.finish(0, jobs, ops, 0) ? -1 : n;
@@ -384,6 +400,7 @@ int fdc_segdet_work_device(fdc_segdet* b, int n, const void* d_in, void* stream)
     std::vector<EdgeBlock> edges;
     if (b->det.run(b->e, rows, n, b->st.g, b->thresh, 0, 0, edges, st)) return -1;
     std::vector<ActJob> jobs; std::vector<ActOp> ops;
+    jobs.reserve((size_t)n * 16 + 16); ops.reserve((size_t)n * 18 + 16);     /* no reallocation (and op copies) while the blocks are walked */
     for (int i = 0; i < n; i++) { b->st.block(i, edges[(size_t)i], b->blockcount, b->e.uid_counter, jobs, ops); b->blockcount++; }
     if (b->e.finish(rows, jobs, ops, st)) return -1;
     if (b->e.save_hist(rows, n, st)) return -1;
@@ -492,6 +509,7 @@ int fdc_actdet_logic_work(fdc_actdet* b, int n, const float* P)
     long rowlen = 0;
     for (size_t s = 0; s < b->segs.size(); s++) rowlen += b->segs[s].g.M;
     std::vector<ActJob> jobs; std::vector<ActOp> ops;
+    jobs.reserve((size_t)n * 16 + 16); ops.reserve((size_t)n * 18 + 16);     /* no reallocation (and op copies) while the blocks are walked */
     std::vector<EdgeBlock> eb;
     for (int i = 0; i < n; i++) {
         long off = 0;
@@ -516,6 +534,7 @@ int fdc_actdet_work_device(fdc_actdet* b, int n, const void* d_in, void* stream)
     for (size_t s = 0; s < b->segs.size(); s++)
         if (b->det[s].run(b->e, rows, n, b->segs[s].g, b->thresh, 1, 1, edges[s], st)) return -1;
     std::vector<ActJob> jobs; std::vector<ActOp> ops;
+    jobs.reserve((size_t)n * 16 + 16); ops.reserve((size_t)n * 18 + 16);     /* no reallocation (and op copies) while the blocks are walked */
     for (int i = 0; i < n; i++) {
         /* detection in every segment first, then extraction segment by segment (work(), …vcm_impl.cc:553-566); both orders coincide
          * because a segment's detection only touches its own channel list */
