@@ -188,7 +188,10 @@ struct ExtractParams {
     int glob_phase0;       /* (global index of the chunk's first block) mod nphase */
     int nphase;
     int tma_ok;            /* every slice of this launch is 16-byte aligned (even f, aligned spectrum base and stride) */
+    int phase_mask;        /* nphase - 1 when nphase is a power of two (the hier block's relinvovl always is), else -1 */
 };
+/* x mod nphase without an integer division when nphase is a power of two */
+FDC_HD unsigned phase_mod(const ExtractParams& p, unsigned x) { return p.phase_mask >= 0 ? (x & (unsigned)p.phase_mask) : x % (unsigned)p.nphase; }
 template <int L, int B> struct ExtractLoader {
     struct Ctx { const float2* x; const float2* w; };
     static constexpr bool HAS_FINISH = true;
@@ -199,7 +202,7 @@ template <int L, int B> struct ExtractLoader {
         int s = ytile * B + batch;
         if (s >= p.nsel) s = p.nsel - 1;                   /* ragged last tile: recompute the last channel, store nothing */
         const ChanDev& ch = p.chans[s];
-        const unsigned phase = (bphase * (unsigned)ch.shift) % (unsigned)p.nphase;
+        const unsigned phase = phase_mod(p, bphase * (unsigned)ch.shift);
         c.x = p.spec + (b * p.spec_stride + ch.f + j);
         c.w = p.tables + (ch.tab_off + (long)phase * L + j);
         return c;
@@ -246,7 +249,7 @@ template <int L, int B> struct ExtractStageLoader {
     {
         Ctx c;
         const ChanDev& ch = p.chans[signal(batch)];
-        const unsigned phase = (bphase * (unsigned)ch.shift) % (unsigned)p.nphase;
+        const unsigned phase = phase_mod(p, bphase * (unsigned)ch.shift);
         c.x = stage + (batch * L + j);
         c.w = p.tables + (ch.tab_off + (long)phase * L + j);
         return c;
@@ -262,7 +265,7 @@ template <int L, int B> struct ExtractStageTiles {
     FDC_HD int ninner() const { return p.ny; }
     FDC_HD ExtractStageLoader<L, B> loader(TilePos t) const
     {
-        return ExtractStageLoader<L, B>{p, t.inner, (long)t.outer, ((unsigned)p.glob_phase0 + (unsigned)t.outer) % (unsigned)p.nphase, stage};
+        return ExtractStageLoader<L, B>{p, t.inner, (long)t.outer, phase_mod(p, (unsigned)p.glob_phase0 + (unsigned)t.outer), stage};
     }
     FDC_HD ExtractStorer<L, B> storer(TilePos t) const { return ExtractStorer<L, B>{p, t.inner, (long)t.outer}; }
 };
@@ -271,7 +274,7 @@ template <int L, int B> struct ExtractTiles {           /* tile = block * ny + c
     FDC_HD int ninner() const { return p.ny; }
     FDC_HD ExtractLoader<L, B> loader(TilePos t) const
     {
-        return ExtractLoader<L, B>{p, t.inner, (long)t.outer, ((unsigned)p.glob_phase0 + (unsigned)t.outer) % (unsigned)p.nphase};
+        return ExtractLoader<L, B>{p, t.inner, (long)t.outer, phase_mod(p, (unsigned)p.glob_phase0 + (unsigned)t.outer)};
     }
     FDC_HD ExtractStorer<L, B> storer(TilePos t) const { return ExtractStorer<L, B>{p, t.inner, (long)t.outer}; }
 };

@@ -210,7 +210,7 @@ template <int L, int E = 16> static void check_extract(int N, int nchan, long nb
     const std::vector<float2> tw = pass_twiddles(L, E);
     ExtractParams p; p.spec = spec.data(); p.spec_stride = N; p.tables = tables.data(); p.chans = chans.data();
     p.nsel = nchan; p.ny = (nchan + B - 1) / B; p.out = out.data(); p.nb = nb; p.call_blocks = call_blocks; p.call_blk0 = call_blk0;
-    p.glob_phase0 = glob_phase0; p.nphase = nphase;
+    p.glob_phase0 = glob_phase0; p.nphase = nphase; p.tma_ok = 0; p.phase_mask = (nphase & (nphase - 1)) == 0 ? nphase - 1 : -1;
     run_tiles<ENG>(ExtractTiles<L, B>{p}, nb * p.ny, tw.data());
     double worst = 0;
     for (int i = 0; i < nchan; i++)
@@ -258,7 +258,7 @@ template <int L> static void check_extract_staged(int N, int nchan, long nb, int
     std::vector<float2> out((size_t)(nb * prefix));
     const std::vector<float2> tw = pass_twiddles(L, 32);
     ExtractParams p; p.spec = spec.data(); p.spec_stride = N; p.tables = tables.data(); p.chans = chans.data(); p.nsel = nchan;
-    p.ny = (nchan + B - 1) / B; p.out = out.data(); p.nb = nb; p.call_blocks = nb; p.call_blk0 = 0; p.glob_phase0 = 0; p.nphase = nphase; p.tma_ok = 1;
+    p.ny = (nchan + B - 1) / B; p.out = out.data(); p.nb = nb; p.call_blocks = nb; p.call_blk0 = 0; p.glob_phase0 = 0; p.nphase = nphase; p.tma_ok = 1; p.phase_mask = (nphase & (nphase - 1)) == 0 ? nphase - 1 : -1;
     ExtractStageTiles<L, B> tiles{p, stage.data()};
     std::vector<float2> smem(ENG::SMEM_ELEMS);
     std::vector<std::array<float2, 32>> regs(ENG::T);
