@@ -590,19 +590,18 @@ int fdc_chan_work_host(fdc_chan* c, const void* in_v, long nblocks, void* const*
             if (e != cudaSuccess) return cuda_fail(e, "D2H spectrum");
         }
     }
-    for (int i = 0; i < fdc_chan::NSLOT; i++) if ((e = cudaStreamSynchronize(c->hs[i])) != cudaSuccess) return cuda_fail(e, "sync");
-    /* history for the next call straight from the caller's buffer */
+    /* history for the next call = the last ovl samples of the last chunk's device input [halo | samples]: a device copy on
+     * that chunk's stream into the spare buffer (the first chunk may still be reading the current one), swapped in below */
     if (c->ovl) {
-        const long n_new = nblocks * c->hop;
-        if (n_new >= c->ovl) e = cudaMemcpy(c->d_hist.p, in + (n_new - c->ovl), sizeof(float2) * (size_t)c->ovl, cudaMemcpyHostToDevice);
-        else {
-            float2* h = (float2*)c->d_hist.p; float2* h2 = (float2*)c->d_hist2.p;
-            e = cudaMemcpy(h2, h + n_new, sizeof(float2) * (size_t)(c->ovl - n_new), cudaMemcpyDeviceToDevice);
-            if (e == cudaSuccess) e = cudaMemcpy(h2 + (c->ovl - n_new), in, sizeof(float2) * (size_t)n_new, cudaMemcpyHostToDevice);
-            c->d_hist.swap(c->d_hist2);
-        }
+        const int last = (slot + fdc_chan::NSLOT - 1) % fdc_chan::NSLOT;
+        const long last_b0 = ((nblocks - 1) / chunk) * chunk, last_nb = nblocks - last_b0;
+        e = cudaMemcpyAsync(c->d_hist2.p, (const float2*)c->h_in[last].p + last_nb * c->hop, sizeof(float2) * (size_t)c->ovl,
+                            cudaMemcpyDeviceToDevice, c->hs[last]);
         if (e != cudaSuccess) return cuda_fail(e, "history save");
     }
+    const int used = (int)std::min((long)fdc_chan::NSLOT, (nblocks + chunk - 1) / chunk);
+    for (int i = 0; i < used; i++) if ((e = cudaStreamSynchronize(c->hs[i])) != cudaSuccess) return cuda_fail(e, "sync");
+    if (c->ovl) c->d_hist.swap(c->d_hist2);
     c->blockcount += nblocks;
     return 0;
 }

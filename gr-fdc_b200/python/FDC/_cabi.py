@@ -120,6 +120,8 @@ def lib():
     """Load libfdc_b200.so (once).  Raises FDCError when it has not been built."""
     global _lib
     if _lib is None:
+        if os is None:                 # interpreter shutdown: module globals are being torn down, nothing to load any more
+            raise FDCError("interpreter is shutting down")
         if not os.path.exists(LIB_PATH):
             raise FDCError("libfdc_b200.so not built (%s): run `python -c 'import __graft_entry__ as g; g.build()'` "
                            "or `make -C gr-fdc_b200/csrc`; there is no CPU fallback" % LIB_PATH)
@@ -131,6 +133,11 @@ def lib():
             fn.restype = res
             fn.argtypes = args
         _lib = L
+    return _lib
+
+
+def loaded():
+    """The library if it has been loaded already, else None (destructors use this: they must not load or raise)."""
     return _lib
 
 

@@ -26,8 +26,9 @@ class _MsgBlock(_SyncBlock):
         return getattr(lib(), "fdc_%s_%s" % (self._prefix, name))
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            self._fn("destroy")(self._h); self._h = None
+        L = _cabi.loaded() if _cabi is not None else None
+        if L is not None and getattr(self, "_h", None):
+            getattr(L, "fdc_%s_destroy" % self._prefix)(self._h); self._h = None
 
     def message_ports_out(self):
         return ["msgout"]

@@ -52,8 +52,9 @@ class overlap_save(_SyncBlock):
         self._h = handle(lib().fdc_overlap_save_create(self.itemsize, self.outputlen, self.overlaplen), "overlap_save")
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().fdc_overlap_save_destroy(self._h); self._h = None
+        L = _cabi.loaded() if _cabi is not None else None
+        if L is not None and getattr(self, "_h", None):
+            L.fdc_overlap_save_destroy(self._h); self._h = None
 
     def work(self, noutput_items, input_items, output_items):
         check(lib().fdc_overlap_save_work(self._h, int(noutput_items), _ptr(input_items[0]), _ptr(output_items[0])), "overlap_save")
@@ -77,8 +78,9 @@ class vector_cut_vxx(_SyncBlock):
         self._h = handle(lib().fdc_vector_cut_create(self.itemsize, self.veclen, self.offset, self.blocklen), "vector_cut_vxx")
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().fdc_vector_cut_destroy(self._h); self._h = None
+        L = _cabi.loaded() if _cabi is not None else None
+        if L is not None and getattr(self, "_h", None):
+            L.fdc_vector_cut_destroy(self._h); self._h = None
 
     def work(self, noutput_items, input_items, output_items):
         check(lib().fdc_vector_cut_work(self._h, int(noutput_items), _ptr(input_items[0]), _ptr(output_items[0])), "vector_cut_vxx")
@@ -103,8 +105,9 @@ class phase_shifting_windowing_vcc(_SyncBlock):
                                               int(windowtype)), "phase_shifting_windowing_vcc")
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().fdc_psw_destroy(self._h); self._h = None
+        L = _cabi.loaded() if _cabi is not None else None
+        if L is not None and getattr(self, "_h", None):
+            L.fdc_psw_destroy(self._h); self._h = None
 
     def work(self, noutput_items, input_items, output_items):
         check(lib().fdc_psw_work(self._h, int(noutput_items), _ptr(input_items[0]), _ptr(output_items[0])), "psw")
@@ -141,8 +144,9 @@ class fft_vcc(_SyncBlock):
         self._h = handle(lib().fdc_fft_create(self.n, int(bool(forward)), int(bool(shift))), "fft_vcc")
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().fdc_fft_destroy(self._h); self._h = None
+        L = _cabi.loaded() if _cabi is not None else None
+        if L is not None and getattr(self, "_h", None):
+            L.fdc_fft_destroy(self._h); self._h = None
 
     def work(self, noutput_items, input_items, output_items):
         check(lib().fdc_fft_work(self._h, int(noutput_items), _ptr(input_items[0]), _ptr(output_items[0])), "fft_vcc")
@@ -190,8 +194,9 @@ class Channelizer(object):
         self._h = handle(lib().fdc_chan_create(self.N, self.ovl, self.nphase, self.nchan, C.cast(arr, C.c_void_p)), "fdc_chan_create")
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().fdc_chan_destroy(self._h); self._h = None
+        L = _cabi.loaded() if _cabi is not None else None
+        if L is not None and getattr(self, "_h", None):
+            L.fdc_chan_destroy(self._h); self._h = None
 
     @property
     def blockcount(self):
