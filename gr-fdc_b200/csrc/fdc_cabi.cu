@@ -284,6 +284,7 @@ fdc_chan* fdc_chan_create(int N, int ovl, int nphase, int nchan, const fdc_chan_
 
 void fdc_chan_destroy(fdc_chan* c)
 {
+    OnDevice on_dev(c ? c->dev : -1);
     if (!c) return;
     cudaDeviceSynchronize();
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -298,6 +299,7 @@ int fdc_chan_hop(const fdc_chan* c) { return c ? c->hop : -1; }
 long fdc_chan_blockcount(const fdc_chan* c) { return c ? c->blockcount : -1; }
 int fdc_chan_reset(fdc_chan* c)
 {
+    OnDevice on_dev(c ? c->dev : -1);
     if (!c) return fail("null context");
     cudaDeviceSynchronize();
     c->blockcount = 0;
@@ -312,6 +314,7 @@ int fdc_chan_seek(fdc_chan* c, long first_block)
 }
 int fdc_chan_set_history(fdc_chan* c, const void* host)
 {
+    OnDevice on_dev(c ? c->dev : -1);
     if (!c || !host) return fail("fdc_chan_set_history: bad arguments");
     if (c->ovl == 0) return 0;
     cudaDeviceSynchronize();
@@ -344,6 +347,7 @@ int fdc_chan_work_device(fdc_chan* c, const void* d_in_v, long nblocks, void* d_
 int fdc_chan_work_device_slab(fdc_chan* c, const void* d_in_v, long nblocks, void* d_out_v, long slab_blocks, long slab_first_block,
                               void* d_spectrum_v, void* stream)
 {
+    OnDevice on_dev(c ? c->dev : -1);
     if (!c) return fail("null context");
     if (nblocks < 0) return fail("nblocks < 0");
     if (slab_first_block < 0 || slab_first_block + nblocks > slab_blocks) return fail("fdc_chan_work_device_slab: blocks outside the slab");
@@ -419,6 +423,7 @@ int fdc_chan_work_device_slab(fdc_chan* c, const void* d_in_v, long nblocks, voi
  * fft-shifted, unnormalised spectra; only normalize_input (x 1/N, :216) and the per-channel chains run. */
 int fdc_chan_work_spectrum_device(fdc_chan* c, const void* d_spec_in_v, long nblocks, void* d_out_v, void* d_spectrum_v, void* stream)
 {
+    OnDevice on_dev(c ? c->dev : -1);
     if (!c) return fail("null context");
     if (nblocks < 0) return fail("nblocks < 0");
     if (nblocks == 0) return 0;
@@ -475,6 +480,7 @@ int fdc_ipc_close(void* d_ptr)
 
 int fdc_chan_set_profiling(fdc_chan* c, int enable)
 {
+    OnDevice on_dev(c ? c->dev : -1);
     if (!c) return fail("null context");
     cudaDeviceSynchronize();
     c->prof = enable != 0;
@@ -484,6 +490,7 @@ int fdc_chan_set_profiling(fdc_chan* c, int enable)
 }
 int fdc_chan_get_profile(fdc_chan* c, double* ms_fwd, double* ms_extract, long* chunks)
 {
+    OnDevice on_dev(c ? c->dev : -1);
     if (!c) return fail("null context");
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) return cuda_fail(e, "fdc_chan_get_profile");
@@ -512,6 +519,7 @@ int fdc_chan_set_chunk_blocks(fdc_chan* c, int blocks)
 
 int fdc_chan_sync(fdc_chan* c)
 {
+    OnDevice on_dev(c ? c->dev : -1);
     if (!c) return fail("null context");
     cudaError_t e = cudaStreamSynchronize(c->stream);
     for (int i = 0; i < fdc_chan::NWORK && e == cudaSuccess; i++) if (c->ws[i]) e = cudaStreamSynchronize(c->ws[i]);
@@ -524,6 +532,7 @@ int fdc_chan_sync(fdc_chan* c)
  * its own ovl-sample halo from the caller's buffer, so chunks are independent. */
 int fdc_chan_work_host(fdc_chan* c, const void* in_v, long nblocks, void* const* outs, void* spectrum_v)
 {
+    OnDevice on_dev(c ? c->dev : -1);
     if (!c) return fail("null context");
     if (nblocks < 0) return fail("nblocks < 0");
     if (nblocks == 0) return 0;
@@ -611,10 +620,10 @@ int fdc_chan_work_host(fdc_chan* c, const void* in_v, long nblocks, void* const*
 /* ================================================================================================
  * copy / multiply / FFT block replacements (host buffers)
  * ================================================================================================ */
-struct fdc_overlap_save { int itemsize, outputlen, overlaplen; DevBuf d_in, d_out, d_hist; cudaStream_t s; };
-struct fdc_vector_cut { int itemsize, veclen, offset, blocklen; DevBuf d_in, d_out; cudaStream_t s; };
-struct fdc_psw { int blocksize, relinvovl, counter, shift; std::vector<std::complex<float> > tables; DevBuf d_tab, d_in, d_out; cudaStream_t s; };
-struct fdc_fft { int n, forward, shift; DevBuf d_in, d_out; cudaStream_t s; };
+struct fdc_overlap_save : DevCtx { int itemsize, outputlen, overlaplen; DevBuf d_in, d_out, d_hist; cudaStream_t s; };
+struct fdc_vector_cut : DevCtx { int itemsize, veclen, offset, blocklen; DevBuf d_in, d_out; cudaStream_t s; };
+struct fdc_psw : DevCtx { int blocksize, relinvovl, counter, shift; std::vector<std::complex<float> > tables; DevBuf d_tab, d_in, d_out; cudaStream_t s; };
+struct fdc_fft : DevCtx { int n, forward, shift; DevBuf d_in, d_out; cudaStream_t s; };
 
 extern "C" {
 
@@ -633,6 +642,7 @@ fdc_overlap_save* fdc_overlap_save_create(int itemsize, int outputlen, int overl
 }
 int fdc_overlap_save_work(fdc_overlap_save* b, int n, const void* in, void* out)
 {
+    OnDevice on_dev(b ? b->dev : -1);
     if (!b || n < 0) return fail("overlap_save work: bad arguments");
     if (n == 0) return 0;
     const long inplen = b->outputlen - b->overlaplen;
@@ -671,6 +681,7 @@ fdc_vector_cut* fdc_vector_cut_create(int itemsize, int veclen, int offset, int 
 }
 int fdc_vector_cut_work(fdc_vector_cut* b, int n, const void* in, void* out)
 {
+    OnDevice on_dev(b ? b->dev : -1);
     if (!b || n < 0) return fail("vector_cut work: bad arguments");
     if (n == 0) return 0;
     const size_t ib = (size_t)n * b->veclen * b->itemsize, ob = (size_t)n * b->blocklen * b->itemsize;
@@ -701,6 +712,7 @@ fdc_psw* fdc_psw_create(int blocklen, int numphasestates, int shifts, float pass
 }
 int fdc_psw_work(fdc_psw* b, int n, const void* in, void* out)
 {
+    OnDevice on_dev(b ? b->dev : -1);
     if (!b || n < 0) return fail("psw work: bad arguments");
     if (n == 0) return 0;
     const size_t bytes = sizeof(float2) * (size_t)n * b->blocksize;
@@ -736,6 +748,7 @@ fdc_fft* fdc_fft_create(int n, int forward, int shift)
 }
 int fdc_fft_work(fdc_fft* b, long nvec, const void* in, void* out)
 {
+    OnDevice on_dev(b ? b->dev : -1);
     if (!b || nvec < 0) return fail("fft work: bad arguments");
     if (nvec == 0) return 0;
     const size_t bytes = sizeof(float2) * (size_t)nvec * b->n;

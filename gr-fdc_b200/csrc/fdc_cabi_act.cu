@@ -17,7 +17,8 @@ using namespace fdc;
 
 namespace {
 
-struct OutMsg { MsgMeta meta; std::vector<cfloat> data; long logic_samples; OutMsg() : logic_samples(-1) {} };
+/* a published message; the payload lives in the engine's message arena (stable until msg_clear) */
+struct OutMsg { MsgMeta meta; const cfloat* ptr; size_t n; long logic_samples; OutMsg() : ptr(0), n(0), logic_samples(-1) {} };
 
 static void log_line(int verbose, const std::string& logfile, std::string s)
 {
@@ -39,45 +40,121 @@ static void init_logfile(int verbose, const std::string& logfile)
 
 /* device side shared by the three blocks */
 struct ActEngine {
-    int N; int verbose; std::string logfile;
+    int N; int dev; int verbose; std::string logfile;
     cudaStream_t s;
     DevBuf d_in, d_hist, d_tab, d_jobs, d_out, d_P, d_cnt, d_rr, d_ri, d_fi, d_pw;
     PinBuf h_out, h_misc;
-    /* buffered output blocks of one active channel (the reference's `data` deque of vectors): one contiguous, append-only
-     * run of samples + the number of blocks in it; EMIT takes blocks from the front */
+    /* buffered output blocks of one active channel (the reference's `data` deque of vectors).  Blocks extracted in the current
+     * call are only REFERENCED (they sit in the call's result buffer); what is still buffered when the call ends is copied into
+     * `data`.  A burst that is published in the call it was extracted in is therefore copied once, into the message arena. */
     struct Pending {
-        std::vector<cfloat> data; size_t head; size_t nblocks;
-        Pending() : head(0), nblocks(0) {}
-        void push(const cfloat* p, size_t n) { data.insert(data.end(), p, p + n); nblocks++; }
-        void take(size_t nb, size_t blocksamples, std::vector<cfloat>* out)
+        std::vector<cfloat> data; size_t head; size_t nowned;            /* blocks kept from earlier calls: data[head ...] */
+        std::vector<std::pair<const cfloat*, size_t> > segs; size_t seg_head;   /* blocks of this call, in order */
+        size_t nblocks;
+        Pending() : head(0), nowned(0), seg_head(0), nblocks(0) {}
+        void push(const cfloat* p, size_t n) { segs.push_back(std::make_pair(p, n)); nblocks++; }
+        /* the first nb buffered blocks -> out (null: drop them) */
+        void take(size_t nb, size_t blocksamples, cfloat* out)
         {
-            const size_t n = nb * blocksamples;
-            if (out) out->assign(data.begin() + head, data.begin() + head + n);
-            head += n; nblocks -= nb;
-            if (nblocks == 0) { data.clear(); head = 0; }
-            else if (head > (1u << 20)) { data.erase(data.begin(), data.begin() + head); head = 0; }
+            nblocks -= nb;
+            const size_t from_owned = std::min(nb, nowned);
+            if (from_owned) {
+                const size_t n = from_owned * blocksamples;
+                if (out) { memcpy(out, data.data() + head, sizeof(cfloat) * n); out += n; }
+                head += n; nowned -= from_owned; nb -= from_owned;
+                if (nowned == 0) { data.clear(); head = 0; }
+            }
+            for (; nb > 0 && seg_head < segs.size(); nb--, seg_head++) {
+                if (out) { memcpy(out, segs[seg_head].first, sizeof(cfloat) * segs[seg_head].second); out += segs[seg_head].second; }
+            }
+            if (seg_head == segs.size()) { segs.clear(); seg_head = 0; }
+        }
+        /* end of the call: the result buffer is about to be reused */
+        void keep()
+        {
+            if (segs.empty()) return;
+            if (head > (1u << 20)) { data.erase(data.begin(), data.begin() + head); head = 0; }
+            for (size_t k = seg_head; k < segs.size(); k++) { data.insert(data.end(), segs[k].first, segs[k].first + segs[k].second); nowned++; }
+            segs.clear(); seg_head = 0;
         }
     };
+    /* message payloads: fixed-size chunks that are recycled by msg_clear (no allocation, no page faults in steady state);
+     * a chunk never moves, so the pointers handed out by msg_get stay valid until msg_clear */
+    struct Arena {
+        struct Chunk { std::vector<cfloat> buf; size_t used; Chunk(size_t n) : buf(n), used(0) {} };
+        std::vector<std::unique_ptr<Chunk> > chunks; size_t cur;
+        Arena() : cur(0) {}
+        cfloat* alloc(size_t n)
+        {
+            for (; cur < chunks.size(); cur++)
+                if (chunks[cur]->buf.size() - chunks[cur]->used >= n) { cfloat* p = chunks[cur]->buf.data() + chunks[cur]->used; chunks[cur]->used += n; return p; }
+            chunks.push_back(std::unique_ptr<Chunk>(new Chunk(std::max(n, (size_t)1 << 20))));       /* 8 MiB */
+            cur = chunks.size() - 1; chunks[cur]->used = n;
+            return chunks[cur]->buf.data();
+        }
+        void reset() { for (size_t i = 0; i < chunks.size(); i++) chunks[i]->used = 0; cur = 0; }
+    } arena;
+    void msg_clear() { msgs.clear(); arena.reset(); }
     std::map<long, Pending> pending;
     std::vector<OutMsg> msgs;
     long uid_counter;
     bool logic_only;               /* host-logic hooks: no device, messages carry metadata and sample counts only */
 
-    ActEngine() : N(0), verbose(0), s(0), uid_counter(0), logic_only(false) {}
-    ~ActEngine() { if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); } }
+    ActEngine() : N(0), dev(-1), verbose(0), s(0), uid_counter(0), logic_only(false) {}
+    ~ActEngine() { OnDevice on_dev(dev); if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); } }
 
     bool init(int blocklen, const std::vector<cfloat>& tab)
     {
         N = blocklen;
+        if (cudaGetDevice(&dev) != cudaSuccess) return false;
         if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return false;
         if (!d_hist.reserve(sizeof(float2) * (size_t)N) || cudaMemset(d_hist.p, 0, sizeof(float2) * (size_t)N) != cudaSuccess) return false;
         return d_tab.upload(tab.data(), sizeof(cfloat) * tab.size());
     }
 
-    /* run all extraction jobs of a call and replay the ops */
-    int finish(const float2* d_rows, std::vector<ActJob>& jobs, const std::vector<ActOp>& ops, cudaStream_t st)
+    /* run extraction jobs [j0, j1) of a call from the spectrum rows at d_rows (row `row0` of the call is d_rows[0]; the row before
+     * it is `d_prev`, the saved history block when that is null); results land in h_out, job j at dst[j] (job order) */
+    int extract(const float2* d_rows, const float2* d_prev, const std::vector<ActJob>& jobs, size_t j0, size_t j1, int row0,
+                std::vector<long>& dst, long* total_out, cudaStream_t st, float2* d_dst = 0)
     {
-        std::vector<long> dst(jobs.size(), 0);
+        dst.assign(jobs.size(), 0);
+        long total = 0;
+        for (size_t i = j0; i < j1; i++) { dst[i] = total; total += jobs[i].L - jobs[i].skip; }
+        *total_out = total;
+        if (j1 <= j0 || logic_only) return 0;
+        /* group by IFFT length */
+        std::vector<int> order(j1 - j0);
+        for (size_t i = 0; i < order.size(); i++) order[i] = (int)(j0 + i);
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return jobs[a].L < jobs[b].L; });
+        std::vector<ExtractJob> ej(order.size());
+        for (size_t k = 0; k < order.size(); k++) {
+            const ActJob& j = jobs[order[k]];
+            if (!tile_len_supported(j.L)) return fail("activity channel wider than 16384 bins is not supported by the extract kernel");
+            ej[k].row = j.row - row0; ej[k].start = j.start; ej[k].tab_off = (int)j.tab_off; ej[k].skip = j.skip; ej[k].dst_off = dst[order[k]];
+            if (ej[k].row < -1) return fail("activity extract: job refers to a row this shard does not hold");
+        }
+        /* d_dst: the caller's device buffer (possibly peer memory of the sink rank), results stay on the device */
+        if (!d_jobs.upload(ej.data(), sizeof(ExtractJob) * ej.size()) ||
+            (!d_dst && (!d_out.reserve(sizeof(float2) * (size_t)total) || !h_out.reserve(sizeof(float2) * (size_t)total))))
+            return cuda_fail(cudaGetLastError(), "activity extract buffers");
+        size_t k = 0;
+        while (k < order.size()) {
+            size_t e = k; const int L = jobs[order[k]].L;
+            while (e < order.size() && jobs[order[e]].L == L) e++;
+            JobParams p; p.spec = d_rows; p.spec_stride = N; p.hist = d_prev ? d_prev : (const float2*)d_hist.p; p.tables = (const float2*)d_tab.p;
+            p.jobs = (const ExtractJob*)d_jobs.p + k; p.out = d_dst ? d_dst : (float2*)d_out.p; p.njobs = (int)(e - k);
+            const cudaError_t ce = launch_jobs(p, L, st);
+            if (ce != cudaSuccess) return cuda_fail(ce, "activity extract launch");
+            k = e;
+        }
+        cudaError_t ce = d_dst ? cudaSuccess : cudaMemcpyAsync(h_out.p, d_out.p, sizeof(float2) * (size_t)total, cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+        if (ce != cudaSuccess) return cuda_fail(ce, "activity extract D2H");
+        return 0;
+    }
+    /* replay the ops of a call on the extracted blocks (res + dst[job]) -> PDUs / files in the reference's order */
+    void replay(const cfloat* res, const std::vector<long>& dst, const std::vector<ActJob>& jobs, const std::vector<ActOp>& ops)
+    {
         if (logic_only) {
             for (size_t i = 0; i < ops.size(); i++) {
                 const ActOp& o = ops[i];
@@ -88,43 +165,11 @@ struct ActEngine {
                     const size_t ntake = o.ntake < 0 ? q.nblocks : std::min((size_t)o.ntake, q.nblocks);
                     OutMsg m; m.meta = *o.meta; m.logic_samples = (long)(ntake * (size_t)o.blocksamples);
                     q.nblocks -= ntake;
-                    if (m.meta.publish) msgs.push_back(m);
+                    if (m.meta.publish) msgs.push_back(std::move(m));
                 }
             }
-            return 0;
+            return;
         }
-        if (!jobs.empty()) {
-            /* group by IFFT length, assign output offsets */
-            std::vector<int> order(jobs.size());
-            for (size_t i = 0; i < jobs.size(); i++) order[i] = (int)i;
-            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return jobs[a].L < jobs[b].L; });
-            std::vector<ExtractJob> ej(jobs.size());
-            long total = 0;
-            for (size_t k = 0; k < order.size(); k++) {
-                const ActJob& j = jobs[order[k]];
-                if (!tile_len_supported(j.L)) return fail("activity channel wider than 16384 bins is not supported by the extract kernel");
-                ej[k].row = j.row; ej[k].start = j.start; ej[k].tab_off = (int)j.tab_off; ej[k].skip = j.skip; ej[k].dst_off = total;
-                dst[order[k]] = total;
-                total += j.L - j.skip;
-            }
-            if (!d_jobs.upload(ej.data(), sizeof(ExtractJob) * ej.size()) || !d_out.reserve(sizeof(float2) * (size_t)total) ||
-                !h_out.reserve(sizeof(float2) * (size_t)total))
-                return cuda_fail(cudaGetLastError(), "activity extract buffers");
-            size_t k = 0;
-            while (k < order.size()) {
-                size_t e = k; const int L = jobs[order[k]].L;
-                while (e < order.size() && jobs[order[e]].L == L) e++;
-                JobParams p; p.spec = d_rows; p.spec_stride = N; p.hist = (const float2*)d_hist.p; p.tables = (const float2*)d_tab.p;
-                p.jobs = (const ExtractJob*)d_jobs.p + k; p.out = (float2*)d_out.p; p.njobs = (int)(e - k);
-                const cudaError_t ce = launch_jobs(p, L, st);
-                if (ce != cudaSuccess) return cuda_fail(ce, "activity extract launch");
-                k = e;
-            }
-            cudaError_t ce = cudaMemcpyAsync(h_out.p, d_out.p, sizeof(float2) * (size_t)total, cudaMemcpyDeviceToHost, st);
-            if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
-            if (ce != cudaSuccess) return cuda_fail(ce, "activity extract D2H");
-        }
-        const cfloat* res = (const cfloat*)h_out.p;
         for (size_t i = 0; i < ops.size(); i++) {
             const ActOp& o = ops[i];
             if (o.kind == ActOp::PUSH) {
@@ -136,16 +181,116 @@ struct ActEngine {
                 Pending& q = pending[o.uid];
                 const size_t ntake = o.ntake < 0 ? q.nblocks : std::min((size_t)o.ntake, q.nblocks);
                 OutMsg m; m.meta = *o.meta;
-                q.take(ntake, (size_t)o.blocksamples, &m.data);
+                m.n = ntake * (size_t)o.blocksamples;
+                const bool wanted = m.meta.publish || !m.meta.filename.empty();
+                cfloat* dstp = (wanted && m.n) ? arena.alloc(m.n) : 0;
+                m.ptr = dstp;
+                q.take(ntake, (size_t)o.blocksamples, dstp);
                 if (!m.meta.filename.empty()) {
                     FILE* fh = fopen(m.meta.filename.c_str(), "wb");
                     if (!fh) std::cerr << "Cannot write to file " << m.meta.filename << std::endl;
-                    else { fwrite(m.data.data(), sizeof(cfloat), m.data.size(), fh); fclose(fh); }
+                    else { if (m.n) fwrite(m.ptr, sizeof(cfloat), m.n, fh); fclose(fh); }
                 }
                 if (!m.meta.logline.empty()) log_line(verbose, logfile, m.meta.logline);
-                if (m.meta.publish) msgs.push_back(m);
+                if (m.meta.publish) msgs.push_back(std::move(m));
             }
         }
+        for (std::map<long, Pending>::iterator it = pending.begin(); it != pending.end(); ++it) it->second.keep();
+    }
+    /* run all extraction jobs of a call and replay the ops */
+    int finish(const float2* d_rows, std::vector<ActJob>& jobs, const std::vector<ActOp>& ops, cudaStream_t st)
+    {
+        std::vector<long> dst; long total = 0;
+        if (extract(d_rows, 0, jobs, 0, jobs.size(), 0, dst, &total, st)) return -1;
+        replay((const cfloat*)h_out.p, dst, jobs, ops);
+        return 0;
+    }
+
+    /* ---- time-sharded call (one process per GPU): every rank measures its own rows, the compact detection records of
+     * all ranks are concatenated and EVERY rank runs the same sequential bookkeeping over them (`decide`), each rank extracts the
+     * jobs emitted by its own blocks (a contiguous range of the job list), and the sink rank replays the ops on the concatenated
+     * results (`assemble`). */
+    struct ShardCall {
+        std::vector<char> blob; std::vector<ActJob> jobs; std::vector<ActOp> ops; std::vector<long> job_first; bool decided;
+        ShardCall() : decided(false) {}
+    } sh;
+    template <class T> void blob_put(const T& v) { const char* c = (const char*)&v; sh.blob.insert(sh.blob.end(), c, c + sizeof(T)); }
+    void blob_put_edges(const EdgeBlock& e)
+    {
+        blob_put((int)e.rise.size()); blob_put((int)e.fall.size());
+        for (size_t k = 0; k < e.rise.size(); k++) { blob_put(e.rise[k].first); blob_put(e.rise[k].second); }
+        for (size_t k = 0; k < e.fall.size(); k++) blob_put(e.fall[k]);
+    }
+    static bool blob_get_edges(const char*& cur, const char* end, EdgeBlock& e)
+    {
+        int n[2];
+        if (end - cur < (long)sizeof(n)) return false;
+        memcpy(n, cur, sizeof(n)); cur += sizeof(n);
+        if (n[0] < 0 || n[1] < 0 || end - cur < (long)n[0] * 8 + (long)n[1] * 4) return false;
+        e.rise.resize((size_t)n[0]); e.fall.resize((size_t)n[1]);
+        for (int k = 0; k < n[0]; k++) { memcpy(&e.rise[(size_t)k].first, cur, 4); memcpy(&e.rise[(size_t)k].second, cur + 4, 4); cur += 8; }
+        if (n[1]) memcpy(e.fall.data(), cur, (size_t)n[1] * 4);
+        cur += (size_t)n[1] * 4;
+        return true;
+    }
+    void shard_begin(int nblocks_total)
+    {
+        sh.jobs.clear(); sh.ops.clear(); sh.job_first.assign(1, 0); sh.decided = false;
+        sh.jobs.reserve((size_t)nblocks_total * 16 + 16); sh.ops.reserve((size_t)nblocks_total * 18 + 16);
+    }
+    bool shard_rows_ok(int first_row, int nrows) const
+    { return sh.decided && first_row >= 0 && nrows >= 0 && (size_t)first_row + (size_t)nrows + 1 <= sh.job_first.size(); }
+    long shard_samples(int first_row, int nrows) const
+    {
+        if (!shard_rows_ok(first_row, nrows)) return fail("shard call: rows out of range or no decided call");
+        long t = 0;
+        for (long j = sh.job_first[(size_t)first_row]; j < sh.job_first[(size_t)(first_row + nrows)]; j++) t += sh.jobs[(size_t)j].L - sh.jobs[(size_t)j].skip;
+        return t;
+    }
+    long shard_extract(int first_row, int nrows, const void* d_rows, const void* d_prev, void* stream, void* out_host)
+    {
+        if (!shard_rows_ok(first_row, nrows)) return fail("shard call: rows out of range or no decided call");
+        OnDevice on_dev(dev);
+        cudaStream_t st = stream ? (cudaStream_t)stream : s;
+        std::vector<long> dst; long total = 0;
+        if (extract((const float2*)d_rows, (const float2*)d_prev, sh.jobs, (size_t)sh.job_first[(size_t)first_row],
+                    (size_t)sh.job_first[(size_t)(first_row + nrows)], first_row, dst, &total, st)) return -1;
+        if (!logic_only && total > 0 && out_host) memcpy(out_host, h_out.p, sizeof(float2) * (size_t)total);
+        return total;
+    }
+    long shard_extract_device(int first_row, int nrows, const void* d_rows, const void* d_prev, void* stream, void* d_dst)
+    {
+        if (!shard_rows_ok(first_row, nrows) || logic_only || !d_dst) return fail("shard call: rows out of range, no decided call or no destination");
+        OnDevice on_dev(dev);
+        std::vector<long> dst; long total = 0;
+        if (extract((const float2*)d_rows, (const float2*)d_prev, sh.jobs, (size_t)sh.job_first[(size_t)first_row],
+                    (size_t)sh.job_first[(size_t)(first_row + nrows)], first_row, dst, &total, stream ? (cudaStream_t)stream : s, (float2*)d_dst)) return -1;
+        return total;
+    }
+    int shard_assemble_device(const void* d_results, long nsamples, void* stream)
+    {
+        if (!sh.decided || logic_only) return fail("shard call: nothing decided");
+        OnDevice on_dev(dev);
+        cudaStream_t st = stream ? (cudaStream_t)stream : s;
+        if (nsamples > 0) {
+            if (!h_out.reserve(sizeof(float2) * (size_t)nsamples)) return cuda_fail(cudaGetLastError(), "assemble buffer");
+            cudaError_t ce = cudaMemcpyAsync(h_out.p, d_results, sizeof(float2) * (size_t)nsamples, cudaMemcpyDeviceToHost, st);
+            if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+            if (ce != cudaSuccess) return cuda_fail(ce, "assemble D2H");
+        }
+        static const float2 none = {0.0f, 0.0f};           /* a null result pointer means "drop the call" to shard_assemble */
+        return shard_assemble(h_out.p ? h_out.p : (const void*)&none, nsamples);
+    }
+    int shard_assemble(const void* results, long nsamples)
+    {
+        if (!sh.decided) return fail("shard call: nothing decided");
+        if (results || logic_only) {
+            std::vector<long> dst(sh.jobs.size(), 0); long total = 0;
+            for (size_t i = 0; i < sh.jobs.size(); i++) { dst[i] = total; total += sh.jobs[i].L - sh.jobs[i].skip; }
+            if (!logic_only && total != nsamples) return fail("shard assemble: result size does not match the job list");
+            replay((const cfloat*)results, dst, sh.jobs, sh.ops);
+        }
+        sh.jobs.clear(); sh.ops.clear(); sh.decided = false;
         return 0;
     }
     int save_hist(const float2* d_rows, int n, cudaStream_t st)
@@ -161,6 +306,23 @@ struct ActEngine {
         if (e != cudaSuccess) { cuda_fail(e, "H2D"); return 0; }
         return (const float2*)d_in.p;
     }
+    int msg_get_all(fdc_msg* out) const
+    {
+        for (size_t i = 0; i < msgs.size(); i++)
+            if (msg_get((int)i, out + i)) return -1;
+        return (int)msgs.size();
+    }
+    long msg_copy_data(float* out) const
+    {
+        long total = 0;
+        for (size_t i = 0; i < msgs.size(); i++) {
+            const OutMsg& m = msgs[i];
+            if (m.logic_samples >= 0 || m.n == 0) continue;
+            if (out) memcpy(out + 2 * total, m.ptr, sizeof(cfloat) * m.n);
+            total += (long)m.n;
+        }
+        return total;
+    }
     int msg_get(int i, fdc_msg* out) const
     {
         if (i < 0 || i >= (int)msgs.size() || !out) return fail("message index out of range");
@@ -169,8 +331,8 @@ struct ActEngine {
         strncpy(out->id, m.meta.id.c_str(), sizeof(out->id) - 1);
         out->finalized = m.meta.finalized ? 1 : 0; out->part = m.meta.part; out->rel_cfreq = m.meta.rel_cfreq; out->rel_bw = m.meta.rel_bw;
         out->blockstart = m.meta.blockstart; out->blockend = m.meta.blockend; out->vectorstart = m.meta.vectorstart; out->vectorend = m.meta.vectorend;
-        out->nsamples = m.logic_samples >= 0 ? m.logic_samples : (long)m.data.size();
-        out->data = m.logic_samples >= 0 ? (const float*)0 : (const float*)m.data.data();
+        out->nsamples = m.logic_samples >= 0 ? m.logic_samples : (long)m.n;
+        out->data = m.logic_samples >= 0 ? (const float*)0 : (const float*)m.ptr;
         return 0;
     }
 };
@@ -275,6 +437,7 @@ int fdc_pac_logic_work(fdc_pac* b, int n, const float* pwr)
 }
 int fdc_pac_work_device(fdc_pac* b, int n, const void* d_in, void* stream)
 {
+    OnDevice on_dev(b ? b->e.dev : -1);
     if (!b || n < 0 || b->e.logic_only) return fail("PowerActivationChannel work: bad arguments");
     if (n == 0) return 0;
     cudaStream_t st = stream ? (cudaStream_t)stream : b->e.s;
@@ -294,6 +457,7 @@ int fdc_pac_work_device(fdc_pac* b, int n, const void* d_in, void* stream)
 }
 int fdc_pac_work_host(fdc_pac* b, int n, const void* in)
 {
+    OnDevice on_dev(b ? b->e.dev : -1);
     if (!b || n < 0 || b->e.logic_only) return fail("PowerActivationChannel work: bad arguments");
     if (n == 0) return 0;
     const float2* rows = b->e.stage_host(in, n);
@@ -315,7 +479,7 @@ int fdc_pac_tables(const fdc_pac* b, float* out)
 }
 int fdc_pac_msg_count(const fdc_pac* b) { return b ? (int)b->e.msgs.size() : -1; }
 int fdc_pac_msg_get(const fdc_pac* b, int i, fdc_msg* out) { return b ? b->e.msg_get(i, out) : fail("null block"); }
-void fdc_pac_msg_clear(fdc_pac* b) { if (b) b->e.msgs.clear(); }
+void fdc_pac_msg_clear(fdc_pac* b) { if (b) b->e.msg_clear(); }
 void fdc_pac_destroy(fdc_pac* b) { delete b; }
 
 }  // extern "C"
@@ -393,6 +557,7 @@ int fdc_segdet_logic_work(fdc_segdet* b, int n, const float* P)
 }
 int fdc_segdet_work_device(fdc_segdet* b, int n, const void* d_in, void* stream)
 {
+    OnDevice on_dev(b ? b->e.dev : -1);
     if (!b || n < 0 || b->e.logic_only) return fail("SegmentDetection work: bad arguments");
     if (n == 0) return 0;
     cudaStream_t st = stream ? (cudaStream_t)stream : b->e.s;
@@ -408,6 +573,7 @@ int fdc_segdet_work_device(fdc_segdet* b, int n, const void* d_in, void* stream)
 }
 int fdc_segdet_work_host(fdc_segdet* b, int n, const void* in)
 {
+    OnDevice on_dev(b ? b->e.dev : -1);
     if (!b || n < 0 || b->e.logic_only) return fail("SegmentDetection work: bad arguments");
     if (n == 0) return 0;
     const float2* rows = b->e.stage_host(in, n);
@@ -442,7 +608,7 @@ int fdc_segdet_active(const fdc_segdet* b, int i, int* out)
 }
 int fdc_segdet_msg_count(const fdc_segdet* b) { return b ? (int)b->e.msgs.size() : -1; }
 int fdc_segdet_msg_get(const fdc_segdet* b, int i, fdc_msg* out) { return b ? b->e.msg_get(i, out) : fail("null block"); }
-void fdc_segdet_msg_clear(fdc_segdet* b) { if (b) b->e.msgs.clear(); }
+void fdc_segdet_msg_clear(fdc_segdet* b) { if (b) b->e.msg_clear(); }
 void fdc_segdet_destroy(fdc_segdet* b) { delete b; }
 
 }  // extern "C"
@@ -526,6 +692,7 @@ int fdc_actdet_logic_work(fdc_actdet* b, int n, const float* P)
 }
 int fdc_actdet_work_device(fdc_actdet* b, int n, const void* d_in, void* stream)
 {
+    OnDevice on_dev(b ? b->e.dev : -1);
     if (!b || n < 0 || b->e.logic_only) return fail("activity_detection_channelizer_vcm work: bad arguments");
     if (n == 0) return 0;
     cudaStream_t st = stream ? (cudaStream_t)stream : b->e.s;
@@ -547,6 +714,7 @@ int fdc_actdet_work_device(fdc_actdet* b, int n, const void* d_in, void* stream)
 }
 int fdc_actdet_work_host(fdc_actdet* b, int n, const void* in)
 {
+    OnDevice on_dev(b ? b->e.dev : -1);
     if (!b || n < 0 || b->e.logic_only) return fail("activity_detection_channelizer_vcm work: bad arguments");
     if (n == 0) return 0;
     const float2* rows = b->e.stage_host(in, n);
@@ -568,7 +736,163 @@ int fdc_actdet_power(const fdc_actdet* b, int seg, float* out)
 }
 int fdc_actdet_msg_count(const fdc_actdet* b) { return b ? (int)b->e.msgs.size() : -1; }
 int fdc_actdet_msg_get(const fdc_actdet* b, int i, fdc_msg* out) { return b ? b->e.msg_get(i, out) : fail("null block"); }
-void fdc_actdet_msg_clear(fdc_actdet* b) { if (b) b->e.msgs.clear(); }
+void fdc_actdet_msg_clear(fdc_actdet* b) { if (b) b->e.msg_clear(); }
 void fdc_actdet_destroy(fdc_actdet* b) { delete b; }
+
+}  // extern "C"
+
+/* ================================================================================================ time-sharded calls
+ * the blocks' state crosses shard boundaries, the measurements do not.  Per global call over `nblocks_total` blocks:
+ *   rank r:   *_shard_measure(own rows)            -> compact record (band powers / edge lists), a few bytes per block
+ *   all:      all-gather of the records (host side plumbing, FDC/sharded.py), concatenated in block order
+ *   all:      *_shard_decide(all records)          -> the same job + op lists on every rank (sequential bookkeeping, replicated)
+ *   rank r:   *_shard_extract(own rows)            -> samples of the jobs its blocks emitted, in job order
+ *   sink:     *_shard_assemble(concatenated)       -> PDUs; other ranks pass NULL and only drop the call */
+extern "C" {
+
+long fdc_pac_shard_measure(fdc_pac* b, int n, const void* d_rows, void* stream)
+{
+    OnDevice on_dev(b ? b->e.dev : -1);
+    if (!b || n < 0 || b->e.logic_only) return fail("PowerActivationChannel shard_measure: bad arguments");
+    b->e.sh.blob.clear();
+    if (n == 0) return 0;
+    cudaStream_t st = stream ? (cudaStream_t)stream : b->e.s;
+    if (!b->e.d_pw.reserve(sizeof(float) * (size_t)n) || !b->e.h_misc.reserve(sizeof(float) * (size_t)n)) return cuda_fail(cudaGetLastError(), "power buffers");
+    cudaError_t ce = launch_band_power((const float2*)d_rows, b->e.N, n, b->st.measure_start, b->st.measure_stop, (float*)b->e.d_pw.p, st);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(b->e.h_misc.p, b->e.d_pw.p, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    if (ce != cudaSuccess) return cuda_fail(ce, "band power");
+    b->e.sh.blob.assign((const char*)b->e.h_misc.p, (const char*)b->e.h_misc.p + sizeof(float) * (size_t)n);
+    return (long)b->e.sh.blob.size();
+}
+long fdc_pac_shard_measure_logic(fdc_pac* b, int n, const float* pwr)
+{
+    if (!b || n < 0 || !b->e.logic_only) return fail("fdc_pac_shard_measure_logic: needs a context from fdc_pac_create_logic");
+    b->e.sh.blob.assign((const char*)pwr, (const char*)pwr + sizeof(float) * (size_t)n);
+    return (long)b->e.sh.blob.size();
+}
+long fdc_pac_shard_decide(fdc_pac* b, int n, const void* blob, long bytes)
+{
+    if (!b || n < 0 || bytes != (long)sizeof(float) * n) return fail("PowerActivationChannel shard_decide: record size does not match the block count");
+    b->e.shard_begin(n);
+    for (int i = 0; i < n; i++) {
+        float pw; memcpy(&pw, (const char*)blob + sizeof(float) * (size_t)i, sizeof(float));
+        b->st.block(i, pw, b->e.uid_counter, b->e.sh.jobs, b->e.sh.ops);
+        b->e.sh.job_first.push_back((long)b->e.sh.jobs.size());
+    }
+    b->e.sh.decided = true;
+    return (long)b->e.sh.jobs.size();
+}
+
+long fdc_segdet_shard_measure(fdc_segdet* b, int n, const void* d_rows, void* stream)
+{
+    OnDevice on_dev(b ? b->e.dev : -1);
+    if (!b || n < 0 || b->e.logic_only) return fail("SegmentDetection shard_measure: bad arguments");
+    b->e.sh.blob.clear();
+    if (n == 0) return 0;
+    std::vector<EdgeBlock> edges;
+    if (b->det.run(b->e, (const float2*)d_rows, n, b->st.g, b->thresh, 0, 0, edges, stream ? (cudaStream_t)stream : b->e.s)) return -1;
+    for (int i = 0; i < n; i++) b->e.blob_put_edges(edges[(size_t)i]);
+    return (long)b->e.sh.blob.size();
+}
+long fdc_segdet_shard_measure_logic(fdc_segdet* b, int n, const float* P)
+{
+    if (!b || n < 0 || !b->e.logic_only) return fail("fdc_segdet_shard_measure_logic: needs a context from fdc_segdet_create_logic");
+    std::vector<EdgeBlock> edges;
+    classify_rows(P, n, (int)b->st.g.M, b->thresh, 0, edges);
+    b->e.sh.blob.clear();
+    for (int i = 0; i < n; i++) b->e.blob_put_edges(edges[(size_t)i]);
+    return (long)b->e.sh.blob.size();
+}
+long fdc_segdet_shard_decide(fdc_segdet* b, int n, const void* blob, long bytes)
+{
+    if (!b || n < 0 || bytes < 0) return fail("SegmentDetection shard_decide: bad arguments");
+    const char* cur = (const char*)blob; const char* end = cur + bytes;
+    b->e.shard_begin(n);
+    EdgeBlock eb;
+    for (int i = 0; i < n; i++) {
+        if (!ActEngine::blob_get_edges(cur, end, eb)) return fail("SegmentDetection shard_decide: truncated detection record");
+        b->st.block(i, eb, b->blockcount, b->e.uid_counter, b->e.sh.jobs, b->e.sh.ops); b->blockcount++;
+        b->e.sh.job_first.push_back((long)b->e.sh.jobs.size());
+    }
+    if (cur != end) return fail("SegmentDetection shard_decide: detection record longer than the block count");
+    b->e.sh.decided = true;
+    return (long)b->e.sh.jobs.size();
+}
+
+long fdc_actdet_shard_measure(fdc_actdet* b, int n, const void* d_rows, void* stream)
+{
+    OnDevice on_dev(b ? b->e.dev : -1);
+    if (!b || n < 0 || b->e.logic_only) return fail("activity_detection_channelizer_vcm shard_measure: bad arguments");
+    b->e.sh.blob.clear();
+    if (n == 0) return 0;
+    std::vector<std::vector<EdgeBlock> > edges(b->segs.size());
+    for (size_t s = 0; s < b->segs.size(); s++)
+        if (b->det[s].run(b->e, (const float2*)d_rows, n, b->segs[s].g, b->thresh, 1, 1, edges[s], stream ? (cudaStream_t)stream : b->e.s)) return -1;
+    for (int i = 0; i < n; i++)
+        for (size_t s = 0; s < b->segs.size(); s++) b->e.blob_put_edges(edges[s][(size_t)i]);
+    return (long)b->e.sh.blob.size();
+}
+long fdc_actdet_shard_measure_logic(fdc_actdet* b, int n, const float* P)
+{
+    if (!b || n < 0 || !b->e.logic_only) return fail("fdc_actdet_shard_measure_logic: needs a context from fdc_actdet_create_logic");
+    long rowlen = 0;
+    for (size_t s = 0; s < b->segs.size(); s++) rowlen += b->segs[s].g.M;
+    std::vector<EdgeBlock> eb;
+    b->e.sh.blob.clear();
+    for (int i = 0; i < n; i++) {
+        long off = 0;
+        for (size_t s = 0; s < b->segs.size(); s++) {
+            classify_rows(P + (size_t)i * rowlen + off, 1, (int)b->segs[s].g.M, b->thresh, 1, eb);
+            b->e.blob_put_edges(eb[0]);
+            off += b->segs[s].g.M;
+        }
+    }
+    return (long)b->e.sh.blob.size();
+}
+long fdc_actdet_shard_decide(fdc_actdet* b, int n, const void* blob, long bytes)
+{
+    if (!b || n < 0 || bytes < 0) return fail("activity_detection_channelizer_vcm shard_decide: bad arguments");
+    const char* cur = (const char*)blob; const char* end = cur + bytes;
+    b->e.shard_begin(n);
+    EdgeBlock eb;
+    for (int i = 0; i < n; i++) {
+        for (size_t s = 0; s < b->segs.size(); s++) {
+            if (!ActEngine::blob_get_edges(cur, end, eb)) return fail("activity_detection_channelizer_vcm shard_decide: truncated detection record");
+            b->segs[s].block(i, eb, b->blockcount, b->e.uid_counter, b->e.sh.jobs, b->e.sh.ops);
+        }
+        b->blockcount++;
+        b->e.sh.job_first.push_back((long)b->e.sh.jobs.size());
+    }
+    if (cur != end) return fail("activity_detection_channelizer_vcm shard_decide: detection record longer than the block count");
+    b->e.sh.decided = true;
+    return (long)b->e.sh.jobs.size();
+}
+
+#define FDC_SHARD_COMMON(X)                                                                                                        \
+    int fdc_##X##_shard_blob(const fdc_##X* b, void* out)                                                                          \
+    {                                                                                                                              \
+        if (!b || !out) return fail("null argument");                                                                              \
+        if (!b->e.sh.blob.empty()) memcpy(out, b->e.sh.blob.data(), b->e.sh.blob.size());                                          \
+        return 0;                                                                                                                  \
+    }                                                                                                                              \
+    long fdc_##X##_shard_samples(const fdc_##X* b, int first_row, int nrows)                                                      \
+    { return b ? b->e.shard_samples(first_row, nrows) : fail("null block"); }                                                     \
+    long fdc_##X##_shard_extract(fdc_##X* b, int first_row, int nrows, const void* d_rows, const void* d_prev, void* stream, void* out_host) \
+    { return b ? b->e.shard_extract(first_row, nrows, d_rows, d_prev, stream, out_host) : fail("null block"); }                   \
+    int fdc_##X##_shard_assemble(fdc_##X* b, const void* results, long nsamples)                                                  \
+    { return b ? b->e.shard_assemble(results, nsamples) : fail("null block"); }                                                   \
+    long fdc_##X##_shard_extract_device(fdc_##X* b, int first_row, int nrows, const void* d_rows, const void* d_prev, void* stream, void* d_dst) \
+    { return b ? b->e.shard_extract_device(first_row, nrows, d_rows, d_prev, stream, d_dst) : fail("null block"); }               \
+    int fdc_##X##_shard_assemble_device(fdc_##X* b, const void* d_results, long nsamples, void* stream)                           \
+    { return b ? b->e.shard_assemble_device(d_results, nsamples, stream) : fail("null block"); }                                  \
+    int fdc_##X##_msg_get_all(const fdc_##X* b, fdc_msg* out)                                                                      \
+    { return (b && out) ? b->e.msg_get_all(out) : fail("null argument"); }                                                        \
+    long fdc_##X##_msg_copy_data(const fdc_##X* b, float* out)                                                                     \
+    { return b ? b->e.msg_copy_data(out) : fail("null block"); }
+FDC_SHARD_COMMON(pac)
+FDC_SHARD_COMMON(segdet)
+FDC_SHARD_COMMON(actdet)
+#undef FDC_SHARD_COMMON
 
 }  // extern "C"

@@ -17,6 +17,22 @@ int fail(const std::string& s);                       /* records the text, retur
 int cuda_fail(cudaError_t e, const char* what);       /* same with the CUDA error string */
 bool require_device();                                /* false (+ error text) when no CUDA device is usable */
 
+/* A context lives on the device that was current when it was made.  CUDA's current device is a per-thread setting and GNU
+ * Radio calls a block's work() from a scheduler thread, not from the thread that constructed the block: every entry point
+ * that touches the device switches to the context's device for the duration of the call. */
+struct OnDevice {
+    int prev;
+    explicit OnDevice(int dev) : prev(-1)
+    {
+        int cur = -1;
+        if (dev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != dev && cudaSetDevice(dev) == cudaSuccess) prev = cur;
+    }
+    ~OnDevice() { if (prev >= 0) cudaSetDevice(prev); }
+private:
+    OnDevice(const OnDevice&); OnDevice& operator=(const OnDevice&);
+};
+struct DevCtx { int dev; DevCtx() : dev(-1) { if (cudaGetDevice(&dev) != cudaSuccess) { dev = -1; cudaGetLastError(); } } };
+
 /* grow-only device buffer */
 struct DevBuf {
     void* p; size_t cap;

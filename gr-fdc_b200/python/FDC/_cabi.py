@@ -84,6 +84,8 @@ SIGNATURES = {
     "fdc_pac_tables": (_i, [_vp, _vp]),
     "fdc_pac_msg_count": (_i, [_vp]),
     "fdc_pac_msg_get": (_i, [_vp, _i, _vp]),
+    "fdc_pac_msg_get_all": (_i, [_vp, _vp]),
+    "fdc_pac_msg_copy_data": (_l, [_vp, _vp]),
     "fdc_pac_msg_clear": (None, [_vp]),
     "fdc_pac_destroy": (None, [_vp]),
     "fdc_segdet_create": (_vp, [_i, _i, _i, _f, _f, _f, _f, _f, _i, _i, _i, _i, _cp, _i, _i]),
@@ -95,6 +97,8 @@ SIGNATURES = {
     "fdc_segdet_active": (_i, [_vp, _i, _vp]),
     "fdc_segdet_msg_count": (_i, [_vp]),
     "fdc_segdet_msg_get": (_i, [_vp, _i, _vp]),
+    "fdc_segdet_msg_get_all": (_i, [_vp, _vp]),
+    "fdc_segdet_msg_copy_data": (_l, [_vp, _vp]),
     "fdc_segdet_msg_clear": (None, [_vp]),
     "fdc_segdet_destroy": (None, [_vp]),
     "fdc_actdet_create": (_vp, [_i, _vp, _i, _f, _i, _i, _i, _i, _cp, _i, _f, _i, _d, _i]),
@@ -105,6 +109,8 @@ SIGNATURES = {
     "fdc_actdet_power": (_i, [_vp, _i, _vp]),
     "fdc_actdet_msg_count": (_i, [_vp]),
     "fdc_actdet_msg_get": (_i, [_vp, _i, _vp]),
+    "fdc_actdet_msg_get_all": (_i, [_vp, _vp]),
+    "fdc_actdet_msg_copy_data": (_l, [_vp, _vp]),
     "fdc_actdet_msg_clear": (None, [_vp]),
     "fdc_actdet_destroy": (None, [_vp]),
     "fdc_pac_create_logic": (_vp, [_i, _f, _f, _i, _f, _i, _i, _i, _i, _cp, _i, _i]),
@@ -113,6 +119,33 @@ SIGNATURES = {
     "fdc_segdet_logic_work": (_i, [_vp, _i, _vp]),
     "fdc_actdet_create_logic": (_vp, [_i, _vp, _i, _f, _i, _i, _i, _i, _cp, _i, _f, _i, _d, _i]),
     "fdc_actdet_logic_work": (_i, [_vp, _i, _vp]),
+    "fdc_pac_shard_measure": (_l, [_vp, _i, _vp, _vp]),
+    "fdc_pac_shard_measure_logic": (_l, [_vp, _i, _vp]),
+    "fdc_pac_shard_blob": (_i, [_vp, _vp]),
+    "fdc_pac_shard_decide": (_l, [_vp, _i, _vp, _l]),
+    "fdc_pac_shard_samples": (_l, [_vp, _i, _i]),
+    "fdc_pac_shard_extract": (_l, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "fdc_pac_shard_assemble": (_i, [_vp, _vp, _l]),
+    "fdc_pac_shard_extract_device": (_l, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "fdc_pac_shard_assemble_device": (_i, [_vp, _vp, _l, _vp]),
+    "fdc_segdet_shard_measure": (_l, [_vp, _i, _vp, _vp]),
+    "fdc_segdet_shard_measure_logic": (_l, [_vp, _i, _vp]),
+    "fdc_segdet_shard_blob": (_i, [_vp, _vp]),
+    "fdc_segdet_shard_decide": (_l, [_vp, _i, _vp, _l]),
+    "fdc_segdet_shard_samples": (_l, [_vp, _i, _i]),
+    "fdc_segdet_shard_extract": (_l, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "fdc_segdet_shard_assemble": (_i, [_vp, _vp, _l]),
+    "fdc_segdet_shard_extract_device": (_l, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "fdc_segdet_shard_assemble_device": (_i, [_vp, _vp, _l, _vp]),
+    "fdc_actdet_shard_measure": (_l, [_vp, _i, _vp, _vp]),
+    "fdc_actdet_shard_measure_logic": (_l, [_vp, _i, _vp]),
+    "fdc_actdet_shard_blob": (_i, [_vp, _vp]),
+    "fdc_actdet_shard_decide": (_l, [_vp, _i, _vp, _l]),
+    "fdc_actdet_shard_samples": (_l, [_vp, _i, _i]),
+    "fdc_actdet_shard_extract": (_l, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "fdc_actdet_shard_assemble": (_i, [_vp, _vp, _l]),
+    "fdc_actdet_shard_extract_device": (_l, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "fdc_actdet_shard_assemble_device": (_i, [_vp, _vp, _l, _vp]),
 }
 
 

@@ -60,28 +60,90 @@ class _MsgBlock(_SyncBlock):
         self._dispatch()
         return nblocks
 
+    # ---- time-sharded calls (fdc_*_shard_*, one process per GPU; orchestration in FDC/sharded.py: ShardedActivity) ----
+    def shard_measure(self, nrows, d_rows=0, stream=0, power=None):
+        """Step 1: compact detection record (bytes) of this rank's rows.  d_rows: device pointer to the spectrum rows;
+        host-logic contexts pass `power` (as for logic_work) instead."""
+        if power is not None:
+            p = np.ascontiguousarray(power, dtype=np.float32)
+            n = check(self._fn("shard_measure_logic")(self._h, int(nrows), _ptr(p)), self._name)
+        else:
+            n = check(self._fn("shard_measure")(self._h, int(nrows), C.c_void_p(d_rows), C.c_void_p(stream) if stream else None), self._name)
+        buf = C.create_string_buffer(max(int(n), 1))
+        check(self._fn("shard_blob")(self._h, buf), self._name)
+        return bytes(buf.raw[:int(n)])
+
+    def shard_decide(self, nblocks_total, records):
+        """Step 3: the sequential bookkeeping over the records of ALL ranks (concatenated in row order); returns the job count."""
+        return int(check(self._fn("shard_decide")(self._h, int(nblocks_total), C.c_char_p(records), len(records)), self._name))
+
+    def shard_samples(self, first_row, nrows):
+        return int(check(self._fn("shard_samples")(self._h, int(first_row), int(nrows)), self._name))
+
+    def shard_extract(self, first_row, nrows, d_rows=0, d_prev=0, stream=0):
+        """Step 4: samples of the jobs this rank's rows emitted, in job order (complex64)."""
+        out = np.empty(self.shard_samples(first_row, nrows), dtype=np.complex64)
+        n = check(self._fn("shard_extract")(self._h, int(first_row), int(nrows), C.c_void_p(d_rows) if d_rows else None,
+                                            C.c_void_p(d_prev) if d_prev else None, C.c_void_p(stream) if stream else None,
+                                            _ptr(out) if out.size else None), self._name)
+        assert int(n) == out.size
+        return out
+
+    def shard_extract_device(self, first_row, nrows, d_rows, d_prev, d_dst, stream=0):
+        """Step 4, device form: the samples go to the device buffer d_dst (possibly the sink rank's, mapped over CUDA IPC)."""
+        return int(check(self._fn("shard_extract_device")(self._h, int(first_row), int(nrows), C.c_void_p(d_rows), C.c_void_p(d_prev) if d_prev else None,
+                                                          C.c_void_p(stream) if stream else None, C.c_void_p(d_dst)), self._name))
+
+    def shard_assemble_device(self, d_results, nsamples, stream=0):
+        """Step 5 on the sink, device form: d_results holds every rank's samples of this block in rank order."""
+        check(self._fn("shard_assemble_device")(self._h, C.c_void_p(d_results), int(nsamples), C.c_void_p(stream) if stream else None), self._name)
+        self._dispatch()
+
+    def shard_assemble(self, results=None):
+        """Step 5: the sink passes every rank's samples concatenated in rank order; the other ranks pass None."""
+        if results is None:
+            check(self._fn("shard_assemble")(self._h, None, 0), self._name)
+            return
+        r = np.ascontiguousarray(results, dtype=np.complex64)
+        dummy = np.zeros(1, dtype=np.complex64)
+        check(self._fn("shard_assemble")(self._h, _ptr(r if r.size else dummy), int(r.size)), self._name)
+        self._dispatch()
+
     def _dispatch(self):
         if self._handler is not None:
             for m in self.messages():
                 self._handler(m)
 
     def messages(self, clear=True):
+        """Pending PDUs as dicts.  Two calls for the whole batch (records, then all payloads into one buffer the dicts' `data`
+        arrays are slices of) instead of two per message: a work() call on a busy band publishes hundreds of PDUs."""
         n = self._fn("msg_count")(self._h)
-        res = []
-        for k in range(n):
-            m = _cabi.msg()
-            check(self._fn("msg_get")(self._h, k, C.byref(m)))
-            have = bool(m.data) and m.nsamples > 0         # host-logic contexts report counts only (data == NULL)
-            data = np.empty(m.nsamples if have else 0, dtype=np.complex64)
-            if have:
-                C.memmove(data.ctypes.data, m.data, 8 * m.nsamples)
-            d = dict(ID=m.id.decode(), finalized=bool(m.finalized), part=int(m.part), rel_bw=m.rel_bw, rel_cfreq=m.rel_cfreq,
-                     blockstart=int(m.blockstart), blockend=int(m.blockend), vectorstart=int(m.vectorstart),
-                     vectorend=int(m.vectorend), nsamples=int(m.nsamples), data=data)
-            res.append(d)
+        if n <= 0:
+            return []
+        recs = (_cabi.msg * n)()
+        check(self._fn("msg_get_all")(self._h, recs), self._name)
+        r = np.frombuffer(recs, dtype=_MSG_DTYPE)
+        have = (r["data"] != 0) & (r["nsamples"] > 0)               # host-logic contexts report counts only (data == NULL)
+        sizes = np.where(have, r["nsamples"], 0)
+        buf = np.empty(int(sizes.sum()), dtype=np.complex64)
+        if buf.size:
+            check(self._fn("msg_copy_data")(self._h, _ptr(buf)), self._name)
+        cut = np.concatenate([[0], np.cumsum(sizes)]).tolist()
+        ids = [bytes(x).split(b"\0", 1)[0].decode() for x in r["id"].tolist()]
+        cols = [r[k].tolist() for k in ("finalized", "part", "rel_bw", "rel_cfreq", "blockstart", "blockend", "vectorstart", "vectorend", "nsamples")]
+        res = [dict(ID=ids[k], finalized=bool(fin), part=part, rel_bw=bw, rel_cfreq=cf, blockstart=b0, blockend=b1, vectorstart=v0, vectorend=v1,
+                    nsamples=ns, data=buf[cut[k]:cut[k + 1]])
+               for k, (fin, part, bw, cf, b0, b1, v0, v1, ns) in enumerate(zip(*cols))]
         if clear:
             self._fn("msg_clear")(self._h)
         return res
+
+
+_MSG_DTYPE = np.dtype({"names": ["id", "finalized", "part", "rel_cfreq", "rel_bw", "blockstart", "blockend", "vectorstart", "vectorend", "nsamples", "data"],
+                       "formats": ["V160", "i4", "i8", "f8", "f8", "i8", "i8", "i8", "i8", "i8", "u8"],
+                       "offsets": [getattr(_cabi.msg, k).offset for k in ("id", "finalized", "part", "rel_cfreq", "rel_bw", "blockstart", "blockend",
+                                                                             "vectorstart", "vectorend", "nsamples", "data")],
+                       "itemsize": C.sizeof(_cabi.msg)})
 
 
 class PowerActivationChannel(_MsgBlock):

@@ -94,13 +94,14 @@ class PeerSink(object):
     no collective runs afterwards.  Layout: channel-major slabs of world * blocks_per_rank rows; rank r owns rows
     [r * blocks_per_rank, (r + 1) * blocks_per_rank) of every slab (Channelizer.work_device_slab)."""
 
-    def __init__(self, out_per_block, blocks_per_rank, rank, world, dst=0, group=None):
+    def __init__(self, out_per_block, blocks_per_rank, rank, world, dst=0, group=None, nbytes=None):
+        """nbytes: a plain buffer of that size instead of the channel-major slab layout (ShardedActivityGroup)."""
         import ctypes as C
         import torch.distributed as dist
         from ._cabi import lib, check, handle
         self.rank, self.world, self.dst, self.blocks_per_rank = rank, world, dst, int(blocks_per_rank)
         self.slab_blocks = world * self.blocks_per_rank
-        self.nbytes = 8 * self.slab_blocks * int(out_per_block)
+        self.nbytes = int(nbytes) if nbytes is not None else 8 * self.slab_blocks * int(out_per_block)
         self._local = None
         box = [None]
         if rank == dst:
@@ -127,3 +128,145 @@ class PeerSink(object):
         if self._local:
             lib().fdc_dev_free(self._local)
         self.ptr = self._local = None
+
+
+class ShardedActivity(object):
+    """An activity-gated block (PowerActivationChannel, SegmentDetection, activity_detection_channelizer_vcm) on a
+    time-sharded stream.  The reference blocks carry state from block to block (lib/PowerActivationChannel_impl.cc:137-177,
+    lib/SegmentDetection_impl.cc:163-300); their per-block measurements are stateless.  So every rank measures its own rows
+    on its GPU, the compact records (a few bytes per block) are all-gathered, EVERY rank runs the same sequential bookkeeping
+    over them and thereby knows the whole job list, each rank extracts the jobs its rows emitted, and only those samples
+    travel to the sink rank, which publishes the PDUs in the reference's order.
+
+    Every rank builds `block` with the same constructor arguments.  Rows: the fft-shifted, 1/N-scaled spectrum blocks the
+    reference block would see on its input."""
+
+    def __init__(self, block, rank, world, dst=0, group=None):
+        self.block, self.rank, self.world, self.dst, self.group = block, int(rank), int(world), int(dst), group
+
+    def work(self, nblocks_total, d_rows=0, d_prev=0, stream=0, power=None):
+        """One global call over nblocks_total blocks; this rank holds rows partition(nblocks_total, world)[rank] at d_rows
+        and the row before its first one at d_prev (0: all-zero row, start of the stream).  Host-logic contexts pass this
+        rank's `power` rows instead.  Returns the messages on the sink rank, None elsewhere."""
+        g = ShardedActivityGroup([self.block], self.rank, self.world, self.dst, self.group)
+        res = g.work(nblocks_total, d_rows, d_prev, stream, powers=None if power is None else [power])
+        return None if res is None else res[0]
+
+
+class ShardedActivityGroup(object):
+    """Several activity-gated blocks fed by the same spectrum (the hier block hangs 2 SegmentDetection and 16
+    PowerActivationChannel blocks on one FFT in configs[2]): ONE all-gather of all blocks' records and ONE gather of all
+    blocks' samples per call.  `pool` (a concurrent.futures executor) runs the per-block local phases concurrently, as
+    GNU Radio's thread-per-block scheduler would; the collectives are issued from the calling thread only."""
+
+    def __init__(self, blocks, rank, world, dst=0, group=None, pool=None, sink=None):
+        """sink: a PeerSink(nbytes=...) made by all ranks -- the extract kernels then store the burst samples straight into
+        the sink rank's buffer (peer memory over NVLink) and the gather of the samples is a barrier; calls whose samples do
+        not fit the buffer fall back to the NCCL gather."""
+        self.blocks, self.rank, self.world, self.dst, self.group = list(blocks), int(rank), int(world), int(dst), group
+        self.sink = sink
+        self._map = pool.map if pool is not None else (lambda f, it: list(map(f, it)))
+        self.phase_seconds = {}                 # wall clock per phase, accumulated over calls (for measurements)
+
+    def work(self, nblocks_total, d_rows=0, d_prev=0, stream=0, powers=None):
+        import time
+        import torch.distributed as dist
+        first, count = partition(nblocks_total, self.world)
+        me, nb = self.rank, len(self.blocks)
+        idx = range(nb)
+        t = [time.perf_counter()]
+        recs = list(self._map(lambda i: self.blocks[i].shard_measure(count[me], d_rows, stream, power=None if powers is None else powers[i]), idx))
+        t.append(time.perf_counter())
+        allrecs = _all_gather_bytes(recs, self.world, self.group)
+        t.append(time.perf_counter())
+
+        def decide(i):
+            b = self.blocks[i]
+            b.shard_decide(nblocks_total, b"".join(allrecs[r][i] for r in range(self.world)))
+            return [b.shard_samples(first[r], count[r]) for r in range(self.world)]
+        sizes = list(self._map(decide, idx))                                        # [block][rank], known everywhere: no size exchange
+        total = [sum(sz) for sz in sizes]
+        t.append(time.perf_counter())
+        out = None
+        if self.sink is not None and 8 * sum(total) <= self.sink.nbytes:
+            # block-major layout in the sink's buffer, a block's ranks in rank order: what shard_assemble wants
+            base = np.concatenate([[0], np.cumsum(total)]).tolist()
+            list(self._map(lambda i: self.blocks[i].shard_extract_device(first[me], count[me], d_rows, d_prev,
+                                                                         self.sink.ptr + 8 * (base[i] + sum(sizes[i][:me])), stream), idx))
+            t.append(time.perf_counter())
+            dist.barrier(group=self.group)                                          # every rank's stores have landed
+            t.append(time.perf_counter())
+            if me == self.dst:
+                def assemble_dev(i):
+                    self.blocks[i].shard_assemble_device(self.sink.ptr + 8 * base[i], total[i], stream)
+                    return self.blocks[i].messages()
+                out = list(self._map(assemble_dev, idx))
+            else:
+                for b in self.blocks:
+                    b.shard_assemble(None)
+        else:
+            res = list(self._map(lambda i: self.blocks[i].shard_extract(first[me], count[me], d_rows, d_prev, stream), idx))
+            t.append(time.perf_counter())
+            mine = np.concatenate(res) if nb else np.zeros(0, np.complex64)
+            parts = _gather_ragged(mine, [sum(sizes[i][r] for i in idx) for r in range(self.world)], me, self.world, self.dst, self.group)
+            t.append(time.perf_counter())
+            if me != self.dst:
+                for b in self.blocks:
+                    b.shard_assemble(None)
+            else:
+                cuts = [np.concatenate([[0], np.cumsum([sizes[i][r] for i in idx])]).tolist() for r in range(self.world)]
+
+                def assemble(i):
+                    b = self.blocks[i]
+                    b.shard_assemble(np.concatenate([parts[r][cuts[r][i]:cuts[r][i + 1]] for r in range(self.world)]))
+                    return b.messages()
+                out = list(self._map(assemble, idx))
+        t.append(time.perf_counter())
+        for k, name in enumerate(("measure", "allgather_records", "decide", "extract", "gather_samples", "assemble")):
+            self.phase_seconds[name] = self.phase_seconds.get(name, 0.0) + t[k + 1] - t[k]
+        return out
+
+
+def _all_gather_bytes(recs, world, group):
+    """All-gather of every rank's list of byte strings (the detection records): sizes first, then one padded all_gather --
+    two small collectives instead of a pickled object gather."""
+    import torch
+    import torch.distributed as dist
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    lens = torch.tensor([len(r) for r in recs], dtype=torch.int64, device=dev)
+    all_lens = [torch.empty_like(lens) for _ in range(world)]
+    dist.all_gather(all_lens, lens, group=group)
+    all_lens = [a.cpu().numpy() for a in all_lens]
+    width = max(int(max(a.sum() for a in all_lens)), 1)
+    buf = torch.zeros(width, dtype=torch.uint8)
+    flat = b"".join(recs)
+    if flat:
+        buf[:len(flat)] = torch.frombuffer(bytearray(flat), dtype=torch.uint8)
+    buf = buf.to(dev)
+    outs = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(outs, buf, group=group)
+    res = []
+    for r in range(world):
+        raw = outs[r].cpu().numpy().tobytes()
+        cut = np.concatenate([[0], np.cumsum(all_lens[r])])
+        res.append([raw[cut[i]:cut[i + 1]] for i in range(len(recs))])
+    return res
+
+
+def _gather_ragged(mine, sizes, rank, world, dst, group):
+    """Gather complex64 runs of known sizes on rank dst (one padded gather; the NCCL path when the group is NCCL)."""
+    import torch
+    import torch.distributed as dist
+    width = max(max(sizes), 1)
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    slab = torch.zeros(2 * width, dtype=torch.float32)
+    if mine.size:
+        slab[:2 * mine.size] = torch.from_numpy(np.ascontiguousarray(mine).view(np.float32))
+    slab = slab.to(dev)
+    bufs = [torch.empty_like(slab) for _ in range(world)] if rank == dst else None
+    dist.gather(slab, bufs, dst=dst, group=group)
+    if rank != dst:
+        return None
+    return [bufs[r].cpu().numpy().view(np.complex64)[:sizes[r]].copy() for r in range(world)]

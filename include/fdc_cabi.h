@@ -175,6 +175,9 @@ int fdc_pac_state(const fdc_pac* b, int* geo, float* f);
 int fdc_pac_tables(const fdc_pac* b, float* out);    /* relinvovl * blocklen complex floats */
 int fdc_pac_msg_count(const fdc_pac* b);
 int fdc_pac_msg_get(const fdc_pac* b, int i, fdc_msg* out);
+/* all pending messages at once: out[fdc_pac_msg_count()] records; payloads of all messages concatenated (NULL: only count) */
+int fdc_pac_msg_get_all(const fdc_pac* b, fdc_msg* out);
+long fdc_pac_msg_copy_data(const fdc_pac* b, float* out);
 void fdc_pac_msg_clear(fdc_pac* b);
 void fdc_pac_destroy(fdc_pac* b);
 
@@ -195,6 +198,9 @@ int fdc_segdet_power(const fdc_segdet* b, float* out);          /* decimated pow
 int fdc_segdet_active(const fdc_segdet* b, int i, int* out);
 int fdc_segdet_msg_count(const fdc_segdet* b);
 int fdc_segdet_msg_get(const fdc_segdet* b, int i, fdc_msg* out);
+/* all pending messages at once: out[fdc_segdet_msg_count()] records; payloads of all messages concatenated (NULL: only count) */
+int fdc_segdet_msg_get_all(const fdc_segdet* b, fdc_msg* out);
+long fdc_segdet_msg_copy_data(const fdc_segdet* b, float* out);
 void fdc_segdet_msg_clear(fdc_segdet* b);
 void fdc_segdet_destroy(fdc_segdet* b);
 
@@ -213,6 +219,9 @@ int fdc_actdet_segment(const fdc_actdet* b, int i, int* out);
 int fdc_actdet_power(const fdc_actdet* b, int seg, float* out);
 int fdc_actdet_msg_count(const fdc_actdet* b);
 int fdc_actdet_msg_get(const fdc_actdet* b, int i, fdc_msg* out);
+/* all pending messages at once: out[fdc_actdet_msg_count()] records; payloads of all messages concatenated (NULL: only count) */
+int fdc_actdet_msg_get_all(const fdc_actdet* b, fdc_msg* out);
+long fdc_actdet_msg_copy_data(const fdc_actdet* b, float* out);
 void fdc_actdet_msg_clear(fdc_actdet* b);
 void fdc_actdet_destroy(fdc_actdet* b);
 
@@ -235,6 +244,53 @@ fdc_actdet* fdc_actdet_create_logic(int blocklen, const float* segments, int nse
                                     float minchandist, int channel_deactivation_delay, double window_flank_puffer,
                                     int verbose);
 int fdc_actdet_logic_work(fdc_actdet* b, int nblocks, const float* power_rows);
+
+/* ---- time-sharded calls of the activity-gated blocks (one process per GPU) ----------------------
+ * The reference blocks carry state from block to block (active flag and last power, PowerActivationChannel_impl.cc:137-177;
+ * the active-channel list and its inactivity counters, SegmentDetection_impl.cc:131-161,163-300), their measurements do not.
+ * A call over nblocks_total blocks of the stream, cut into contiguous runs of rows, one run per rank:
+ *   1. every rank:  n = *_shard_measure(b, nrows, d_rows, stream); *_shard_blob(b, buf)   compact record of ITS rows (bytes)
+ *   2. the records of all ranks are concatenated in row order (an all-gather of a few bytes per block, host plumbing)
+ *   3. every rank:  *_shard_decide(b, nblocks_total, records, bytes)   the sequential bookkeeping, replicated: every rank derives
+ *                   the same extraction jobs and message list; returns the number of jobs
+ *   4. every rank:  *_shard_extract(b, first_row, nrows, d_rows, d_prev, stream, out)   runs the jobs its rows emitted (a
+ *                   contiguous range of the job list) and writes *_shard_samples(b, first_row, nrows) complex floats to the
+ *                   host buffer `out`, in job order.  d_prev: device pointer to the spectrum row before first_row (a freshly
+ *                   activated channel also takes the previous block); NULL = all-zero row (start of the stream)
+ *   5. sink rank:   *_shard_assemble(b, results, nsamples) with the ranks' outputs concatenated in rank order -> messages
+ *                   (fdc_*_msg_*); every other rank passes NULL, which only closes the call.
+ * Device form of steps 4 and 5 (the gather fused into the extract kernel): *_shard_extract_device stores the samples at d_dst,
+ * which may be the sink rank's buffer mapped over CUDA IPC (fdc_ipc_open) -- the kernel's stores then cross NVLink -- and returns
+ * after its stream has drained; after a barrier the sink calls *_shard_assemble_device on its buffer.
+ * All ranks must make the same sequence of calls on contexts built with the same arguments.  *_shard_measure_logic is the
+ * host-logic form of step 1 (contexts from *_create_logic; input as for *_logic_work), for CPU tests of the plumbing. */
+long fdc_pac_shard_measure(fdc_pac* b, int nrows, const void* d_rows, void* stream);
+long fdc_pac_shard_measure_logic(fdc_pac* b, int nrows, const float* power);
+int fdc_pac_shard_blob(const fdc_pac* b, void* out);
+long fdc_pac_shard_decide(fdc_pac* b, int nblocks_total, const void* records, long bytes);
+long fdc_pac_shard_samples(const fdc_pac* b, int first_row, int nrows);
+long fdc_pac_shard_extract(fdc_pac* b, int first_row, int nrows, const void* d_rows, const void* d_prev, void* stream, void* out_host);
+int fdc_pac_shard_assemble(fdc_pac* b, const void* results, long nsamples);
+long fdc_pac_shard_extract_device(fdc_pac* b, int first_row, int nrows, const void* d_rows, const void* d_prev, void* stream, void* d_dst);
+int fdc_pac_shard_assemble_device(fdc_pac* b, const void* d_results, long nsamples, void* stream);
+long fdc_segdet_shard_measure(fdc_segdet* b, int nrows, const void* d_rows, void* stream);
+long fdc_segdet_shard_measure_logic(fdc_segdet* b, int nrows, const float* power);
+int fdc_segdet_shard_blob(const fdc_segdet* b, void* out);
+long fdc_segdet_shard_decide(fdc_segdet* b, int nblocks_total, const void* records, long bytes);
+long fdc_segdet_shard_samples(const fdc_segdet* b, int first_row, int nrows);
+long fdc_segdet_shard_extract(fdc_segdet* b, int first_row, int nrows, const void* d_rows, const void* d_prev, void* stream, void* out_host);
+int fdc_segdet_shard_assemble(fdc_segdet* b, const void* results, long nsamples);
+long fdc_segdet_shard_extract_device(fdc_segdet* b, int first_row, int nrows, const void* d_rows, const void* d_prev, void* stream, void* d_dst);
+int fdc_segdet_shard_assemble_device(fdc_segdet* b, const void* d_results, long nsamples, void* stream);
+long fdc_actdet_shard_measure(fdc_actdet* b, int nrows, const void* d_rows, void* stream);
+long fdc_actdet_shard_measure_logic(fdc_actdet* b, int nrows, const float* power);
+int fdc_actdet_shard_blob(const fdc_actdet* b, void* out);
+long fdc_actdet_shard_decide(fdc_actdet* b, int nblocks_total, const void* records, long bytes);
+long fdc_actdet_shard_samples(const fdc_actdet* b, int first_row, int nrows);
+long fdc_actdet_shard_extract(fdc_actdet* b, int first_row, int nrows, const void* d_rows, const void* d_prev, void* stream, void* out_host);
+int fdc_actdet_shard_assemble(fdc_actdet* b, const void* results, long nsamples);
+long fdc_actdet_shard_extract_device(fdc_actdet* b, int first_row, int nrows, const void* d_rows, const void* d_prev, void* stream, void* d_dst);
+int fdc_actdet_shard_assemble_device(fdc_actdet* b, const void* d_results, long nsamples, void* stream);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -216,3 +216,84 @@ def test_hier_block_transformed_input_mode(FDC, ref):
         got = np.concatenate([o1[1 + i], o2[1 + i]])
         assert got.size == y.size == nblocks * lout
         assert rel_l2(got, y) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ time-sharded calls
+def _virtual_ranks_run(mk, x, N, calls, world, device_form=False):
+    """The fdc_*_shard_* sequence of FDC/sharded.py: ShardedActivity with `world` contexts in ONE process (no process group
+    needed to check the arithmetic): every virtual rank holds only its own rows plus the one before them on the device."""
+    import torch
+    from FDC import sharded
+    ranks = [mk() for _ in range(world)]
+    rows = x.reshape(-1, N)
+    msgs, pos = [], 0
+    for n in calls:
+        first, count = sharded.partition(n, world)
+        dev, prev = [], []
+        for r in range(world):
+            lo = pos + first[r]
+            own = torch.from_numpy(np.ascontiguousarray(rows[lo:lo + count[r]]).view(np.float32)).cuda()
+            before = torch.from_numpy(np.ascontiguousarray(rows[lo - 1:lo]).view(np.float32)).cuda() if lo > 0 else None
+            dev.append(own); prev.append(before)
+        recs = [ranks[r].shard_measure(count[r], dev[r].data_ptr()) for r in range(world)]
+        blob = b"".join(recs)
+        njobs = [ranks[r].shard_decide(n, blob) for r in range(world)]
+        assert len(set(njobs)) == 1
+        if device_form:          # the gather fused into the extract kernel: every rank stores into the sink's device buffer
+            sizes = [ranks[0].shard_samples(first[r], count[r]) for r in range(world)]
+            sink = torch.zeros(2 * max(sum(sizes), 1), dtype=torch.float32, device="cuda")
+            for r in range(world):
+                got = ranks[r].shard_extract_device(first[r], count[r], dev[r].data_ptr(), prev[r].data_ptr() if prev[r] is not None else 0,
+                                                    sink.data_ptr() + 8 * sum(sizes[:r]))
+                assert got == sizes[r]
+            for r in range(1, world):
+                ranks[r].shard_assemble(None)
+            ranks[0].shard_assemble_device(sink.data_ptr(), sum(sizes))
+        else:
+            parts = [ranks[r].shard_extract(first[r], count[r], dev[r].data_ptr(), prev[r].data_ptr() if prev[r] is not None else 0)
+                     for r in range(world)]
+            for r in range(1, world):
+                ranks[r].shard_assemble(None)
+            ranks[0].shard_assemble(np.concatenate(parts))
+        msgs += ranks[0].messages()
+        pos += n
+    return msgs, ranks
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_sharded_segdet_equals_single_stream(FDC, ref, world):
+    N, nblocks = 4096, 100
+    x, _ = sc.bursty_spectra(N, nblocks, 12, seed=5, widths=(16, 32, 64, 128), raster=256)
+    args = (1, N, 4, 0.1, 0.9, 10.0, 0.004, 0.2, 8, 1, True, False, "", False, 0)
+    a = ref.SegmentDetection(*args); feed(a, x.reshape(-1), N, (nblocks,))
+    b = FDC.SegmentDetection(*args); feed(b, x.reshape(-1), N, (nblocks,))
+    mb = b.messages()
+    ms, ranks = _virtual_ranks_run(lambda: FDC.SegmentDetection(*args), x, N, (37, 1, 62), world)
+    assert len(mb) >= 5
+    compare_messages(a.messages(), ms)
+    # against the single-stream GPU block: the same kernels on the same rows -> identical bits
+    assert [sc.meta_tuple(m) for m in mb] == [sc.meta_tuple(m) for m in ms]
+    for u, v in zip(mb, ms):
+        assert np.array_equal(u["data"].view(np.uint32), v["data"].view(np.uint32))
+    assert all(r.active_channels() == b.active_channels() for r in ranks)
+    md, _ = _virtual_ranks_run(lambda: FDC.SegmentDetection(*args), x, N, (37, 1, 62), world, device_form=True)
+    assert [sc.meta_tuple(m) for m in mb] == [sc.meta_tuple(m) for m in md]
+    for u, v in zip(mb, md):
+        assert np.array_equal(u["data"].view(np.uint32), v["data"].view(np.uint32))
+
+
+def test_sharded_pac_and_actdet_equal_single_stream(FDC, ref):
+    N, nblocks = 4096, 80
+    x, _ = sc.bursty_spectra(N, nblocks, 14, seed=8, widths=(32, 64), raster=256)
+    args = (N, [[0.1, 0.45], [0.55, 0.9]], 10.0, 4, 6, True, False, "", False, 0.004, 1, 0.2, 0)
+    a = ref.activity_detection_channelizer_vcm(*args); feed(a, x.reshape(-1), N, (nblocks,))
+    ms, _ = _virtual_ranks_run(lambda: FDC.activity_detection_channelizer_vcm(*args), x, N, (50, 30), 3)
+    assert len(ms) >= 5
+    compare_messages(a.messages(), ms)
+    x = sc.b8_input().reshape(-1)
+    args = (256, 0.45, 0.1, 4, 6.0, 3, 1, True, False, "", 0, 7)
+    a = ref.PowerActivationChannel(*args); feed(a, x, 256, (16,))
+    ms, ranks = _virtual_ranks_run(lambda: FDC.PowerActivationChannel(*args), x, 256, (7, 9), 4)
+    assert [(m["part"], m["blockstart"], m["blockend"], m["data"].size) for m in ms] == [(0, 3, 6, 72), (1, 3, 9, 72), (2, 3, 11, 48)]
+    compare_messages(a.messages(), ms)
+    assert all(r.state() == a.state() for r in ranks)

@@ -4,6 +4,7 @@ rel-L2 <= 1e-5 (BASELINE.json north_star); byte-copy blocks and tables bit exact
 import numpy as np
 import pytest
 
+import scenarios as sc
 import workloads
 from helpers import rel_l2, make_ref_chain, make_gpu_chain
 
@@ -237,3 +238,36 @@ def test_empty_and_ragged_calls(FDC, ref):
         FDC.Channelizer(1000, 250, 4, [])
     with pytest.raises(FDC.FDCError, match="outside the spectrum"):
         FDC.Channelizer(1024, 256, 4, [(1000, 64, 48, 0, 64.0, FDC.psw_tables(64, 4, 0.5, 0.75, 1))])
+
+
+def test_context_follows_its_device_across_threads(FDC):
+    """CUDA's current device is per thread and GNU Radio calls work() from a scheduler thread: a context made on device 1 must
+    work when called from a thread whose current device is 0 (needs two GPUs; the single-GPU box still runs the thread part)"""
+    import threading
+    from oracle import fdc_numpy as fnp
+    L = FDC._cabi.lib()
+    dev = 1 if L.fdc_device_count() > 1 else 0
+    FDC._cabi.check(L.fdc_set_device(dev))
+    try:
+        cfg = workloads.cfg_example(1024, 4, workloads.HANN)
+        chan = make_gpu_chain(FDC, cfg)
+        sd = FDC.SegmentDetection(1, 1024, 4, 0.1, 0.9, 10.0, 0.0312, 0.2, 4, 1, True, False, "", False, 0)
+    finally:
+        FDC._cabi.check(L.fdc_set_device(0))
+    x = workloads.tones_input(cfg, 40 * cfg.hop, seed=77)
+    spec, _ = sc.bursty_spectra(1024, 40, 6, seed=3, widths=(16, 32), raster=64)
+    box = {}
+
+    def worker():                                   # a fresh thread: current device 0
+        try:
+            box["outs"], _ = chan.work_host(x)
+            sd.work(40, [spec.reshape(-1)])
+            box["msgs"] = sd.messages()
+        except Exception as e:                      # noqa: BLE001
+            box["err"] = e
+    t = threading.Thread(target=worker); t.start(); t.join()
+    assert "err" not in box, box.get("err")
+    want, _ = fnp.channelize(x, cfg.N, cfg.R, cfg.params, cfg.windowtype)
+    for o, w in zip(box["outs"], want):
+        assert rel_l2(o, w) < TOL
+    assert len(box["msgs"]) >= 1

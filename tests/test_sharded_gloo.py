@@ -92,3 +92,97 @@ def test_partition_and_halo():
     hist = -np.arange(1, 26, dtype=np.complex64)
     halo, new = sharded.shard_input(x, 10, 25, 1, 2, stream_history=hist)
     assert np.array_equal(halo, np.concatenate([hist[10:], x[:10]])) and np.array_equal(new, x[10:30])
+
+
+# ------------------------------------------------------------------------------------------------ activity-gated blocks, time sharded
+def _activity_blocks(FDC, N):
+    """(name, block, power rows) for the three activity-gated blocks on one bursty scenario (host-logic contexts: no GPU)"""
+    import scenarios as sc
+    x, _ = sc.bursty_spectra(N, 96, 8, seed=52, widths=(16, 32, 64), mean_on=9, mean_off=12)
+    res = []
+    b = FDC.SegmentDetection(5, N, 4, 0.1, 0.9, 10.0, 0.0312, 0.2, 4, 1, True, False, "", False, 0, _logic=True)
+    st = b.state()
+    res.append(("segdet", b, sc.group_power(x, st["d_start"], st["D"], st["M"])))
+    b = FDC.activity_detection_channelizer_vcm(N, [[0.1, 0.45], [0.55, 0.9]], 10.0, 4, 4, True, False, "", False, 0.0312, 1, 0.2, 0, _logic=True)
+    res.append(("actdet", b, np.concatenate([sc.group_power(x, s["start"], s["D"], s["M"], mean=True) for s in b.segments()], axis=1)))
+    b = FDC.PowerActivationChannel(N, 0.45, 0.1, 4, 6.0, 3, 1, True, False, "", 0, 7, _logic=True)
+    st = b.state()
+    # a carrier of its own inside the measured band so that the channel really toggles
+    y = x.copy(); y[:, st["measure_start"]:st["measure_stop"]] *= np.where((np.arange(96) // 7) % 2, 8.0, 1.0).astype(np.float32)[:, None]
+    res.append(("pac", b, sc.band_power(y, st["measure_start"], st["measure_stop"])))
+    return res
+
+
+ACT_CALLS = (40, 1, 55)       # global calls (blocks each): 96 blocks in all
+
+
+def _rank_activity(rank, world, port, q):
+    for p in (ROOT, os.path.join(ROOT, "gr-fdc_b200", "python"), os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    import FDC
+    import scenarios as sc
+    from FDC import sharded
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        got = {}
+        for name, blk, P in _activity_blocks(FDC, 1024):
+            sa = sharded.ShardedActivity(blk, rank, world, dst=0)
+            msgs, pos = [], 0
+            for n in ACT_CALLS:
+                first, count = sharded.partition(n, world)
+                m = sa.work(n, power=P[pos + first[rank]:pos + first[rank] + count[rank]])
+                pos += n
+                if rank == 0:
+                    msgs += m
+                else:
+                    assert m is None
+            got[name] = [sc.meta_tuple(m) for m in msgs]
+        # the three blocks as one group (one all-gather + one gather per call), local phases on a thread pool
+        from concurrent.futures import ThreadPoolExecutor
+        trio = _activity_blocks(FDC, 1024)
+        grp = sharded.ShardedActivityGroup([t[1] for t in trio], rank, world, dst=0, pool=ThreadPoolExecutor(3))
+        msgs, pos = [[] for _ in trio], 0
+        for n in ACT_CALLS:
+            first, count = sharded.partition(n, world)
+            m = grp.work(n, powers=[t[2][pos + first[rank]:pos + first[rank] + count[rank]] for t in trio])
+            pos += n
+            if rank == 0:
+                for i, mm in enumerate(m):
+                    msgs[i] += mm
+        for t, mm in zip(trio, msgs):
+            got["group_" + t[0]] = [sc.meta_tuple(m) for m in mm]
+        if rank == 0:
+            q.put(got)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_activity_bookkeeping(world):
+    """measure (own rows) -> all-gather of the records -> replicated bookkeeping -> extract (own jobs) -> assemble on the sink:
+    the PDU sequence equals the single-stream block's (which test_host_logic.py checks against the reference blocks)"""
+    import torch.multiprocessing as mp
+    for p in (ROOT, os.path.join(ROOT, "gr-fdc_b200", "python"), os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import FDC
+    import scenarios as sc
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_rank_activity, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    for name, blk, P in _activity_blocks(FDC, 1024):
+        blk.logic_work(P.shape[0], P)
+        want = [sc.meta_tuple(m) for m in blk.messages()]
+        assert len(want) >= 3, name
+        assert got[name] == want, name
+        assert got["group_" + name] == want, name
