@@ -297,3 +297,23 @@ def test_sharded_pac_and_actdet_equal_single_stream(FDC, ref):
     assert [(m["part"], m["blockstart"], m["blockend"], m["data"].size) for m in ms] == [(0, 3, 6, 72), (1, 3, 9, 72), (2, 3, 11, 48)]
     compare_messages(a.messages(), ms)
     assert all(r.state() == a.state() for r in ranks)
+
+
+def test_segdet_cfg5_geometry(FDC, ref):
+    """configs[4] class: FFT 262144, narrow (40-bin) DAMA carriers on a 64-bin raster over [0.02, 0.98], hundreds of them active per
+    block; single stream and time sharded over 4 virtual ranks against the reference block"""
+    N, nblocks = 262144, 14
+    x, truth = sc.bursty_spectra(N, nblocks, 1500, seed=55, raster=64, widths=(40,), mean_on=4, mean_off=30, lo=0.02, hi=0.98)
+    args = (2, N, 4, 0.02, 0.98, 10.0, 16.0 / N, 0.2, 3, 1, True, False, "", False, 0)
+    a = ref.SegmentDetection(*args); b = FDC.SegmentDetection(*args)
+    assert a.state() == b.state() and a.state()["D"] <= 16
+    feed(a, x.reshape(-1), N, (nblocks,)); feed(b, x.reshape(-1), N, (5, 9))
+    ma, mb = a.messages(), b.messages()
+    assert len(ma) >= 300
+    compare_messages(ma, mb)
+    assert a.active_channels() == b.active_channels()
+    assert np.array_equal(a.power().view(np.uint32), b.power().view(np.uint32))
+    ms, _ = _virtual_ranks_run(lambda: FDC.SegmentDetection(*args), x, N, (nblocks,), 4, device_form=True)
+    assert [sc.meta_tuple(m) for m in mb] == [sc.meta_tuple(m) for m in ms]
+    for u, v in zip(mb, ms):
+        assert np.array_equal(u["data"].view(np.uint32), v["data"].view(np.uint32))
