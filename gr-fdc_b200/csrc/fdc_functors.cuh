@@ -188,6 +188,7 @@ struct ExtractParams {
     int glob_phase0;       /* (global index of the chunk's first block) mod nphase */
     int nphase;
     int tma_ok;            /* every slice of this launch is 16-byte aligned (even f, aligned spectrum base and stride) */
+    int l2pf;              /* bulk-prefetch the next tile's slices into L2 while this tile is transformed (needs tma_ok) */
     int phase_mask;        /* nphase - 1 when nphase is a power of two (the hier block's relinvovl always is), else -1 */
 };
 /* x mod nphase without an integer division when nphase is a power of two */
@@ -277,6 +278,17 @@ template <int L, int B> struct ExtractTiles {           /* tile = block * ny + c
         return ExtractLoader<L, B>{p, t.inner, (long)t.outer, phase_mod(p, (unsigned)p.glob_phase0 + (unsigned)t.outer)};
     }
     FDC_HD ExtractStorer<L, B> storer(TilePos t) const { return ExtractStorer<L, B>{p, t.inner, (long)t.outer}; }
+#if defined(__CUDACC__) && !defined(FDC_HOST_EMU)
+    /* thread `tid` < B asks the TMA engine to pull signal tid's slice of tile t into L2 */
+    static constexpr bool HAS_L2_PREFETCH = true;
+    __device__ __forceinline__ void prefetch_l2(TilePos t, int tid) const
+    {
+        if (!p.l2pf || tid >= B) return;
+        int s = t.inner * B + tid;
+        if (s >= p.nsel) return;
+        bulk_prefetch_l2(p.spec + ((long)t.outer * p.spec_stride + p.chans[s].f), (uint32_t)(sizeof(float2) * L));
+    }
+#endif
 };
 
 /* ------------------------------------------------- K2 (activity gated): explicit job list

@@ -27,9 +27,10 @@
  * that the same functions run on the device and under the host emulator (see fdc_hd.h). */
 #ifndef FDC_TILE_FFT_CUH
 #define FDC_TILE_FFT_CUH
+#include <type_traits>
 #include "fdc_bfly.cuh"
-#include "fdc_functors.cuh"
 #include "fdc_tma.cuh"
+#include "fdc_functors.cuh"
 
 namespace fdc {
 
@@ -277,6 +278,8 @@ __device__ __forceinline__ void tile_fft_from(float2* v, float2* smem, const flo
  * Order inside an iteration: finish (the loader's own table loads + arithmetic) -> prefetch of the next tile ->
  * butterflies.  The only global loads in flight during the butterflies are the prefetch: the twiddles come from
  * shared memory, so no instruction waits on a scoreboard that it shares with a DRAM access. */
+template <class T, class = void> struct tiles_l2_prefetch { static constexpr bool value = false; };
+template <class T> struct tiles_l2_prefetch<T, typename std::enable_if<T::HAS_L2_PREFETCH>::type> { static constexpr bool value = true; };
 template <class ENG, bool PF, class Tiles, bool TW_SMEM = true>
 __device__ __forceinline__ void tile_fft_loop(float2* smem, const float2* tw_global, const Tiles& tiles, long first, long stride, long ntiles)
 {
@@ -313,6 +316,7 @@ __device__ __forceinline__ void tile_fft_loop(float2* smem, const float2* tw_glo
             for (int i = 0; i < ENG::E; i++) v[i] = nx[i];
         } else {
             ENG::fetch(threadIdx.x, v, tiles.loader(pos));
+            if constexpr (tiles_l2_prefetch<Tiles>::value) { if (next < ntiles) tiles.prefetch_l2(npos, (int)threadIdx.x); }
             ENG::finish(threadIdx.x, v, tiles.loader(pos));
             tile_fft_from<ENG, 0, TWS>(v, smem, tw, tiles.storer(pos));
             if (next >= ntiles) break;

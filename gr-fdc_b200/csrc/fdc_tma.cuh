@@ -28,6 +28,12 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_glo
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_global), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+/* ask the TMA engine to bring [src, src + bytes) into L2 (no destination, no completion to wait for): one instruction of one
+ * thread per contiguous run; src 16-byte aligned, bytes a multiple of 16 */
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src_global, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_global), "r"(bytes) : "memory");
+}
 /* wait until the barrier's phase with the given parity has completed; traps instead of hanging the GPU if the bytes never
  * arrive (a mis-sized expect_tx would otherwise spin forever) */
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
