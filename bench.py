@@ -346,7 +346,7 @@ def run_cfg3(args, rank, world, local):
         rsd = [ref.SegmentDetection(i, N, R, a, b, 10.0, 0.002, 0.2, 128, 1, True, False, "", False, 0) for i, (a, b) in enumerate(segs)]
         rpc = [ref.PowerActivationChannel(N, f, bw, R, 6.0, 128, 1, True, False, "", 0, i) for i, (f, bw) in enumerate(pac)]
         t1 = time.perf_counter(); reps = 0
-        while time.perf_counter() - t1 < 10.0 and reps < 16:
+        while time.perf_counter() - t1 < 10.0 and reps < 256:
             _, sp = chain.run(x, nthreads=cores, want_spectrum=True, want_outputs=False)
             list(pool.map(lambda b: (b.work(sp), b.messages()), rsd + rpc))
             reps += 1
