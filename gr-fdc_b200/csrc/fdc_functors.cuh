@@ -21,6 +21,7 @@
 #ifndef FDC_FUNCTORS_CUH
 #define FDC_FUNCTORS_CUH
 #include "fdc_hd.h"
+#include "fdc_tma.cuh"
 
 namespace fdc {
 
