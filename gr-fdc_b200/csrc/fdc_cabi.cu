@@ -168,7 +168,7 @@ static int chan_enqueue_chunk(fdc_chan* c, const float2* d_in, long nb, float2* 
     if (c->prof) cudaEventRecord(c->ev(), s);
     if (!c->big) {
         FwdParams p; p.in = d_in; p.spec = d_spec; p.nblocks = nb; p.hop = c->hop; p.ovl = c->ovl; p.N = c->N;
-        p.scale = 1.0f / (float)c->N;
+        p.scale = 1.0f / (float)c->N; p.l2pf = tuning().l2pf ? 1 : 0;
         e = launch_fwd_small(p, s);
     } else {
         BigParams p; p.in = d_in; p.mid = d_mid; p.spec = d_spec; p.tw4 = c->tw4;

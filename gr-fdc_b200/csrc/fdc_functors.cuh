@@ -47,6 +47,7 @@ struct FwdParams {
     long nblocks;
     int hop, ovl, N;
     float scale;           /* 1/N (a power of two: exact) */
+    int l2pf;              /* kernels without a register prefetch: bulk-prefetch the next tile's samples into L2 */
 };
 template <int N, int B> struct FwdLoader {
     typedef const float2* Ctx;
@@ -81,6 +82,22 @@ template <int N, int B> struct FwdTiles {
     FDC_HD int ninner() const { return 1; }
     FDC_HD FwdLoader<N, B> loader(TilePos t) const { return FwdLoader<N, B>{p, (long)t.outer}; }
     FDC_HD FwdStorer<N, B> storer(TilePos t) const { return FwdStorer<N, B>{p, (long)t.outer}; }
+#if defined(__CUDACC__) && !defined(FDC_HOST_EMU)
+    /* the B blocks of a tile are one contiguous run of samples: one bulk prefetch by one thread */
+    static constexpr bool HAS_L2_PREFETCH = true;
+    __device__ __forceinline__ void prefetch_l2(TilePos t, int tid) const
+    {
+        if (!p.l2pf || tid != 0) return;
+        const long blk0 = (long)t.outer * B;
+        const long nb = p.nblocks - blk0 < B ? p.nblocks - blk0 : B;
+        if (nb <= 0) return;
+        const char* a = reinterpret_cast<const char*>(p.in + (blk0 * p.hop - p.ovl));
+        long bytes = (long)sizeof(float2) * ((nb - 1) * p.hop + N);
+        if (reinterpret_cast<uintptr_t>(a) & 15) { a += 8; bytes -= 8; }          /* float2 granularity: at most 8 bytes off */
+        bytes &= ~15L;
+        if (bytes > 0) bulk_prefetch_l2(a, (uint32_t)bytes);
+    }
+#endif
 };
 
 /* ------------------------------------------------------ K1 (large N = N1*N2): four-step, two kernels

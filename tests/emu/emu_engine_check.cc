@@ -123,7 +123,7 @@ template <int N, int E = 16> static void check_fwd_small(int ovl, long nblocks)
     std::vector<float2> buf((size_t)ovl + (size_t)nblocks * hop), spec((size_t)nblocks * N);
     for (auto& v : buf) { v.x = frand(); v.y = frand(); }
     const std::vector<float2> tw = pass_twiddles(N, E);
-    FwdParams p; p.in = buf.data() + ovl; p.spec = spec.data(); p.nblocks = nblocks; p.hop = hop; p.ovl = ovl; p.N = N; p.scale = 1.0f / N;
+    FwdParams p; p.in = buf.data() + ovl; p.spec = spec.data(); p.nblocks = nblocks; p.hop = hop; p.ovl = ovl; p.N = N; p.scale = 1.0f / N; p.l2pf = 0;
     run_tiles<ENG>(FwdTiles<N, B>{p}, (nblocks + B - 1) / B, tw.data());
     double worst = 0;
     for (long b = 0; b < nblocks; b++) {
@@ -208,7 +208,7 @@ template <int L, int E = 16> static void check_extract(int N, int nchan, long nb
     }
     std::vector<float2> out((size_t)(call_blocks * prefix), make_float2(-9.f, -9.f));
     const std::vector<float2> tw = pass_twiddles(L, E);
-    ExtractParams p; p.spec = spec.data(); p.spec_stride = N; p.tables = tables.data(); p.chans = chans.data();
+    ExtractParams p; p.l2pf = 0; p.spec = spec.data(); p.spec_stride = N; p.tables = tables.data(); p.chans = chans.data();
     p.nsel = nchan; p.ny = (nchan + B - 1) / B; p.out = out.data(); p.nb = nb; p.call_blocks = call_blocks; p.call_blk0 = call_blk0;
     p.glob_phase0 = glob_phase0; p.nphase = nphase; p.tma_ok = 0; p.phase_mask = (nphase & (nphase - 1)) == 0 ? nphase - 1 : -1;
     run_tiles<ENG>(ExtractTiles<L, B>{p}, nb * p.ny, tw.data());
@@ -257,7 +257,7 @@ template <int L> static void check_extract_staged(int N, int nchan, long nb, int
     }
     std::vector<float2> out((size_t)(nb * prefix));
     const std::vector<float2> tw = pass_twiddles(L, 32);
-    ExtractParams p; p.spec = spec.data(); p.spec_stride = N; p.tables = tables.data(); p.chans = chans.data(); p.nsel = nchan;
+    ExtractParams p; p.l2pf = 0; p.spec = spec.data(); p.spec_stride = N; p.tables = tables.data(); p.chans = chans.data(); p.nsel = nchan;
     p.ny = (nchan + B - 1) / B; p.out = out.data(); p.nb = nb; p.call_blocks = nb; p.call_blk0 = 0; p.glob_phase0 = 0; p.nphase = nphase; p.tma_ok = 1; p.phase_mask = (nphase & (nphase - 1)) == 0 ? nphase - 1 : -1;
     ExtractStageTiles<L, B> tiles{p, stage.data()};
     std::vector<float2> smem(ENG::SMEM_ELEMS);
