@@ -183,7 +183,7 @@ static int chan_enqueue_chunk(fdc_chan* c, const float2* d_in, long nb, float2* 
         q.chans = (const ChanDev*)c->d_chans.p + c->groups[g].second.first;
         q.nsel = c->groups[g].second.second; q.ny = 0; q.out = d_out;
         q.tma_ok = ((uintptr_t)d_spec % 16 == 0) && (c->N % 2 == 0) && c->group_even_f[g];
-        q.l2pf = (tuning().l2pf && q.tma_ok) ? 1 : 0;
+        q.l2pf = (tuning().l2pf && q.tma_ok) ? 1 : 0; q.bpt = 1;
         q.nb = nb; q.call_blocks = call_blocks; q.call_blk0 = call_blk0; q.glob_phase0 = (int)(glob_blk0 % c->nphase); q.nphase = c->nphase;
         q.phase_mask = (c->nphase & (c->nphase - 1)) == 0 ? c->nphase - 1 : -1;
         e = launch_extract(q, c->groups[g].first, s);
@@ -442,7 +442,7 @@ int fdc_chan_work_spectrum_device(fdc_chan* c, const void* d_spec_in_v, long nbl
             ExtractParams q; q.spec = spec; q.spec_stride = c->N; q.tables = (const float2*)c->d_tables.p;
             q.chans = (const ChanDev*)c->d_chans.p + c->groups[g].second.first; q.nsel = c->groups[g].second.second; q.ny = 0; q.out = d_out;
             q.tma_ok = ((uintptr_t)spec % 16 == 0) && (c->N % 2 == 0) && c->group_even_f[g];
-            q.l2pf = (tuning().l2pf && q.tma_ok) ? 1 : 0;
+            q.l2pf = (tuning().l2pf && q.tma_ok) ? 1 : 0; q.bpt = 1;
             q.nb = nb; q.call_blocks = nblocks; q.call_blk0 = b0; q.glob_phase0 = (int)((c->blockcount + b0) % c->nphase); q.nphase = c->nphase;
             q.phase_mask = (c->nphase & (c->nphase - 1)) == 0 ? c->nphase - 1 : -1;
             e = launch_extract(q, c->groups[g].first, s);

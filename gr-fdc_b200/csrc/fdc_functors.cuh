@@ -207,6 +207,7 @@ struct ExtractParams {
     int nphase;
     int tma_ok;            /* every slice of this launch is 16-byte aligned (even f, aligned spectrum base and stride) */
     int l2pf;              /* bulk-prefetch the next tile's slices into L2 while this tile is transformed (needs tma_ok) */
+    int bpt;               /* packed tiles (few channels of this length): a tile holds all nsel channels of bpt consecutive blocks */
     int phase_mask;        /* nphase - 1 when nphase is a power of two (the hier block's relinvovl always is), else -1 */
 };
 /* x mod nphase without an integer division when nphase is a power of two */
@@ -305,6 +306,75 @@ template <int L, int B> struct ExtractTiles {           /* tile = block * ny + c
         int s = t.inner * B + tid;
         if (s >= p.nsel) return;
         bulk_prefetch_l2(p.spec + ((long)t.outer * p.spec_stride + p.chans[s].f), (uint32_t)(sizeof(float2) * L));
+    }
+#endif
+};
+
+/* Packed tiles: when a launch has fewer than B / 2 channels of this length (the usual GNU Radio flowgraph has a handful),
+ * one block does not fill a tile and most of the CTA would transform padding.  A packed tile takes all nsel channels of
+ * bpt = B / nsel consecutive blocks instead: signal `batch` is channel batch % nsel of block first + batch / nsel. */
+template <int L, int B> struct PackedSignal {
+    long blk; int s; bool valid;
+    FDC_HD PackedSignal(const ExtractParams& p, long first, int batch)
+    {
+        const int db = batch / p.nsel;
+        s = batch - db * p.nsel; blk = first + db;
+        valid = db < p.bpt && blk < p.nb;
+        if (!valid) { blk = first; s = 0; }                /* padding signals recompute the first one, nothing is stored */
+    }
+};
+template <int L, int B> struct PackedExtractLoader {
+    struct Ctx { const float2* x; const float2* w; };
+    static constexpr bool HAS_FINISH = true;
+    const ExtractParams& p; long first;
+    FDC_HD Ctx begin(int batch, int j) const
+    {
+        Ctx c;
+        const PackedSignal<L, B> g(p, first, batch);
+        const ChanDev& ch = p.chans[g.s];
+        const unsigned phase = phase_mod(p, phase_mod(p, (unsigned)p.glob_phase0 + (unsigned)g.blk) * (unsigned)ch.shift);
+        c.x = p.spec + (g.blk * p.spec_stride + ch.f + j);
+        c.w = p.tables + (ch.tab_off + (long)phase * L + j);
+        return c;
+    }
+    template <int R, int STRIDE> FDC_HD float2 fetch(const Ctx& c, int t) const { return fdc_ldg(c.x + ((t + R / 2) % R) * STRIDE); }
+    template <int R, int STRIDE> FDC_HD float2 finish(const Ctx& c, int t, float2 raw) const
+    {
+        return cmul(raw, fdc_ldg(c.w + ((t + R / 2) % R) * STRIDE));
+    }
+};
+template <int L, int B> struct PackedExtractStorer {
+    struct Ctx { float2* dst; int skip; float gain; };
+    const ExtractParams& p; long first;
+    FDC_HD Ctx begin(int batch, int o) const
+    {
+        Ctx c; c.dst = p.out; c.skip = 1 << 30; c.gain = 0.f;
+        const PackedSignal<L, B> g(p, first, batch);
+        if (!g.valid) return c;
+        const ChanDev& ch = p.chans[g.s];
+        c.skip = L - ch.lout - o; c.gain = ch.gain;
+        c.dst = p.out + (p.call_blocks * ch.lout_prefix + (p.call_blk0 + g.blk) * ch.lout - (L - ch.lout) + o);
+        return c;
+    }
+    static constexpr bool HAS_VARIANT = true;
+    FDC_HD bool variant(const Ctx& c) const { return c.gain == 1.0f; }
+    template <int R, int NS, bool UNIT> FDC_HD void put(const Ctx& c, int t, float2 v) const
+    {
+        if (t * NS >= c.skip) c.dst[t * NS] = UNIT ? v : make_float2(v.x * c.gain, v.y * c.gain);
+    }
+};
+template <int L, int B> struct PackedExtractTiles {     /* tile = group of bpt blocks */
+    const ExtractParams& p;
+    FDC_HD int ninner() const { return 1; }
+    FDC_HD PackedExtractLoader<L, B> loader(TilePos t) const { return PackedExtractLoader<L, B>{p, (long)t.outer * p.bpt}; }
+    FDC_HD PackedExtractStorer<L, B> storer(TilePos t) const { return PackedExtractStorer<L, B>{p, (long)t.outer * p.bpt}; }
+#if defined(__CUDACC__) && !defined(FDC_HOST_EMU)
+    static constexpr bool HAS_L2_PREFETCH = true;
+    __device__ __forceinline__ void prefetch_l2(TilePos t, int tid) const
+    {
+        if (!p.l2pf || tid >= B) return;
+        const PackedSignal<L, B> g(p, (long)t.outer * p.bpt, tid);
+        if (g.valid) bulk_prefetch_l2(p.spec + (g.blk * p.spec_stride + p.chans[g.s].f), (uint32_t)(sizeof(float2) * L));
     }
 #endif
 };

@@ -13,6 +13,25 @@ k_extract(const ExtractParams p, const float2* __restrict__ tw, long ntiles)
 {
     tile_kernel_body<TileFFT<L, B, -1, false, false>, PF>(ExtractTiles<L, B>{p}, tw, ntiles);
 }
+/* packed tiles (few channels: a tile spans several blocks, fdc_functors.cuh) */
+template <int L, int B>
+__global__ void __launch_bounds__((TileFFT<L, B, -1, false, false>::T), min_ctas(TileFFT<L, B, -1, false, false>::T, false, L))
+k_extract_packed(const ExtractParams p, const float2* __restrict__ tw, long ntiles)
+{
+    tile_kernel_body<TileFFT<L, B, -1, false, false>, false>(PackedExtractTiles<L, B>{p}, tw, ntiles);
+}
+template <int L, int B>
+__global__ void __launch_bounds__(256, 4)
+k_extract8_packed(const ExtractParams p, const float2* __restrict__ tw, long ntiles)
+{
+    tile_kernel_body<TileFFT<L, B, -1, false, false, 8>, false>(PackedExtractTiles<L, B>{p}, tw, ntiles);
+}
+template <int L, int B>
+__global__ void __launch_bounds__(128, 5)
+k_extract32_packed(const ExtractParams p, const float2* __restrict__ tw, long ntiles)
+{
+    tile_kernel_body<TileFFT<L, B, -1, false, false, 32>, false>(PackedExtractTiles<L, B>{p}, tw, ntiles);
+}
 /* 8 points per thread: tiles of 2048 points on 256 threads at <= 64 registers, four CTAs (32 warps) per SM instead of two
  * CTAs (16 warps) -- the extract is latency bound, not bandwidth bound, so it is the warps in flight that count */
 template <int L, int B, bool PF>
@@ -49,11 +68,28 @@ k_jobs(const JobParams p, const float2* __restrict__ tw, long ntiles)
     tile_kernel_body<TileFFT<L, B, -1, false, false>, false>(JobTiles<L, B>{p}, tw, ntiles);
 }
 
+/* fewer than half a tile of channels and more than one block: pack several blocks into a tile */
+static bool use_packed(ExtractParams& p, int B, long* ntiles)
+{
+    p.bpt = 1;
+    if (B < 2 || p.nsel * 2 > B || p.nb < 2 || !tuning().pack) return false;
+    p.bpt = B / p.nsel; p.ny = 1;
+    *ntiles = (p.nb + p.bpt - 1) / p.bpt;
+    return true;
+}
 template <int L, bool PF> static cudaError_t go_extract(const ExtractParams& p0, cudaStream_t s)
 {
     constexpr int B = tile_batch(L);
     typedef TileFFT<L, B, -1, false, false> ENG;
     ExtractParams p = p0;
+    if constexpr (B >= 2) {
+        long nt = 0;
+        if (use_packed(p, B, &nt)) {
+            unsigned g = 1;
+            FDC_CHECK(persistent_grid(k_extract_packed<L, B>, ENG::T, tile_smem_bytes<ENG>(), nt, 1, &g, tuning().ctas_ext));
+            return launch_tile_kernel(k_extract_packed<L, B>, g, ENG::T, tile_smem_bytes<ENG>(), s, p, twiddle_table(L), nt);
+        }
+    }
     p.ny = (p.nsel + B - 1) / B;
     const long ntiles = p.nb * p.ny;
     unsigned grid = 1;
@@ -66,6 +102,14 @@ template <int L, bool PF> static cudaError_t go_extract8(const ExtractParams& p0
     typedef TileFFT<L, B, -1, false, false, 8> ENG;
     static_assert(ENG::T == 256, "2048-point tiles");
     ExtractParams p = p0;
+    {
+        long nt = 0;
+        if (use_packed(p, B, &nt)) {
+            unsigned g = 1;
+            FDC_CHECK(persistent_grid(k_extract8_packed<L, B>, ENG::T, tile_smem_bytes<ENG>(), nt, 1, &g));
+            return launch_tile_kernel(k_extract8_packed<L, B>, g, ENG::T, tile_smem_bytes<ENG>(), s, p, twiddle_table(L, 8), nt);
+        }
+    }
     p.ny = (p.nsel + B - 1) / B;
     const long ntiles = p.nb * p.ny;
     unsigned grid = 1;
@@ -78,6 +122,14 @@ template <int L> static cudaError_t go_extract32(const ExtractParams& p0, cudaSt
     typedef TileFFT<L, B, -1, false, false, 32> ENG;
     static_assert(ENG::T == 128, "4096-point tiles on 128 threads");
     ExtractParams p = p0;
+    {
+        long nt = 0;
+        if (use_packed(p, B, &nt)) {
+            unsigned g = 1;
+            FDC_CHECK(persistent_grid(k_extract32_packed<L, B>, ENG::T, tile_smem_bytes<ENG>(), nt, 1, &g, tuning().ctas_ext));
+            return launch_tile_kernel(k_extract32_packed<L, B>, g, ENG::T, tile_smem_bytes<ENG>(), s, p, twiddle_table(L, 32), nt);
+        }
+    }
     p.ny = (p.nsel + B - 1) / B;
     const long ntiles = p.nb * p.ny;
     unsigned grid = 1;

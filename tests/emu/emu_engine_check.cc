@@ -189,7 +189,7 @@ template <int N1, int N2> static void check_fwd_big(int ovl, long nblocks)
 }
 
 /* ---- K2: channel tiles, shared tables, phase selection, overlap discard, gain ---- */
-template <int L, int E = 16> static void check_extract(int N, int nchan, long nb, int nphase)
+template <int L, int E = 16, bool PACK = false> static void check_extract(int N, int nchan, long nb, int nphase)
 {
     constexpr int B = E == 8 ? 2048 / L : (L >= 4096 ? 1 : 4096 / L);
     typedef TileFFT<L, B, -1, false, false, E> ENG;
@@ -211,7 +211,13 @@ template <int L, int E = 16> static void check_extract(int N, int nchan, long nb
     ExtractParams p; p.l2pf = 0; p.spec = spec.data(); p.spec_stride = N; p.tables = tables.data(); p.chans = chans.data();
     p.nsel = nchan; p.ny = (nchan + B - 1) / B; p.out = out.data(); p.nb = nb; p.call_blocks = call_blocks; p.call_blk0 = call_blk0;
     p.glob_phase0 = glob_phase0; p.nphase = nphase; p.tma_ok = 0; p.phase_mask = (nphase & (nphase - 1)) == 0 ? nphase - 1 : -1;
-    run_tiles<ENG>(ExtractTiles<L, B>{p}, nb * p.ny, tw.data());
+    p.bpt = 1;
+    if (PACK) {              /* few channels: a tile holds all channels of bpt consecutive blocks */
+        p.bpt = B / nchan; p.ny = 1;
+        if (p.bpt < 2) { printf("packed case needs nchan <= B / 2\n"); exit(2); }
+        run_tiles<ENG>(PackedExtractTiles<L, B>{p}, (nb + p.bpt - 1) / p.bpt, tw.data());
+    } else
+        run_tiles<ENG>(ExtractTiles<L, B>{p}, nb * p.ny, tw.data());
     double worst = 0;
     for (int i = 0; i < nchan; i++)
         for (long b = 0; b < nb; b++) {
@@ -236,7 +242,7 @@ template <int L, int E = 16> static void check_extract(int N, int nchan, long nb
             const float2* r = out.data() + (size_t)(call_blocks * chans[i].lout_prefix + b * chans[i].lout);
             for (int k = 0; k < chans[i].lout; k++) if (r[k].x != -9.f) stray++;
         }
-    char name[128]; snprintf(name, sizeof name, "extract L=%d E=%d N=%d nchan=%d nb=%ld nphase=%d stray=%ld", L, E, N, nchan, nb, nphase, stray);
+    char name[128]; snprintf(name, sizeof name, "extract%s L=%d E=%d N=%d nchan=%d nb=%ld nphase=%d stray=%ld", PACK ? " packed" : "", L, E, N, nchan, nb, nphase, stray);
     report(name, stray ? 1.0 : worst, 3e-6);
 }
 
@@ -339,6 +345,9 @@ int main()
     check_extract<64, 8>(1024, 16, 5, 2); check_extract<128, 8>(4096, 70, 3, 4); check_extract<256, 8>(8192, 64, 3, 4);
     check_extract<512, 8>(8192, 19, 5, 4); check_extract<1024, 8>(4096, 5, 3, 4); check_extract<2048, 8>(8192, 3, 2, 4);
     check_extract<512, 32>(8192, 19, 5, 4); check_extract<1024, 32>(4096, 5, 3, 4); check_extract<512, 32>(65536, 256, 2, 4);
+    check_extract<64, 16, true>(1024, 16, 11, 2); check_extract<64, 8, true>(1024, 16, 7, 4); check_extract<256, 16, true>(4096, 3, 17, 4);
+    check_extract<128, 8, true>(2048, 5, 9, 3); check_extract<1024, 32, true>(4096, 1, 9, 4); check_extract<512, 32, true>(8192, 3, 6, 4);
+    check_extract<2, 16, true>(64, 5, 700, 4);
     check_extract_staged<512>(8192, 19, 3, 4); check_extract_staged<1024>(8192, 6, 2, 4);
     check_jobs<64>(1024, 70); check_jobs<512>(4096, 11); check_jobs<16>(256, 300);
     printf("%s\n", g_fail ? "EMU FAILED" : "EMU OK");

@@ -18,6 +18,7 @@ VARIANTS = {
     "extract_16_points_per_thread": {"FDC_EXTRACT_E32": "0"},
     "extract_32_points_tma_staged": {"FDC_EXTRACT_E32": "2"},
     "extract_without_l2_prefetch": {"FDC_L2PF": "0"},
+    "extract_one_block_per_tile": {"FDC_PACK": "0"},
     "forward_16_points_per_thread": {"FDC_FWD_E32": "0"},
     "forward_32_points_everywhere": {"FDC_FWD_E32": "2"},
     "four_step_from_4096": {"FDC_FWD_SPLIT": "4096"},
