@@ -157,9 +157,10 @@ template <int L> static cudaError_t go_extract_pf(const ExtractParams& p, cudaSt
     }
     if constexpr (L >= 64 && L <= 2048) {
         /* short slices have many signals per tile and little work per signal: twice the warps wins there (measured: l = 64
-         * 1.5x faster, l >= 256 10-20 % slower); FDC_EXTRACT_E8 = 0 / 1 forces either engine */
+         * 1.5x faster; l = 128 11 % slower on cfg5 since the next tile is prefetched into L2; l >= 256 10-20 % slower);
+         * FDC_EXTRACT_E8 = 0 / 1 forces either engine */
         const int e8 = tuning().extract_e8;
-        if (e8 > 0 || (e8 < 0 && L <= 128)) return (tuning().prefetch & 2) ? go_extract8<L, true>(p, s) : go_extract8<L, false>(p, s);
+        if (e8 > 0 || (e8 < 0 && L <= 64)) return (tuning().prefetch & 2) ? go_extract8<L, true>(p, s) : go_extract8<L, false>(p, s);
     }
     if constexpr (can_prefetch(TileFFT<L, tile_batch(L), -1, false, false>::T)) {
         if (tuning().prefetch & 2) return go_extract<L, true>(p, s);
