@@ -298,14 +298,21 @@ template <int L, int B> struct ExtractTiles {           /* tile = block * ny + c
     }
     FDC_HD ExtractStorer<L, B> storer(TilePos t) const { return ExtractStorer<L, B>{p, t.inner, (long)t.outer}; }
 #if defined(__CUDACC__) && !defined(FDC_HOST_EMU)
-    /* thread `tid` < B asks the TMA engine to pull signal tid's slice of tile t into L2 */
+    /* ONE thread asks the TMA engine to pull the tile's slices into L2: the channels of a tile are neighbours in frequency
+     * (ascending f), so their slices are normally one contiguous run of bins and a single instruction covers them; a
+     * sparse group falls back to one request per channel.  (Per-lane requests would be serialised lane by lane: the
+     * instruction takes its operands from uniform registers.) */
     static constexpr bool HAS_L2_PREFETCH = true;
     __device__ __forceinline__ void prefetch_l2(TilePos t, int tid) const
     {
-        if (!p.l2pf || tid >= B) return;
-        int s = t.inner * B + tid;
-        if (s >= p.nsel) return;
-        bulk_prefetch_l2(p.spec + ((long)t.outer * p.spec_stride + p.chans[s].f), (uint32_t)(sizeof(float2) * L));
+        if (tid != 0 || !p.l2pf) return;
+        const int s0 = t.inner * B;
+        const int s1 = (s0 + B <= p.nsel ? s0 + B : p.nsel) - 1;
+        const float2* row = p.spec + (long)t.outer * p.spec_stride;
+        const int f0 = p.chans[s0].f, span = p.chans[s1].f - f0 + L;
+        if (span <= 2 * B * L) bulk_prefetch_l2(row + f0, (uint32_t)(sizeof(float2) * span));
+        else
+            for (int s = s0; s <= s1; s++) bulk_prefetch_l2(row + p.chans[s].f, (uint32_t)(sizeof(float2) * L));
     }
 #endif
 };
@@ -372,9 +379,15 @@ template <int L, int B> struct PackedExtractTiles {     /* tile = group of bpt b
     static constexpr bool HAS_L2_PREFETCH = true;
     __device__ __forceinline__ void prefetch_l2(TilePos t, int tid) const
     {
-        if (!p.l2pf || tid >= B) return;
-        const PackedSignal<L, B> g(p, (long)t.outer * p.bpt, tid);
-        if (g.valid) bulk_prefetch_l2(p.spec + (g.blk * p.spec_stride + p.chans[g.s].f), (uint32_t)(sizeof(float2) * L));
+        if (tid != 0 || !p.l2pf) return;
+        const long first = (long)t.outer * p.bpt;
+        const int f0 = p.chans[0].f, span = p.chans[p.nsel - 1].f - f0 + L;     /* all channels of the launch, ascending f */
+        for (int db = 0; db < p.bpt && first + db < p.nb; db++) {
+            const float2* row = p.spec + (first + db) * p.spec_stride;
+            if (span <= 4 * p.nsel * L) bulk_prefetch_l2(row + f0, (uint32_t)(sizeof(float2) * span));
+            else
+                for (int c = 0; c < p.nsel; c++) bulk_prefetch_l2(row + p.chans[c].f, (uint32_t)(sizeof(float2) * L));
+        }
     }
 #endif
 };
