@@ -764,4 +764,43 @@ int fdc_fft_work(fdc_fft* b, long nvec, const void* in, void* out)
 }
 void fdc_fft_destroy(fdc_fft* b) { if (!b) return; if (b->s) { cudaStreamSynchronize(b->s); cudaStreamDestroy(b->s); } delete b; }
 
+/* ---- decimated power rows for a waterfall display ---- */
+struct fdc_waterfall : DevCtx { int blocklen, width, logmode; DevBuf d_in, d_rows; PinBuf h_rows; cudaStream_t s; };
+
+fdc_waterfall* fdc_waterfall_create(int blocklen, int width, int logmode)
+{
+    if (!require_device()) return 0;
+    if (blocklen < 1 || (blocklen & (blocklen - 1)) || width < 1 || (width & (width - 1))) { fail("waterfall: blocklen and width must be powers of two"); return 0; }
+    fdc_waterfall* b = new fdc_waterfall; b->blocklen = blocklen; b->width = width; b->logmode = logmode != 0; b->s = 0;
+    if (cudaStreamCreateWithFlags(&b->s, cudaStreamNonBlocking) != cudaSuccess) { cuda_fail(cudaGetLastError(), "waterfall create"); delete b; return 0; }
+    return b;
+}
+int fdc_waterfall_work_device(fdc_waterfall* b, int nblocks, const void* d_spectrum, float* out_host, void* stream)
+{
+    OnDevice on_dev(b ? b->dev : -1);
+    if (!b || nblocks < 0 || (nblocks > 0 && (!d_spectrum || !out_host))) return fail("waterfall work: bad arguments");
+    if (nblocks == 0) return 0;
+    cudaStream_t st = stream ? (cudaStream_t)stream : b->s;
+    const size_t bytes = sizeof(float) * (size_t)nblocks * b->width;
+    if (!b->d_rows.reserve(bytes) || !b->h_rows.reserve(bytes)) return cuda_fail(cudaGetLastError(), "waterfall buffers");
+    cudaError_t e = launch_waterfall_rows((const float2*)d_spectrum, b->blocklen, nblocks, b->blocklen, b->width, b->logmode, (float*)b->d_rows.p, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(b->h_rows.p, b->d_rows.p, bytes, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return cuda_fail(e, "waterfall work");
+    memcpy(out_host, b->h_rows.p, bytes);
+    return nblocks;
+}
+int fdc_waterfall_work_host(fdc_waterfall* b, int nblocks, const void* spectrum, float* out_host)
+{
+    OnDevice on_dev(b ? b->dev : -1);
+    if (!b || nblocks < 0 || (nblocks > 0 && !spectrum)) return fail("waterfall work: bad arguments");
+    if (nblocks == 0) return 0;
+    const size_t bytes = sizeof(float2) * (size_t)nblocks * b->blocklen;
+    if (!b->d_in.reserve(bytes)) return cuda_fail(cudaGetLastError(), "waterfall input staging");
+    const cudaError_t e = cudaMemcpyAsync(b->d_in.p, spectrum, bytes, cudaMemcpyHostToDevice, b->s);
+    if (e != cudaSuccess) return cuda_fail(e, "waterfall H2D");
+    return fdc_waterfall_work_device(b, nblocks, b->d_in.p, out_host, 0);
+}
+void fdc_waterfall_destroy(fdc_waterfall* b) { if (!b) return; if (b->s) { cudaStreamSynchronize(b->s); cudaStreamDestroy(b->s); } delete b; }
+
 }  // extern "C"

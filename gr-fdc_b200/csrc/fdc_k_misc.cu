@@ -288,4 +288,55 @@ cudaError_t launch_band_power(const float2* spec, long spec_stride, long nblocks
     return cudaGetLastError();
 }
 
+/* Decimated power rows for a waterfall display (python/WaterfallMsgTagging.py:272-277 reduces every input vector to 1024
+ * columns by a mean; upstream of it a flowgraph has complex_to_mag_squared and, for a dB display, nlog10_ff).  All three on
+ * the device: W columns per block leave the GPU instead of N.  red = N / W bins per column (N >= W) or every bin repeated
+ * rep = W / N times (N < W).  A warp takes 32 consecutive bins at a time, so the reads are coalesced. */
+__global__ void __launch_bounds__(256) k_waterfall_rows(const float2* __restrict__ spec, long spec_stride, long nblocks, int W, int red,
+                                                         int rep, int logmode, float* __restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const long warp = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int cpw = red >= 32 ? 1 : 32 / red;                  /* columns per warp */
+    const int src_w = W / rep;                                 /* distinct columns */
+    const long wpb = (src_w + cpw - 1) / cpw;                  /* warps per block */
+    const long b = warp / wpb;
+    if (b >= nblocks) return;
+    const int c0 = (int)(warp - b * wpb) * cpw;
+    const float2* x = spec + b * spec_stride + (long)c0 * red;
+    float acc = 0.0f;
+    if (red >= 32) {
+        for (int i = lane; i < red; i += 32) {
+            const float2 v = __ldg(x + i);
+            const float pw = v.x * v.x + v.y * v.y;
+            acc += logmode ? 10.0f * log10f(pw) : pw;
+        }
+        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    } else {
+        if (c0 + lane / red < src_w) {
+            const float2 v = __ldg(x + lane);
+            const float pw = v.x * v.x + v.y * v.y;
+            acc = logmode ? 10.0f * log10f(pw) : pw;
+        }
+        for (int o = red >> 1; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    }
+    const int col = c0 + (red >= 32 ? 0 : lane / red);
+    const bool leader = red >= 32 ? lane == 0 : (lane % red) == 0;
+    if (leader && col < src_w) {
+        const float m = acc / (float)red;
+        for (int r = 0; r < rep; r++) out[b * W + (long)col * rep + r] = m;
+    }
+}
+cudaError_t launch_waterfall_rows(const float2* spec, long spec_stride, long nblocks, int N, int W, int logmode, float* out, cudaStream_t s)
+{
+    if (nblocks <= 0) return cudaSuccess;
+    const int red = N >= W ? N / W : 1, rep = N >= W ? 1 : W / N;
+    const int cpw = red >= 32 ? 1 : 32 / red;
+    const long wpb = (W / rep + cpw - 1) / cpw;
+    const long warps = nblocks * wpb;
+    k_waterfall_rows<<<(unsigned)((warps + 7) / 8), 256, 0, s>>>(spec, spec_stride, nblocks, W, red, rep, logmode, out);
+    count_launch();
+    return cudaGetLastError();
+}
+
 }  // namespace fdc

@@ -55,6 +55,7 @@ cudaError_t launch_group_power(const float2* spec, long spec_stride, long nblock
 cudaError_t launch_edges(const float* P, long nblocks, int M, float T, float invT, int guard, int cap,
                          int* counts, float* rise_ratio, int* rise_idx, int* fall_idx, cudaStream_t s);
 /* pwr[b] = sum_{i in [m0, m1)} re(x * conj x), sequential (lib/PowerActivationChannel_impl.cc:289-291) */
+cudaError_t launch_waterfall_rows(const float2* spec, long spec_stride, long nblocks, int N, int W, int logmode, float* out, cudaStream_t s);
 cudaError_t launch_band_power(const float2* spec, long spec_stride, long nblocks, int m0, int m1, float* pwr,
                               cudaStream_t s);
 

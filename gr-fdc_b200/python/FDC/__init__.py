@@ -9,4 +9,6 @@ try:                                                                            
 except ImportError:                                                                # pragma: no cover
     pass
 
+from .waterfall import WaterfallMsgTagging                                         # noqa: F401
+
 RECTANGULAR, HANN, RAMP = 0, 1, 2

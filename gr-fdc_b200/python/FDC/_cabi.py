@@ -77,6 +77,10 @@ SIGNATURES = {
     "fdc_fft_create": (_vp, [_i, _i, _i]),
     "fdc_fft_work": (_i, [_vp, _l, _vp, _vp]),
     "fdc_fft_destroy": (None, [_vp]),
+    "fdc_waterfall_create": (_vp, [_i, _i, _i]),
+    "fdc_waterfall_work_host": (_i, [_vp, _i, _vp, _vp]),
+    "fdc_waterfall_work_device": (_i, [_vp, _i, _vp, _vp, _vp]),
+    "fdc_waterfall_destroy": (None, [_vp]),
     "fdc_pac_create": (_vp, [_i, _f, _f, _i, _f, _i, _i, _i, _i, _cp, _i, _i]),
     "fdc_pac_work_host": (_i, [_vp, _i, _vp]),
     "fdc_pac_work_device": (_i, [_vp, _i, _vp, _vp]),

@@ -149,6 +149,17 @@ fdc_fft* fdc_fft_create(int n, int forward, int shift);
 int fdc_fft_work(fdc_fft* b, long nvec, const void* in, void* out);
 void fdc_fft_destroy(fdc_fft* b);
 
+/* ---- decimated power rows for a waterfall display --------------------------------------------
+ * Replaces complex_to_mag_squared (+ nlog10_ff for a dB display) and the column reduction at the input of the reference's
+ * waterfall consumer (python/WaterfallMsgTagging.py:272-277: every blocklen vector is reduced to 1024 columns by a mean, or
+ * repeated when blocklen < 1024).  Input: spectrum rows (blocklen complex floats each); output: `width` floats per block:
+ * logmode 0 -> mean of |X|^2 over blocklen / width bins, logmode 1 -> mean of 10 log10 |X|^2. */
+typedef struct fdc_waterfall fdc_waterfall;
+fdc_waterfall* fdc_waterfall_create(int blocklen, int width, int logmode);
+int fdc_waterfall_work_host(fdc_waterfall* b, int nblocks, const void* spectrum, float* out_host);
+int fdc_waterfall_work_device(fdc_waterfall* b, int nblocks, const void* d_spectrum, float* out_host, void* stream);
+void fdc_waterfall_destroy(fdc_waterfall* b);
+
 /* ---- activity-gated channels: PDUs ---------------------------------------------------------- */
 /* One published message: the pmt dict of lib/SegmentDetection_impl.cc:446-460,502-515 /
  * lib/PowerActivationChannel_impl.cc:222-232 plus the c32vector payload. */
