@@ -82,6 +82,9 @@ CASES = {
     # narrow channels on long transforms (slices 128 .. 2048 bins): 256 x 512 and 512 x 512 four-step, 32 points per thread
     "narrow131072": (lambda: workloads.ChanConfig("narrow131072", 131072, 4, NARROW, workloads.HANN), 3),
     "narrow262144_r8": (lambda: workloads.ChanConfig("narrow262144", 262144, 8, NARROW, workloads.RAMP), 3),
+    # the largest transforms the forward kernels take: 512 x 1024 and 1024 x 1024 four-step
+    "narrow524288": (lambda: workloads.ChanConfig("narrow524288", 524288, 4, NARROW, workloads.HANN), 3),
+    "narrow1048576_r2": (lambda: workloads.ChanConfig("narrow1048576", 1048576, 2, NARROW, workloads.RECTANGULAR), 3),
 }
 NARROW = [(0.12, 0.001), (0.22, 0.004), (-0.14, 0.0005), (0.0, 0.002), (-0.4991, 0.0003), (0.4993, 0.0003)]
 
