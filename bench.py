@@ -287,6 +287,45 @@ def run_cfg3_sharded(args, rank, world, local):
     return 0
 
 
+def cfg3_cpu_reference(nb, N, R, hop, x, segs, pac, pool, seconds=10.0):
+    """configs[2] on the host cores: the reference's overlap_save + restated fft_vcc on all cores, then the unmodified
+    SegmentDetection x2 and PowerActivationChannel x16 blocks, one thread per block as under GNU Radio's scheduler."""
+    from oracle import fdc_ref as ref
+    ref.set_fft_mode(1)
+    cores = os.cpu_count() or 1
+    chain = ref.Chain(N, R, [], workloads.HANN)
+    rsd = [ref.SegmentDetection(i, N, R, a, b, 10.0, 0.002, 0.2, 128, 1, True, False, "", False, 0) for i, (a, b) in enumerate(segs)]
+    rpc = [ref.PowerActivationChannel(N, f, bw, R, 6.0, 128, 1, True, False, "", 0, i) for i, (f, bw) in enumerate(pac)]
+    t1 = time.perf_counter(); reps = 0
+    while time.perf_counter() - t1 < seconds and reps < 256:
+        _, sp = chain.run(x, nthreads=cores, want_spectrum=True, want_outputs=False)
+        list(pool.map(lambda b: (b.work(sp), b.messages()), rsd + rpc))
+        reps += 1
+    dtc = time.perf_counter() - t1
+    ref.set_fft_mode(0)
+    return {"value": reps * nb * hop / dtc / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "reference",
+            "sample": "%d x %d blocks, reference overlap_save + restated fft_vcc on all cores, then the unmodified SegmentDetection x2 and "
+                      "PowerActivationChannel x16 blocks, one thread per block as under GNU Radio's thread-per-block scheduler, %.1f s" % (reps, nb, dtc)}
+
+
+def run_cfg3_reference(args):
+    """--impl reference --workload cfg3: the CPU arm alone (no GPU needed)"""
+    from concurrent.futures import ThreadPoolExecutor
+    nb = args.blocks or 1024
+    N, R, hop, x, segs, pac = cfg3_stream(nb)
+    pool = ThreadPoolExecutor(max_workers=min(len(segs) + len(pac), os.cpu_count() or 1))
+    t0 = time.perf_counter()
+    cpu = cfg3_cpu_reference(nb, N, R, hop, x, segs, pac, pool, seconds=max(3.0, 3.0 * args.steps))
+    emit({"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
+          "warmup": args.warmup, "ms_per_step": (time.perf_counter() - t0) * 1e3 / max(args.steps, 1), "higher_is_better": True,
+          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+          "config": {"workload": "cfg3_fft16384_r4_activity", "fft": N, "overlap": N // R, "hop": hop, "segments": segs,
+                     "power_activation_channels": len(pac), "blocks_per_step_per_gpu": nb},
+          "cpu_baseline": cpu, "e2e": {"value": cpu["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+          "gpu_launches": 0})
+    return 0
+
+
 def run_cfg3(args, rank, world, local):
     """configs[2]: the activity-gated path.  One step = nb blocks through overlap-save + forward FFT (spectrum stays in device
     memory) + 2 SegmentDetection + 16 PowerActivationChannel blocks.  The state machines of those blocks run on the host,
@@ -337,24 +376,7 @@ def run_cfg3(args, rank, world, local):
     out_bytes = 8.0 * stats["samples"] / K
     peaks, peak_src = measured_peaks()
     alg = (8.0 * nb * hop + out_bytes)
-    cpu = None
-    if not args.no_cpu:
-        from oracle import fdc_ref as ref
-        ref.set_fft_mode(1)
-        cores = os.cpu_count() or 1
-        chain = ref.Chain(N, R, [], workloads.HANN)
-        rsd = [ref.SegmentDetection(i, N, R, a, b, 10.0, 0.002, 0.2, 128, 1, True, False, "", False, 0) for i, (a, b) in enumerate(segs)]
-        rpc = [ref.PowerActivationChannel(N, f, bw, R, 6.0, 128, 1, True, False, "", 0, i) for i, (f, bw) in enumerate(pac)]
-        t1 = time.perf_counter(); reps = 0
-        while time.perf_counter() - t1 < 10.0 and reps < 256:
-            _, sp = chain.run(x, nthreads=cores, want_spectrum=True, want_outputs=False)
-            list(pool.map(lambda b: (b.work(sp), b.messages()), rsd + rpc))
-            reps += 1
-        dtc = time.perf_counter() - t1
-        ref.set_fft_mode(0)
-        cpu = {"value": reps * nb * hop / dtc / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "reference",
-               "sample": "%d x %d blocks, reference overlap_save + restated fft_vcc on all cores, then the unmodified SegmentDetection x2 and "
-                         "PowerActivationChannel x16 blocks, one thread per block as under GNU Radio's thread-per-block scheduler, %.1f s" % (reps, nb, dtc)}
+    cpu = None if args.no_cpu else cfg3_cpu_reference(nb, N, R, hop, x, segs, pac, pool)
     line = {"metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": dt / K * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "cfg3_fft16384_r4_activity", "fft": N, "overlap": N // R, "hop": hop, "segments": segs,
@@ -387,7 +409,9 @@ def main():
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.workload == "cfg3":
-        if world > 1 and args.impl != "reference":
+        if args.impl == "reference":
+            return run_cfg3_reference(args) if rank == 0 else 0
+        if world > 1:
             return run_cfg3_sharded(args, rank, world, local)
         return run_cfg3(args, rank, world, local) if rank == 0 else 0
     cfg = WORKLOADS[args.workload]()
