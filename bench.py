@@ -182,21 +182,37 @@ def run_reference(args, cfg, rank, world):
     return 0
 
 
-def cfg3_stream(nblocks, seed=3, rows=None):
-    """cfg3: FFT 16384, R = 4, 48 bursty DAMA carriers of 16..128 bins on a 256-bin raster in the segments
-    [0.1, 0.45] and [0.55, 0.9], 25 dB SNR; 16 of the carriers are also watched by PowerActivationChannels.  The spectra
-    are drawn per block and turned into a time stream block by block (the overlap-save blocks then see them smeared by the
-    25 % overlap, which is all a throughput measurement needs).  rows = (lo, hi): only the samples of blocks [lo, hi)."""
+# the activity-gated workloads: configs[2] (FFT 16384, 48 carriers, 2 segments, 16 watched channels) and the activity half of
+# configs[4] (FFT 262144, ~3900 narrow DAMA carriers with 10 % duty on a 64-bin raster, one segment over the whole band)
+ACTIVITY = {
+    "cfg3": dict(name="cfg3_fft16384_r4_activity", N=16384, R=4, carriers=48, widths=(16, 32, 64, 128), raster=256, mean_on=24, mean_off=40,
+                 lo=0.1, hi=0.9, segs=[(0.1, 0.45), (0.55, 0.9)], npac=16, minchandist=0.002, blocks=1024, seed=3),
+    "cfg5_activity": dict(name="cfg5_fft262144_r4_activity", N=262144, R=4, carriers=3900, widths=(40,), raster=64, mean_on=4, mean_off=36,
+                          lo=0.02, hi=0.98, segs=[(0.02, 0.98)], npac=0, minchandist=16.0 / 262144, blocks=64, seed=5),
+}
+ACT = ACTIVITY["cfg3"]
+
+
+def sd_args(i, a, b):
+    """SegmentDetection(ID, blocklen, relinvovl, start, stop, thresh dB, minchandist, flank puffer, maxblocks, delay, msg, file, path, threads, verbose)"""
+    return (i, ACT["N"], ACT["R"], a, b, 10.0, ACT["minchandist"], 0.2, 128, 1, True, False, "", False, 0)
+
+
+def cfg3_stream(nblocks, seed=None, rows=None):
+    """Bursty DAMA carriers: the spectra are drawn per block and turned into a time stream block by block (the
+    overlap-save blocks then see them smeared by the 25 % overlap, which is all a throughput measurement needs); the first
+    `npac` carriers are also watched by PowerActivationChannels.  rows = (lo, hi): only the samples of blocks [lo, hi)."""
     import scenarios as sc
-    N, R = 16384, 4
+    N, R = ACT["N"], ACT["R"]
     hop = N - N // R
-    spec, truth = sc.bursty_spectra(N, nblocks, 48, seed=seed, widths=(16, 32, 64, 128), raster=256, mean_on=24, mean_off=40)
+    spec, truth = sc.bursty_spectra(N, nblocks, ACT["carriers"], seed=ACT["seed"] if seed is None else seed, widths=ACT["widths"], raster=ACT["raster"],
+                                    mean_on=ACT["mean_on"], mean_off=ACT["mean_off"], lo=ACT["lo"], hi=ACT["hi"])
     lo, hi = rows if rows is not None else (0, nblocks)
     t = np.fft.ifft(np.fft.ifftshift(spec[lo:hi], axes=1), axis=1).astype(np.complex64) * np.float32(N)
     x = np.ascontiguousarray(t[:, N - hop:]).reshape(-1)
-    starts = sorted(set(tr[0] for tr in truth))[:16]
+    starts = sorted(set(tr[0] for tr in truth))[:ACT["npac"]]
     pac = [((s0 + 32) / float(N), 64.0 / N) for s0 in starts]
-    return N, R, hop, x, [(0.1, 0.45), (0.55, 0.9)], pac
+    return N, R, hop, x, list(ACT["segs"]), pac
 
 
 def run_cfg3_sharded(args, rank, world, local):
@@ -209,7 +225,7 @@ def run_cfg3_sharded(args, rank, world, local):
     import FDC
     from FDC import sharded
     from concurrent.futures import ThreadPoolExecutor
-    nb = args.blocks or 1024
+    nb = args.blocks or ACT["blocks"]
     W = max(args.warmup, 3); K = max(args.steps, 1)
     torch.cuda.set_device(local)
     if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
@@ -222,7 +238,7 @@ def run_cfg3_sharded(args, rank, world, local):
     N, R, hop, x, segs, pac = cfg3_stream(total, rows=(lo, first[rank] + count[rank]))
     nloc = first[rank] + count[rank] - lo
     front = FDC.Channelizer(N, N // R, R, [])
-    sd = [FDC.SegmentDetection(i, N, R, a, b, 10.0, 0.002, 0.2, 128, 1, True, False, "", False, 0) for i, (a, b) in enumerate(segs)]
+    sd = [FDC.SegmentDetection(*sd_args(i, a, b)) for i, (a, b) in enumerate(segs)]
     pc = [FDC.PowerActivationChannel(N, f, bw, R, 6.0, 128, 1, True, False, "", 0, i) for i, (f, bw) in enumerate(pac)]
     pool = ThreadPoolExecutor(max_workers=max(1, min(len(sd) + len(pc), (os.cpu_count() or 1) // world)))
     sink = None
@@ -268,7 +284,7 @@ def run_cfg3_sharded(args, rank, world, local):
         alg = 8.0 * total * hop + 8.0 * stats["samples"] / K
         line = {"metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dt / K * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "cfg3_fft16384_r4_activity", "fft": N, "overlap": N // R, "hop": hop, "segments": segs,
+                "config": {"workload": ACT["name"], "fft": N, "overlap": N // R, "hop": hop, "segments": segs,
                            "power_activation_channels": len(pac), "blocks_per_step_per_gpu": nb, "sharding": "time",
                            "pdus_per_step": stats["pdus"] / K, "burst_samples_per_step": stats["samples"] / K,
                            "sink_phase_ms_per_step": {k: round(v / K * 1e3, 3) for k, v in grp.phase_seconds.items()},
@@ -294,7 +310,7 @@ def cfg3_cpu_reference(nb, N, R, hop, x, segs, pac, pool, seconds=10.0):
     ref.set_fft_mode(1)
     cores = os.cpu_count() or 1
     chain = ref.Chain(N, R, [], workloads.HANN)
-    rsd = [ref.SegmentDetection(i, N, R, a, b, 10.0, 0.002, 0.2, 128, 1, True, False, "", False, 0) for i, (a, b) in enumerate(segs)]
+    rsd = [ref.SegmentDetection(*sd_args(i, a, b)) for i, (a, b) in enumerate(segs)]
     rpc = [ref.PowerActivationChannel(N, f, bw, R, 6.0, 128, 1, True, False, "", 0, i) for i, (f, bw) in enumerate(pac)]
     t1 = time.perf_counter(); reps = 0
     while time.perf_counter() - t1 < seconds and reps < 256:
@@ -311,7 +327,7 @@ def cfg3_cpu_reference(nb, N, R, hop, x, segs, pac, pool, seconds=10.0):
 def run_cfg3_reference(args):
     """--impl reference --workload cfg3: the CPU arm alone (no GPU needed)"""
     from concurrent.futures import ThreadPoolExecutor
-    nb = args.blocks or 1024
+    nb = args.blocks or ACT["blocks"]
     N, R, hop, x, segs, pac = cfg3_stream(nb)
     pool = ThreadPoolExecutor(max_workers=min(len(segs) + len(pac), os.cpu_count() or 1))
     t0 = time.perf_counter()
@@ -319,7 +335,7 @@ def run_cfg3_reference(args):
     emit({"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
           "warmup": args.warmup, "ms_per_step": (time.perf_counter() - t0) * 1e3 / max(args.steps, 1), "higher_is_better": True,
           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-          "config": {"workload": "cfg3_fft16384_r4_activity", "fft": N, "overlap": N // R, "hop": hop, "segments": segs,
+          "config": {"workload": ACT["name"], "fft": N, "overlap": N // R, "hop": hop, "segments": segs,
                      "power_activation_channels": len(pac), "blocks_per_step_per_gpu": nb},
           "cpu_baseline": cpu, "e2e": {"value": cpu["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
           "gpu_launches": 0})
@@ -332,13 +348,13 @@ def run_cfg3(args, rank, world, local):
     so the step is timed on the wall clock with a device synchronise on both sides."""
     import torch
     import FDC
-    nb = args.blocks or 1024
+    nb = args.blocks or ACT["blocks"]
     W = max(args.warmup, 3); K = max(args.steps, 1)
     N, R, hop, x, segs, pac = cfg3_stream(nb)
     torch.cuda.set_device(local)
     L = FDC._cabi.lib(); FDC._cabi.check(L.fdc_set_device(local))
     front = FDC.Channelizer(N, N // R, R, [])
-    sd = [FDC.SegmentDetection(i, N, R, a, b, 10.0, 0.002, 0.2, 128, 1, True, False, "", False, 0) for i, (a, b) in enumerate(segs)]
+    sd = [FDC.SegmentDetection(*sd_args(i, a, b)) for i, (a, b) in enumerate(segs)]
     pc = [FDC.PowerActivationChannel(N, f, bw, R, 6.0, 128, 1, True, False, "", 0, i) for i, (f, bw) in enumerate(pac)]
     d_in = torch.from_numpy(x.view(np.float32).copy()).cuda(local)
     d_spec = torch.empty(nb * N * 2, dtype=torch.float32, device=d_in.device)
@@ -379,7 +395,7 @@ def run_cfg3(args, rank, world, local):
     cpu = None if args.no_cpu else cfg3_cpu_reference(nb, N, R, hop, x, segs, pac, pool)
     line = {"metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": dt / K * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "cfg3_fft16384_r4_activity", "fft": N, "overlap": N // R, "hop": hop, "segments": segs,
+            "config": {"workload": ACT["name"], "fft": N, "overlap": N // R, "hop": hop, "segments": segs,
                        "power_activation_channels": len(pac), "blocks_per_step_per_gpu": nb,
                        "pdus_per_step": stats["pdus"] / K, "burst_samples_per_step": stats["samples"] / K,
                        "timing": "wall clock (host state machines are part of the path), device synchronised on both sides",
@@ -399,7 +415,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS) + ["cfg3"])
+    ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS) + sorted(ACTIVITY))
     ap.add_argument("--blocks", type=int, default=0, help="blocks per step per GPU (default: input >= 256 MiB)")
     ap.add_argument("--chunk", type=int, default=0, help="override blocks per K1->K2 round trip")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -408,7 +424,9 @@ def main():
     claim_stdout()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.workload == "cfg3":
+    if args.workload in ACTIVITY:
+        global ACT
+        ACT = ACTIVITY[args.workload]
         if args.impl == "reference":
             return run_cfg3_reference(args) if rank == 0 else 0
         if world > 1:

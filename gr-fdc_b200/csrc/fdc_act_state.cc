@@ -14,12 +14,18 @@ template <class T> static std::string num2str(T v) { std::ostringstream ss; ss <
 
 std::string current_time_string()
 {
-    /* lib/SegmentDetection_impl.cc:680-694 */
+    /* lib/SegmentDetection_impl.cc:680-694; the text only changes once a second, so it is formatted once a second
+     * (a wideband segment activates hundreds of carriers per block) */
+    static thread_local time_t cached_at = (time_t)-1;
+    static thread_local std::string cached;
     time_t raw; time(&raw);
-    struct tm ti; localtime_r(&raw, &ti);
-    char p[80];
-    strftime(p, sizeof(p), "%Y-%m-%d-%H-%M-%S", &ti);
-    return std::string(p);
+    if (raw != cached_at) {
+        struct tm ti; localtime_r(&raw, &ti);
+        char p[80];
+        strftime(p, sizeof(p), "%Y-%m-%d-%H-%M-%S", &ti);
+        cached = p; cached_at = raw;
+    }
+    return cached;
 }
 
 /* fmod(fmod(x, y) + 1, y) -- lib/SegmentDetection_impl.cc:700-703 */
@@ -138,15 +144,21 @@ void SegmentState::candidates(const EdgeBlock& e, std::deque<std::array<long, 2>
     for (size_t n = 0; n < e.rise.size(); n++) rise.push_back(fipair(e.rise[n].first, (size_t)e.rise[n].second * (size_t)g.D + (size_t)g.start));
     for (size_t n = 0; n < e.fall.size(); n++) fall.push_back(((size_t)e.fall[n] + 1) * (size_t)g.D + (size_t)g.start);
     std::sort(rise.begin(), rise.end(), fipair_desc);
+    /* The reference tests a new candidate against every accepted one (quadratic in the number of carriers; a wideband
+     * segment has hundreds per block).  Accepted candidates are pairwise disjoint -- a new [s, e] is only taken if for every
+     * accepted [a, b] either s >= b or e < a -- so, kept sorted by start, their ends are sorted too and the only one that can
+     * overlap [s, e] (s < b && e >= a) is the one with the largest a <= e.  Same decisions, one binary search each. */
+    static thread_local std::vector<std::array<long, 2> > sorted;
+    sorted.clear();
     for (size_t r = 0; r < rise.size(); r++) {
         const size_t poss_start = rise[r].second;
         std::vector<size_t>::iterator next_end = std::upper_bound(fall.begin(), fall.end(), poss_start);
         if (next_end == fall.end()) continue;
-        bool overlapping = false;
-        for (size_t k = 0; k < poss.size(); k++)
-            if ((long)poss_start < poss[k][1] && (long)*next_end >= poss[k][0]) { overlapping = true; break; }
-        if (overlapping) continue;
-        std::array<long, 2> a = {{(long)poss_start, (long)*next_end}};
+        const std::array<long, 2> a = {{(long)poss_start, (long)*next_end}};
+        std::vector<std::array<long, 2> >::iterator up =
+            std::upper_bound(sorted.begin(), sorted.end(), a[1], [](long e, const std::array<long, 2>& x) { return e < x[0]; });
+        if (up != sorted.begin() && a[0] < (*(up - 1))[1]) continue;          /* overlapping */
+        sorted.insert(std::upper_bound(sorted.begin(), sorted.end(), a[0], [](long v, const std::array<long, 2>& x) { return v < x[0]; }), a);
         poss.push_back(a);
     }
 }
@@ -169,7 +181,7 @@ bool SegmentState::activate(long detect_start, long detect_end, long& uid_counte
     c.ovlskip = (int)(extract_width / relinvovl);
     c.outputsamples = c.extract_width - c.ovlskip;
     c.count = 0; c.phase = 0; c.phaseincrement = (int)(extract_start % relinvovl); c.inactive = -1; c.part = 0;
-    c.msg_ID = current_time_string() + std::string(".DETECTED.") + num2str(seg_id) + std::string(".") + num2str(c.ID);
+    c.msg_ID = current_time_string() + std::string(".DETECTED.") + std::to_string(seg_id) + std::string(".") + std::to_string(c.ID);
     c.uid = uid_counter++; c.ndata = 0;
     active.push_back(c);
     return true;
@@ -182,20 +194,31 @@ void SegmentState::match(std::deque<std::array<long, 2> >& poss, long& uid_count
         for (size_t k = 0; k < active.size(); k++) active[k].inactive += 1;
         return;
     }
+    /* The reference walks, for every active channel in list order, over all remaining candidates and erases the ones that
+     * touch it (pc_start < detect_stop && pc_end >= detect_start); what is left is activated in candidate (strength) order.
+     * Same result without the quadratic walk: the candidates are disjoint, so sorted by start their ends are sorted as well
+     * and the ones touching a channel are a contiguous run found by binary search; "erased" is a flag. */
+    const size_t n = poss.size();
+    static thread_local std::vector<std::array<long, 3> > idx;       /* (start, end, position in poss), by start */
+    static thread_local std::vector<char> dead;
+    idx.resize(n); dead.assign(n, 0);
+    for (size_t i = 0; i < n; i++) { idx[i][0] = poss[i][0]; idx[i][1] = poss[i][1]; idx[i][2] = (long)i; }
+    std::sort(idx.begin(), idx.end(), [](const std::array<long, 3>& a, const std::array<long, 3>& b) { return a[0] < b[0]; });
     for (size_t k = 0; k < active.size(); k++) {
         ActiveChannel& c = active[k];
         bool inactive = true;
-        size_t i = 0;
-        while (i < poss.size()) {
-            const int pc_start = (int)poss[i][0], pc_end = (int)poss[i][1];
-            if (pc_start < c.detect_stop && pc_end >= c.detect_start) {
-                c.inactive = 0; inactive = false;
-                poss.erase(poss.begin() + i);
-            } else i++;
+        /* first candidate (by start) whose end reaches detect_start; (int) casts as in the reference's comparison */
+        size_t lo = 0, hi = n;
+        while (lo < hi) { const size_t mid = (lo + hi) / 2; if ((int)idx[mid][1] >= c.detect_start) hi = mid; else lo = mid + 1; }
+        for (size_t i = lo; i < n && (int)idx[i][0] < c.detect_stop; i++) {
+            if (dead[(size_t)idx[i][2]]) continue;
+            dead[(size_t)idx[i][2]] = 1;
+            c.inactive = 0; inactive = false;
         }
         if (inactive) c.inactive += 1;
     }
-    for (size_t i = 0; i < poss.size(); i++) activate(poss[i][0], poss[i][1], uid_counter);
+    for (size_t i = 0; i < n; i++)
+        if (!dead[i]) activate(poss[i][0], poss[i][1], uid_counter);
 }
 
 void SegmentState::job(ActiveChannel& c, int row, std::vector<ActJob>& jobs, std::vector<ActOp>& ops)
@@ -267,14 +290,17 @@ void SegmentState::block(int row, const EdgeBlock& e, long blockcount, long& uid
         for (size_t k = 0; k < active.size(); k++)
             if (active[k].ndata >= maxblocks) emit_partial(active[k], blockcount, ops);
     /* clear_inactive_channels, lib/SegmentDetection_impl.cc:541-549 */
-    size_t i = 0;
-    while (i < active.size()) {
+    size_t keep = 0;
+    for (size_t i = 0; i < active.size(); i++) {          /* same survivors in the same order, one pass instead of an erase each */
         if (active[i].inactive > delay) {
             ActOp o; o.kind = ActOp::DROP; o.uid = active[i].uid; o.job = -1; o.ntake = 0; o.blocksamples = 0;
             ops.push_back(o);
-            active.erase(active.begin() + i);
-        } else i++;
+        } else {
+            if (keep != i) active[keep] = std::move(active[i]);
+            keep++;
+        }
     }
+    active.resize(keep);
 }
 
 /* ---- PacState ------------------------------------------------------------------------------------- */

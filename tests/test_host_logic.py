@@ -251,6 +251,37 @@ def test_segdet_state_machine_vs_oracle(FDC, ref, maxblocks, delay):
     assert np.array_equal(a.power(), b.power())
 
 
+@pytest.mark.parametrize("kind", ["noise", "crowded"])
+def test_segdet_dense_scenes_vs_oracle(FDC, ref, kind):
+    """hundreds of candidates per block: the candidate overlap test and the candidate/channel matching are done with binary
+    searches here and with nested walks in the reference -- decisions, order of activation and PDUs must not differ"""
+    if kind == "noise":              # D = 1 on pure noise: touching and overlapping candidates everywhere
+        N = 4096
+        rng = np.random.default_rng(9)
+        x = (rng.standard_normal((14, N)) + 1j * rng.standard_normal((14, N))).astype(np.complex64)
+        args = (0, N, 4, 0.02, 0.999, 3.0, 0.0001, 0.1, 2, 0, True, False, "", False, 0)
+        chunks_a, chunks_b = (14,), (5, 9)
+    else:                            # several hundred narrow carriers switching on and off
+        N = 32768
+        x, _ = sc.bursty_spectra(N, 40, 400, seed=77, raster=64, widths=(24, 40), mean_on=3, mean_off=9, lo=0.05, hi=0.95)
+        args = (4, N, 4, 0.05, 0.95, 10.0, 16.0 / N, 0.2, 3, 1, True, False, "", False, 0)
+        chunks_a, chunks_b = (40,), (13, 1, 26)
+    a = ref.SegmentDetection(*args)
+    _feed(a, x.reshape(-1), N, chunks_a)
+    b = FDC.SegmentDetection(*args, _logic=True)
+    st = b.state()
+    P = sc.group_power(x, st["d_start"], st["D"], st["M"])
+    pos = 0
+    for n in chunks_b:
+        b.logic_work(n, P[pos:pos + n]); pos += n
+    ma, mb = a.messages(), b.messages()
+    assert len(ma) > (50 if kind == "noise" else 300)
+    assert [sc.meta_tuple(m) for m in ma] == [sc.meta_tuple(m) for m in mb]
+    assert a.active_channels() == b.active_channels()
+    sa, sb = a.state(), b.state()
+    assert (sa["blockcount"], sa["n_active"], sa["chan_counter"]) == (sb["blockcount"], sb["n_active"], sb["chan_counter"])
+
+
 @pytest.mark.parametrize("threads", [False, True])
 def test_actdet_state_machine_vs_oracle(FDC, ref, threads):
     N = 1024
