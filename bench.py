@@ -247,7 +247,7 @@ def run_cfg3_sharded(args, rank, world, local):
             sink = sharded.PeerSink(0, 0, rank, world, dst=0, nbytes=256 << 20)
         except Exception as exc:        # no peer access on this box: NCCL gather
             sys.stderr.write("peer sink unavailable (%s), using the NCCL gather\n" % exc)
-    grp = sharded.ShardedActivityGroup(sd + pc, rank, world, dst=0, pool=pool, sink=sink)
+    grp = sharded.ShardedActivityGroup(sd + pc, rank, world, dst=0, pool=pool, sink=sink, arrays=True)
     d_in = torch.from_numpy(x.view(np.float32).copy()).cuda(local)
     d_spec = torch.empty(nloc * N * 2, dtype=torch.float32, device=d_in.device)
     own = d_spec.data_ptr() + 8 * N * (first[rank] - lo)
@@ -259,8 +259,8 @@ def run_cfg3_sharded(args, rank, world, local):
         front.sync()
         res = grp.work(total, own, prev)
         if res is not None:
-            for ms in res:
-                stats["pdus"] += len(ms); stats["samples"] += sum(m["nsamples"] for m in ms)
+            for recs, data, offsets in res:
+                stats["pdus"] += int(recs.size); stats["samples"] += int(data.size)
 
     for _ in range(W):
         step()
@@ -367,8 +367,8 @@ def run_cfg3(args, rank, world, local):
 
     def one(b):
         b.work_device(nb, d_spec.data_ptr())
-        ms = b.messages()
-        return len(ms), sum(m["nsamples"] for m in ms)
+        recs, data, offsets = b.messages_arrays(reuse=True)  # every PDU's metadata and samples, without a dict per PDU
+        return recs.size, int(data.size)
 
     def step():
         front.work_device(d_in.data_ptr(), nb, 0, d_spec.data_ptr(), 0)

@@ -39,7 +39,9 @@ template <class K> cudaError_t persistent_grid(K kernel, int threads, size_t sme
     int capacity = 0;
     FDC_CHECK(kernel_capacity((const void*)kernel, threads, smem, &capacity, limit));
     long g = capacity;
-    if (multiple > 1 && g >= multiple) g -= g % multiple;
+    /* `multiple`: the kernel relies on tile (blockIdx + k * grid) % multiple == blockIdx % multiple (a column CTA keeps its
+     * four-step twiddle slice).  With fewer resident CTAs than that the grid is oversubscribed: a second wave, same result. */
+    if (multiple > 1) g = g >= multiple ? g - g % multiple : multiple;
     if (g > ntiles) g = ntiles;
     if (g < 1) g = 1;
     *grid = (unsigned)g;

@@ -114,29 +114,44 @@ class _MsgBlock(_SyncBlock):
             for m in self.messages():
                 self._handler(m)
 
-    def messages(self, clear=True):
-        """Pending PDUs as dicts.  Two calls for the whole batch (records, then all payloads into one buffer the dicts' `data`
-        arrays are slices of) instead of two per message: a work() call on a busy band publishes hundreds of PDUs."""
+    def messages_arrays(self, clear=True, reuse=False):
+        """Pending PDUs without a Python object per message: (records, data, offsets) -- `records` is a structured array with
+        the PDU keys (id, finalized, part, rel_cfreq, rel_bw, blockstart, blockend, vectorstart, vectorend, nsamples), `data`
+        all payloads back to back (complex64) and message k's samples are data[offsets[k]:offsets[k + 1]].  Two C calls for the
+        whole batch; a busy wideband segment publishes thousands of PDUs per work() call.  reuse=True returns `data` as a view
+        of a buffer that the block keeps and overwrites at the next call (no fresh pages for tens of MB per call)."""
         n = self._fn("msg_count")(self._h)
         if n <= 0:
-            return []
-        recs = (_cabi.msg * n)()
-        check(self._fn("msg_get_all")(self._h, recs), self._name)
-        r = np.frombuffer(recs, dtype=_MSG_DTYPE)
-        have = (r["data"] != 0) & (r["nsamples"] > 0)               # host-logic contexts report counts only (data == NULL)
-        sizes = np.where(have, r["nsamples"], 0)
-        buf = np.empty(int(sizes.sum()), dtype=np.complex64)
-        if buf.size:
-            check(self._fn("msg_copy_data")(self._h, _ptr(buf)), self._name)
-        cut = np.concatenate([[0], np.cumsum(sizes)]).tolist()
-        ids = [bytes(x).split(b"\0", 1)[0].decode() for x in r["id"].tolist()]
-        cols = [r[k].tolist() for k in ("finalized", "part", "rel_bw", "rel_cfreq", "blockstart", "blockend", "vectorstart", "vectorend", "nsamples")]
-        res = [dict(ID=ids[k], finalized=bool(fin), part=part, rel_bw=bw, rel_cfreq=cf, blockstart=b0, blockend=b1, vectorstart=v0, vectorend=v1,
-                    nsamples=ns, data=buf[cut[k]:cut[k + 1]])
-               for k, (fin, part, bw, cf, b0, b1, v0, v1, ns) in enumerate(zip(*cols))]
+            return np.zeros(0, dtype=_MSG_DTYPE), np.zeros(0, dtype=np.complex64), np.zeros(1, dtype=np.int64)
+        recs = np.zeros(n, dtype=_MSG_DTYPE)
+        check(self._fn("msg_get_all")(self._h, recs.ctypes.data_as(C.c_void_p)), self._name)
+        have = (recs["data"] != 0) & (recs["nsamples"] > 0)         # host-logic contexts report counts only (data == NULL)
+        offsets = np.concatenate([[0], np.cumsum(np.where(have, recs["nsamples"], 0))]).astype(np.int64)
+        total = int(offsets[-1])
+        if reuse:
+            buf = getattr(self, "_msgbuf", None)
+            if buf is None or buf.size < total:
+                buf = self._msgbuf = np.empty(max(total, 1 << 16), dtype=np.complex64)
+            data = buf[:total]
+        else:
+            data = np.empty(total, dtype=np.complex64)
+        if data.size:
+            check(self._fn("msg_copy_data")(self._h, _ptr(data)), self._name)
         if clear:
             self._fn("msg_clear")(self._h)
-        return res
+        return recs, data, offsets
+
+    def messages(self, clear=True):
+        """Pending PDUs as dicts (the `data` arrays are slices of one buffer)."""
+        r, buf, cut = self.messages_arrays(clear)
+        if r.size == 0:
+            return []
+        cut = cut.tolist()
+        ids = [bytes(x).split(b"\0", 1)[0].decode() for x in r["id"].tolist()]
+        cols = [r[k].tolist() for k in ("finalized", "part", "rel_bw", "rel_cfreq", "blockstart", "blockend", "vectorstart", "vectorend", "nsamples")]
+        return [dict(ID=ids[k], finalized=bool(fin), part=part, rel_bw=bw, rel_cfreq=cf, blockstart=b0, blockend=b1, vectorstart=v0, vectorend=v1,
+                     nsamples=ns, data=buf[cut[k]:cut[k + 1]])
+                for k, (fin, part, bw, cf, b0, b1, v0, v1, ns) in enumerate(zip(*cols))]
 
 
 _MSG_DTYPE = np.dtype({"names": ["id", "finalized", "part", "rel_cfreq", "rel_bw", "blockstart", "blockend", "vectorstart", "vectorend", "nsamples", "data"],

@@ -159,12 +159,13 @@ class ShardedActivityGroup(object):
     blocks' samples per call.  `pool` (a concurrent.futures executor) runs the per-block local phases concurrently, as
     GNU Radio's thread-per-block scheduler would; the collectives are issued from the calling thread only."""
 
-    def __init__(self, blocks, rank, world, dst=0, group=None, pool=None, sink=None):
+    def __init__(self, blocks, rank, world, dst=0, group=None, pool=None, sink=None, arrays=False):
         """sink: a PeerSink(nbytes=...) made by all ranks -- the extract kernels then store the burst samples straight into
         the sink rank's buffer (peer memory over NVLink) and the gather of the samples is a barrier; calls whose samples do
         not fit the buffer fall back to the NCCL gather."""
         self.blocks, self.rank, self.world, self.dst, self.group = list(blocks), int(rank), int(world), int(dst), group
         self.sink = sink
+        self.arrays = bool(arrays)          # work() returns messages_arrays(reuse=True) per block instead of lists of dicts
         self._map = pool.map if pool is not None else (lambda f, it: list(map(f, it)))
         self.phase_seconds = {}                 # wall clock per phase, accumulated over calls (for measurements)
 
@@ -199,7 +200,7 @@ class ShardedActivityGroup(object):
             if me == self.dst:
                 def assemble_dev(i):
                     self.blocks[i].shard_assemble_device(self.sink.ptr + 8 * base[i], total[i], stream)
-                    return self.blocks[i].messages()
+                    return self.blocks[i].messages_arrays(reuse=True) if self.arrays else self.blocks[i].messages()
                 out = list(self._map(assemble_dev, idx))
             else:
                 for b in self.blocks:
@@ -219,7 +220,7 @@ class ShardedActivityGroup(object):
                 def assemble(i):
                     b = self.blocks[i]
                     b.shard_assemble(np.concatenate([parts[r][cuts[r][i]:cuts[r][i + 1]] for r in range(self.world)]))
-                    return b.messages()
+                    return b.messages_arrays(reuse=True) if self.arrays else b.messages()
                 out = list(self._map(assemble, idx))
         t.append(time.perf_counter())
         for k, name in enumerate(("measure", "allgather_records", "decide", "extract", "gather_samples", "assemble")):
