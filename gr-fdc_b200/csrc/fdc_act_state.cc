@@ -130,7 +130,9 @@ SegGeometry actdet_geometry(int blocklen, float v0, float v1, int D)
 
 /* ---- SegmentState --------------------------------------------------------------------------------- */
 typedef std::pair<float, size_t> fipair;
-static bool fipair_desc(fipair& a, fipair& b) { return a.first > b.first; }
+/* the reference's comparison (descending ratio) as an inlinable functor: std::sort's sequence of comparisons and moves depends
+ * only on the comparison results, so the order among equal ratios stays the reference's */
+struct fipair_desc_t { bool operator()(const fipair& a, const fipair& b) const { return a.first > b.first; } };
 
 void SegmentState::candidates(const EdgeBlock& e, std::deque<std::array<long, 2> >& poss) const
 {
@@ -143,24 +145,33 @@ void SegmentState::candidates(const EdgeBlock& e, std::deque<std::array<long, 2>
     rise.clear(); fall.clear();
     for (size_t n = 0; n < e.rise.size(); n++) rise.push_back(fipair(e.rise[n].first, (size_t)e.rise[n].second * (size_t)g.D + (size_t)g.start));
     for (size_t n = 0; n < e.fall.size(); n++) fall.push_back(((size_t)e.fall[n] + 1) * (size_t)g.D + (size_t)g.start);
-    std::sort(rise.begin(), rise.end(), fipair_desc);
+    std::sort(rise.begin(), rise.end(), fipair_desc_t());
     /* The reference tests a new candidate against every accepted one (quadratic in the number of carriers; a wideband
-     * segment has hundreds per block).  Accepted candidates are pairwise disjoint -- a new [s, e] is only taken if for every
-     * accepted [a, b] either s >= b or e < a -- so, kept sorted by start, their ends are sorted too and the only one that can
-     * overlap [s, e] (s < b && e >= a) is the one with the largest a <= e.  Same decisions, one binary search each. */
-    static thread_local std::vector<std::array<long, 2> > sorted;
-    sorted.clear();
+     * segment has hundreds per block).  Candidates start and end on the detection raster (bin = start + D * p), so the
+     * accepted ones are recorded in an occupancy map over the raster points: candidate [a, b) owns the points a .. b-1.  The
+     * reference's test "s < b && e >= a" for some accepted [a, b) is "one of the points s .. e is owned" -- same decisions,
+     * a few loads per candidate.  match() uses the same map. */
+    std::vector<int>& own = owner_map();
+    own.assign((size_t)g.M + 2, 0);
     for (size_t r = 0; r < rise.size(); r++) {
         const size_t poss_start = rise[r].second;
         std::vector<size_t>::iterator next_end = std::upper_bound(fall.begin(), fall.end(), poss_start);
         if (next_end == fall.end()) continue;
+        const long ps = ((long)poss_start - g.start) / g.D, pe = ((long)*next_end - g.start) / g.D;
+        bool overlapping = false;
+        for (long q = ps; q <= pe; q++)
+            if (own[(size_t)q]) { overlapping = true; break; }
+        if (overlapping) continue;
         const std::array<long, 2> a = {{(long)poss_start, (long)*next_end}};
-        std::vector<std::array<long, 2> >::iterator up =
-            std::upper_bound(sorted.begin(), sorted.end(), a[1], [](long e, const std::array<long, 2>& x) { return e < x[0]; });
-        if (up != sorted.begin() && a[0] < (*(up - 1))[1]) continue;          /* overlapping */
-        sorted.insert(std::upper_bound(sorted.begin(), sorted.end(), a[0], [](long v, const std::array<long, 2>& x) { return v < x[0]; }), a);
         poss.push_back(a);
+        for (long q = ps; q < pe; q++) own[(size_t)q] = (int)poss.size();       /* 1 + position in poss */
     }
+}
+
+std::vector<int>& SegmentState::owner_map()
+{
+    static thread_local std::vector<int> own;       /* scratch shared by candidates() and match() of one block() call */
+    return own;
 }
 
 bool SegmentState::activate(long detect_start, long detect_end, long& uid_counter)
@@ -196,23 +207,22 @@ void SegmentState::match(std::deque<std::array<long, 2> >& poss, long& uid_count
     }
     /* The reference walks, for every active channel in list order, over all remaining candidates and erases the ones that
      * touch it (pc_start < detect_stop && pc_end >= detect_start); what is left is activated in candidate (strength) order.
-     * Same result without the quadratic walk: the candidates are disjoint, so sorted by start their ends are sorted as well
-     * and the ones touching a channel are a contiguous run found by binary search; "erased" is a flag. */
+     * With the occupancy map of candidates(): candidate [a, b) touches the channel iff it owns one of the raster points
+     * detect_start - 1 .. detect_stop - 1 (in raster units); "erased" is a flag.  Same result, no quadratic walk. */
     const size_t n = poss.size();
-    static thread_local std::vector<std::array<long, 3> > idx;       /* (start, end, position in poss), by start */
+    const std::vector<int>& own = owner_map();
     static thread_local std::vector<char> dead;
-    idx.resize(n); dead.assign(n, 0);
-    for (size_t i = 0; i < n; i++) { idx[i][0] = poss[i][0]; idx[i][1] = poss[i][1]; idx[i][2] = (long)i; }
-    std::sort(idx.begin(), idx.end(), [](const std::array<long, 3>& a, const std::array<long, 3>& b) { return a[0] < b[0]; });
+    dead.assign(n, 0);
     for (size_t k = 0; k < active.size(); k++) {
         ActiveChannel& c = active[k];
         bool inactive = true;
-        /* first candidate (by start) whose end reaches detect_start; (int) casts as in the reference's comparison */
-        size_t lo = 0, hi = n;
-        while (lo < hi) { const size_t mid = (lo + hi) / 2; if ((int)idx[mid][1] >= c.detect_start) hi = mid; else lo = mid + 1; }
-        for (size_t i = lo; i < n && (int)idx[i][0] < c.detect_stop; i++) {
-            if (dead[(size_t)idx[i][2]]) continue;
-            dead[(size_t)idx[i][2]] = 1;
+        long lo = ((long)c.detect_start - g.start) / g.D - 1, hi = ((long)c.detect_stop - g.start) / g.D - 1;
+        if (lo < 0) lo = 0;
+        if (hi > g.M) hi = g.M;
+        for (long q = lo; q <= hi; q++) {
+            const int id = own[(size_t)q];
+            if (!id || dead[(size_t)id - 1]) continue;
+            dead[(size_t)id - 1] = 1;
             c.inactive = 0; inactive = false;
         }
         if (inactive) c.inactive += 1;

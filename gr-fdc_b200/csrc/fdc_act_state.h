@@ -97,6 +97,7 @@ public:
     void block(int row, const EdgeBlock& e, long blockcount, long& uid_counter, std::vector<ActJob>& jobs, std::vector<ActOp>& ops);
 private:
     void candidates(const EdgeBlock& e, std::deque<std::array<long, 2> >& poss) const;
+    static std::vector<int>& owner_map();
     void match(std::deque<std::array<long, 2> >& poss, long& uid_counter);
     bool activate(long detect_start, long detect_end, long& uid_counter);
     void job(ActiveChannel& c, int row, std::vector<ActJob>& jobs, std::vector<ActOp>& ops);
