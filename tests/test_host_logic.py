@@ -282,6 +282,39 @@ def test_segdet_dense_scenes_vs_oracle(FDC, ref, kind):
     assert (sa["blockcount"], sa["n_active"], sa["chan_counter"]) == (sb["blockcount"], sb["n_active"], sb["chan_counter"])
 
 
+@pytest.mark.parametrize("seed", range(16))
+def test_segdet_randomised_differential(FDC, ref, seed):
+    """random geometry (raster 1 .. 32 bins), thresholds, deactivation delays, partial-emission limits and scenes (noise only,
+    sparse, crowded, touching carriers): the bookkeeping must make the reference's decisions, in its order"""
+    rng = np.random.default_rng(1000 + seed)
+    N = int(rng.choice([1024, 2048, 4096]))
+    nblocks = int(rng.integers(12, 40))
+    kind = seed % 4
+    if kind == 0:
+        x = (rng.standard_normal((nblocks, N)) + 1j * rng.standard_normal((nblocks, N))).astype(np.complex64)
+    else:
+        ncar = [0, 6, 40, 90][kind]
+        w = [(16, 32, 64), (16, 32, 64), (8, 16), (4, 8)][kind]
+        x, _ = sc.bursty_spectra(N, nblocks, ncar, seed=seed, widths=w, raster=[0, 0, 32, 8][kind] or None, mean_on=int(rng.integers(2, 9)),
+                                 mean_off=int(rng.integers(3, 12)), snr_db=float(rng.choice([12.0, 25.0])), lo=0.05, hi=0.95)
+    thresh = float(rng.choice([3.0, 6.0, 10.0]))
+    mcd = float(rng.choice([1.0, 2.0, 4.0, 8.0, 16.0, 32.0])) / N
+    args = (seed, N, int(rng.choice([2, 4, 8])), 0.05, 0.95, thresh, mcd, float(rng.choice([0.0, 0.2, 0.5])), int(rng.integers(-1, 6)),
+            int(rng.integers(0, 4)), True, False, "", False, 0)
+    a = ref.SegmentDetection(*args)
+    _feed(a, x.reshape(-1), N, (nblocks,))
+    b = FDC.SegmentDetection(*args, _logic=True)
+    st = b.state()
+    assert {k: st[k] for k in ("d_start", "d_stop", "D", "M")} == {k: a.state()[k] for k in ("d_start", "d_stop", "D", "M")}
+    P = sc.group_power(x, st["d_start"], st["D"], st["M"])
+    cut = int(rng.integers(1, nblocks))
+    b.logic_work(cut, P[:cut]); b.logic_work(nblocks - cut, P[cut:])
+    assert [sc.meta_tuple(m) for m in a.messages()] == [sc.meta_tuple(m) for m in b.messages()]
+    assert a.active_channels() == b.active_channels()
+    sa, sb = a.state(), b.state()
+    assert (sa["blockcount"], sa["n_active"], sa["chan_counter"]) == (sb["blockcount"], sb["n_active"], sb["chan_counter"])
+
+
 @pytest.mark.parametrize("threads", [False, True])
 def test_actdet_state_machine_vs_oracle(FDC, ref, threads):
     N = 1024
