@@ -360,13 +360,25 @@ struct SegDetect {
         char* h = (char*)e.h_misc.p;
         int* h_cnt = (int*)h; float* h_rr = (float*)(h_cnt + 2 * (size_t)n); int* h_ri = (int*)(h_rr + (size_t)n * cap); int* h_fi = h_ri + (size_t)n * cap;
         float* h_last = (float*)(h_fi + (size_t)n * cap);
+        /* counts first, then only the used columns of the [block][cap] edge lists (a quiet band has a handful of edges per block:
+         * kilobytes instead of 12 * cap bytes per block) */
         if (ce == cudaSuccess) ce = cudaMemcpyAsync(h_cnt, e.d_cnt.p, sizeof(int) * 2 * (size_t)n, cudaMemcpyDeviceToHost, st);
-        if (ce == cudaSuccess) ce = cudaMemcpyAsync(h_rr, e.d_rr.p, sizeof(float) * (size_t)n * cap, cudaMemcpyDeviceToHost, st);
-        if (ce == cudaSuccess) ce = cudaMemcpyAsync(h_ri, e.d_ri.p, sizeof(int) * (size_t)n * cap, cudaMemcpyDeviceToHost, st);
-        if (ce == cudaSuccess) ce = cudaMemcpyAsync(h_fi, e.d_fi.p, sizeof(int) * (size_t)n * cap, cudaMemcpyDeviceToHost, st);
         if (ce == cudaSuccess) ce = cudaMemcpyAsync(h_last, (const float*)e.d_P.p + (size_t)(n - 1) * M, sizeof(float) * (size_t)M, cudaMemcpyDeviceToHost, st);
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
         if (ce != cudaSuccess) return cuda_fail(ce, "detection kernels");
+        int used = 0;
+        for (int b = 0; b < n; b++) {
+            const int nr = h_cnt[2 * b], nf = h_cnt[2 * b + 1];
+            if (nr <= cap && nf <= cap) used = std::max(used, std::max(nr, nf));
+        }
+        if (used > 0) {
+            const size_t pitch = sizeof(float) * (size_t)cap, width = sizeof(float) * (size_t)used;
+            ce = cudaMemcpy2DAsync(h_rr, pitch, e.d_rr.p, pitch, width, (size_t)n, cudaMemcpyDeviceToHost, st);
+            if (ce == cudaSuccess) ce = cudaMemcpy2DAsync(h_ri, pitch, e.d_ri.p, pitch, width, (size_t)n, cudaMemcpyDeviceToHost, st);
+            if (ce == cudaSuccess) ce = cudaMemcpy2DAsync(h_fi, pitch, e.d_fi.p, pitch, width, (size_t)n, cudaMemcpyDeviceToHost, st);
+            if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+            if (ce != cudaSuccess) return cuda_fail(ce, "edge list D2H");
+        }
         memcpy(last_power.data(), h_last, sizeof(float) * (size_t)M);
         std::vector<float> row;
         for (int b = 0; b < n; b++) {
