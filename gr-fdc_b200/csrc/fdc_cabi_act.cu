@@ -9,6 +9,8 @@
 #include <algorithm>
 #include <cfloat>
 #include <cstdio>
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <iostream>
 #include <map>
@@ -37,6 +39,14 @@ static void init_logfile(int verbose, const std::string& logfile)
     if (!f) std::cerr << "Logfile not writable: " << logfile << std::endl;
     else { fwrite("\n", 1, 1, f); fclose(f); }
 }
+
+/* FDC_ACT_TIMING=1: wall-clock share of the phases of a work() call on stderr (measurement aid) */
+static bool act_timing() { static const bool on = getenv("FDC_ACT_TIMING") && atoi(getenv("FDC_ACT_TIMING")) > 0; return on; }
+struct PhaseClock {
+    std::chrono::steady_clock::time_point t0; double ms[4]; int k;
+    PhaseClock() : t0(std::chrono::steady_clock::now()), k(0) { ms[0] = ms[1] = ms[2] = ms[3] = 0; }
+    void lap() { const std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now(); if (k < 4) ms[k++] = std::chrono::duration<double, std::milli>(t - t0).count(); t0 = t; }
+};
 
 /* device side shared by the three blocks */
 struct ActEngine {
@@ -575,11 +585,21 @@ int fdc_segdet_work_device(fdc_segdet* b, int n, const void* d_in, void* stream)
     cudaStream_t st = stream ? (cudaStream_t)stream : b->e.s;
     const float2* rows = (const float2*)d_in;
     std::vector<EdgeBlock> edges;
+    PhaseClock pc;
     if (b->det.run(b->e, rows, n, b->st.g, b->thresh, 0, 0, edges, st)) return -1;
+    pc.lap();
     std::vector<ActJob> jobs; std::vector<ActOp> ops;
     jobs.reserve((size_t)n * 16 + 16); ops.reserve((size_t)n * 18 + 16);     /* no reallocation (and op copies) while the blocks are walked */
     for (int i = 0; i < n; i++) { b->st.block(i, edges[(size_t)i], b->blockcount, b->e.uid_counter, jobs, ops); b->blockcount++; }
-    if (b->e.finish(rows, jobs, ops, st)) return -1;
+    pc.lap();
+    std::vector<long> dst; long total = 0;
+    if (b->e.extract(rows, 0, jobs, 0, jobs.size(), 0, dst, &total, st)) return -1;
+    pc.lap();
+    b->e.replay((const cfloat*)b->e.h_out.p, dst, jobs, ops);
+    pc.lap();
+    if (act_timing())
+        fprintf(stderr, "SegmentDetection %d blocks: measure %.3f ms, bookkeeping %.3f ms, extract %.3f ms (%zu jobs, %ld samples), replay %.3f ms (%zu msgs)\n",
+                n, pc.ms[0], pc.ms[1], pc.ms[2], jobs.size(), total, pc.ms[3], b->e.msgs.size());
     if (b->e.save_hist(rows, n, st)) return -1;
     return n;
 }
