@@ -4,7 +4,6 @@ NumPy.  The oracle for this piece is unpinned (the reference widget needs PyQt4 
 import numpy as np
 import pytest
 
-import scenarios as sc
 
 
 def _drive(FDC, wf_or, blocklen, dec, scheme, loginput, height, chunks, rng, use_power=True):

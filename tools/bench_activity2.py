@@ -4,7 +4,7 @@ import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "gr-fdc_b200", "python"), os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
-import numpy as np
+
 import FDC
 import scenarios as sc
 N, R = 16384, 4
