@@ -18,22 +18,11 @@ namespace fdc {
 
 /* a * W4^1 : forward -j, backward +j */
 template <int DIR> FDC_HD float2 rot4(float2 a) { return DIR > 0 ? make_float2(a.y, -a.x) : make_float2(-a.y, a.x); }
-/* a * (c -/+ j s) */
-template <int DIR> FDC_HD float2 mulc(float2 a, float c, float s)
-{
-    return DIR > 0 ? make_float2(a.x * c + a.y * s, a.y * c - a.x * s) : make_float2(a.x * c - a.y * s, a.y * c + a.x * s);
-}
-/* a * W8^1, a * W8^3 */
-template <int DIR> FDC_HD float2 rot8_1(float2 a)
-{
-    return DIR > 0 ? make_float2((a.x + a.y) * FDC_SQRT1_2, (a.y - a.x) * FDC_SQRT1_2)
-                   : make_float2((a.x - a.y) * FDC_SQRT1_2, (a.x + a.y) * FDC_SQRT1_2);
-}
-template <int DIR> FDC_HD float2 rot8_3(float2 a)
-{
-    return DIR > 0 ? make_float2((a.y - a.x) * FDC_SQRT1_2, -(a.x + a.y) * FDC_SQRT1_2)
-                   : make_float2(-(a.x + a.y) * FDC_SQRT1_2, (a.x - a.y) * FDC_SQRT1_2);
-}
+/* a * (c -/+ j s): a * c + rot4(a) * s */
+template <int DIR> FDC_HD float2 mulc(float2 a, float c, float s) { return caxpy(rot4<DIR>(a), s, cscale(a, c)); }
+/* a * W8^1 = (a + rot4(a)) / sqrt 2,  a * W8^3 = (rot4(a) - a) / sqrt 2 */
+template <int DIR> FDC_HD float2 rot8_1(float2 a) { return cscale(cadd(a, rot4<DIR>(a)), FDC_SQRT1_2); }
+template <int DIR> FDC_HD float2 rot8_3(float2 a) { return cscale(csub(rot4<DIR>(a), a), FDC_SQRT1_2); }
 
 template <int DIR> FDC_HD void dft2(float2& x0, float2& x1)
 {

@@ -371,7 +371,8 @@ int fdc_chan_work_device_slab(fdc_chan* c, const void* d_in_v, long nblocks, voi
     if (c->prof || nblocks <= nh + c->chunk_blocks / 2) nw = 1;
     cudaStream_t wk[fdc_chan::NWORK];
     for (int i = 0; i < fdc_chan::NWORK; i++) wk[i] = nw == 1 ? s : c->ws[i];
-    const long ring = std::min(nblocks, c->chunk_blocks);
+    /* the staged head (nh blocks, one chunk) must fit the ring as well: nh > chunk_blocks with overlap above 50 % and small chunks */
+    const long ring = std::max(std::min(nblocks, c->chunk_blocks), nh);
     const bool l2pin = tuning().l2_persist_mb > 0 && !d_spectrum && c->big;
     float2* ring_spec[fdc_chan::NWORK]; float2* ring_mid[fdc_chan::NWORK];
     for (int i = 0; i < nw; i++) {

@@ -74,7 +74,7 @@ template <int N, int B> struct FwdStorer {
     template <int R, int NS> FDC_HD void put(const Ctx& row, int t, float2 v) const
     {
         /* fft_vcc shift=True for a forward transform: out[0:N/2] = Y[N/2:N], out[N/2:N] = Y[0:N/2] */
-        if (row) row[(t ^ (R / 2)) * NS] = make_float2(v.x * p.scale, v.y * p.scale);
+        if (row) row[(t ^ (R / 2)) * NS] = cscale(v, p.scale);
     }
 };
 template <int N, int B> struct FwdTiles {
@@ -169,7 +169,7 @@ template <int N1, int N2, int B> struct RowStorer {
     template <int R, int NS> FDC_HD void put(const Ctx& c, int t, float2 v) const
     {
         /* k = k1 + N1 (o + t NS); k ^ (N/2) flips bit log2(N2/2) of k2, i.e. t -> t ^ (R/2) */
-        c[(long)N1 * NS * (t ^ (R / 2))] = make_float2(v.x * p.scale, v.y * p.scale);
+        c[(long)N1 * NS * (t ^ (R / 2))] = cscale(v, p.scale);
     }
 };
 template <int N1, int N2, int B> struct RowTiles {      /* tile = blk * (N1/B) + row tile */
@@ -254,7 +254,7 @@ template <int L, int B> struct ExtractStorer {
     FDC_HD bool variant(const Ctx& c) const { return c.gain == 1.0f; }
     template <int R, int NS, bool UNIT> FDC_HD void put(const Ctx& c, int t, float2 v) const
     {
-        if (t * NS >= c.skip) c.dst[t * NS] = UNIT ? v : make_float2(v.x * c.gain, v.y * c.gain);
+        if (t * NS >= c.skip) c.dst[t * NS] = UNIT ? v : cscale(v, c.gain);
     }
 };
 /* The same extract fed from a shared-memory stage [signal][l] that the TMA engine fills one tile ahead
@@ -311,8 +311,10 @@ template <int L, int B> struct ExtractTiles {           /* tile = block * ny + c
         const float2* row = p.spec + (long)t.outer * p.spec_stride;
         const int f0 = p.chans[s0].f, span = p.chans[s1].f - f0 + L;
         if (span <= 2 * B * L) bulk_prefetch_l2(row + f0, (uint32_t)(sizeof(float2) * span));
-        else
+        else {
+#pragma unroll 1
             for (int s = s0; s <= s1; s++) bulk_prefetch_l2(row + p.chans[s].f, (uint32_t)(sizeof(float2) * L));
+        }
     }
 #endif
 };
@@ -367,7 +369,7 @@ template <int L, int B> struct PackedExtractStorer {
     FDC_HD bool variant(const Ctx& c) const { return c.gain == 1.0f; }
     template <int R, int NS, bool UNIT> FDC_HD void put(const Ctx& c, int t, float2 v) const
     {
-        if (t * NS >= c.skip) c.dst[t * NS] = UNIT ? v : make_float2(v.x * c.gain, v.y * c.gain);
+        if (t * NS >= c.skip) c.dst[t * NS] = UNIT ? v : cscale(v, c.gain);
     }
 };
 template <int L, int B> struct PackedExtractTiles {     /* tile = group of bpt blocks */
@@ -382,11 +384,14 @@ template <int L, int B> struct PackedExtractTiles {     /* tile = group of bpt b
         if (tid != 0 || !p.l2pf) return;
         const long first = (long)t.outer * p.bpt;
         const int f0 = p.chans[0].f, span = p.chans[p.nsel - 1].f - f0 + L;     /* all channels of the launch, ascending f */
+#pragma unroll 1
         for (int db = 0; db < p.bpt && first + db < p.nb; db++) {
             const float2* row = p.spec + (first + db) * p.spec_stride;
             if (span <= 4 * p.nsel * L) bulk_prefetch_l2(row + f0, (uint32_t)(sizeof(float2) * span));
-            else
+            else {
+#pragma unroll 1
                 for (int c = 0; c < p.nsel; c++) bulk_prefetch_l2(row + p.chans[c].f, (uint32_t)(sizeof(float2) * L));
+            }
         }
     }
 #endif

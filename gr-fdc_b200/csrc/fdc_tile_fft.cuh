@@ -202,8 +202,7 @@ struct TileFFT {
                 for (int t = 1; t < PS::R; t++) {
                     const float2 w = TWS ? twp[(t - 1) * PS::NS] : fdc_ldg(twp + (t - 1) * PS::NS);
                     const float2 a = v[u * PS::R + t];
-                    v[u * PS::R + t] = DIR > 0 ? make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x)
-                                               : make_float2(a.x * w.x + a.y * w.y, a.y * w.x - a.x * w.y);
+                    v[u * PS::R + t] = DIR > 0 ? cmul(a, w) : cmulc(a, w);
                 }
             }
             Bfly<PS::R, DIR>::run(v + u * PS::R);

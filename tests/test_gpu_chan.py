@@ -79,6 +79,8 @@ CASES = {
     "cfg2": (workloads.cfg2, 6),
     "example32768": (lambda: workloads.cfg_example(32768, 4, workloads.HANN), 5),
     "cfg4": (workloads.cfg4, 4),
+    # BASELINE configs[4], throughput reading: FFT 262144 (512 x 512 four-step), 4096 channels of 128 bins in one launch
+    "cfg5_fixed": (workloads.cfg5_fixed, 3),
     # narrow channels on long transforms (slices 128 .. 2048 bins): 256 x 512 and 512 x 512 four-step, 32 points per thread
     "narrow131072": (lambda: workloads.ChanConfig("narrow131072", 131072, 4, NARROW, workloads.HANN), 3),
     "narrow262144_r8": (lambda: workloads.ChanConfig("narrow262144", 262144, 8, NARROW, workloads.RAMP), 3),
@@ -94,6 +96,12 @@ def test_chain_matches_reference(FDC, ref, case):
     mk, nblocks = CASES[case]
     cfg = mk()
     x = workloads.tones_input(cfg, nblocks * cfg.hop, seed=11) + workloads.noise_input(nblocks * cfg.hop, 12) * np.float32(0.05)
+    if cfg.nchan > 1024:
+        # tones_input puts a tone into every 64th channel only; the other 4032 channels of cfg5 would carry nothing but the 26 dB
+        # weaker noise, and a per-channel RELATIVE error there measures the fp32 rounding noise the strong tones spread over all
+        # 262144 bins (2e-5 of such a channel, for any fp32 transform) instead of the channel's own arithmetic.  "All channels
+        # active" (BASELINE configs[4]): full-scale noise in every channel plus the tones.
+        x = (workloads.noise_input(nblocks * cfg.hop, 12) + np.float32(0.25) * workloads.tones_input(cfg, nblocks * cfg.hop, seed=11)).astype(np.complex64)
     want, wspec = make_ref_chain(ref, cfg).run(x, nthreads=8, want_spectrum=True)
     g = make_gpu_chain(FDC, cfg)
     # two calls with different sizes: history and phase counters must carry over
@@ -109,6 +117,37 @@ def test_chain_matches_reference(FDC, ref, case):
         worst = max(worst, rel_l2(got, want[i]))
     assert worst < TOL, worst
     assert g.blockcount == nblocks
+
+
+@pytest.mark.parametrize("case,nblocks,chunk,splits", [
+    ("cfg4", 9, 2, (9,)),                 # 1-block head + 4 chunks of 2 over the 3 worker streams, rings reused
+    ("cfg4", 10, 3, (4, 6)),              # two calls: history and phase carried on the device
+    ("cfg2", 25, 4, (25,)),               # single-kernel forward transform, 7 chunks
+    ("cfg4_ovl50", 7, 1, (7,)),           # chunk of one block with a one-block head
+])
+def test_multichunk_device_path_matches_reference(FDC, ref, case, nblocks, chunk, splits):
+    """the path bench.py times (fdc_chan_work_device: chunks alternating over the worker streams, per-stream mid / spectrum
+    rings reused from chunk to chunk) against the compiled reference blocks, not only against itself"""
+    import torch
+    cfg = workloads.ChanConfig("cfg4_ovl50", 65536, 2, workloads.cfg4().user_channels[::16], workloads.RAMP) if case == "cfg4_ovl50" \
+        else getattr(workloads, case)()
+    x = workloads.tones_input(cfg, nblocks * cfg.hop, seed=17) + workloads.noise_input(nblocks * cfg.hop, 18) * np.float32(0.05)
+    want, _ = make_ref_chain(ref, cfg).run(x, nthreads=8)
+    g = make_gpu_chain(FDC, cfg)
+    g.chunk_blocks = chunk
+    d_in = torch.from_numpy(x.view(np.float32).copy()).cuda()
+    got = [[] for _ in range(cfg.nchan)]
+    pos = 0
+    for nb in splits:
+        d_out = torch.empty(nb * cfg.out_per_block * 2, dtype=torch.float32, device="cuda")
+        g.work_device(d_in.data_ptr() + 8 * pos * cfg.hop, nb, d_out.data_ptr(), 0, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        a = d_out.cpu().numpy().view(np.complex64)
+        for i, (off, ln) in enumerate(g.out_slices(nb)):
+            got[i].append(a[off:off + ln].copy())
+        pos += nb
+    worst = max(rel_l2(np.concatenate(got[i]), want[i]) for i in range(cfg.nchan))
+    assert worst < TOL, worst
 
 
 def test_device_path_equals_host_path(FDC):
