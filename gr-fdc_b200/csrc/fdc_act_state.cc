@@ -1,6 +1,7 @@
 /* fdc_act_state.cc -- see fdc_act_state.h.  Compile with -ffp-contract=off: the geometry below is compared
  * integer for integer with the reference, and its float/double mix follows the reference expression by expression. */
 #include "fdc_act_state.h"
+#include <cstdio>
 #include <algorithm>
 #include <cmath>
 #include <ctime>
@@ -181,6 +182,14 @@ bool SegmentState::activate(long detect_start, long detect_end, long& uid_counte
     const long extract_mid = detect_start + detect_width / 2;
     const long extract_width = nextpow2_shift((double)(long)ceil((double)detect_width * (1.0 + 2.0 * flank)));
     if (extract_width > blocklen) return false;         /* the reference logs to cerr and skips the carrier */
+    if (extract_width > max_extract_width) {
+        if (!warned_wide) {
+            fprintf(stderr, "fdc_b200 segment %d: carrier [%ld, %ld) needs a %ld-bin slice, wider than the %ld bins the extract kernel transforms; "
+                            "carriers this wide are skipped (the reference would extract them)\n", seg_id, detect_start, detect_end, extract_width, max_extract_width);
+            warned_wide = true;
+        }
+        return false;
+    }
     long extract_start = extract_mid - extract_width / 2, extract_end = extract_mid + extract_width / 2;
     if (extract_start < 0) { extract_start = 0; extract_end = extract_width; }
     if (extract_end > blocklen) { extract_end = blocklen; extract_start = blocklen - extract_width; }

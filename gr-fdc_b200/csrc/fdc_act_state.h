@@ -90,9 +90,15 @@ public:
     long chan_counter;
     const std::vector<long>* win_offsets;
     std::string path; bool fileoutput; bool verbose; bool msg_output;
+    /* widest slice the extract kernel transforms (one CTA: 16384 points).  The reference extracts any width up to blocklen
+     * (lib/SegmentDetection_impl.cc:290-309); a carrier that would need more is refused HERE, before any state is touched, and
+     * reported once -- it is never half activated (a work() call that fails in the extract after the bookkeeping has
+     * advanced would leave the channel active and fail every later call) */
+    long max_extract_width; bool warned_wide;
 
     SegmentState() : seg_id(0), blocklen(0), relinvovl(1), maxblocks(-1), delay(0), flank(0.0), emit_inside_loop(false),
-                     chan_counter(0), win_offsets(0), fileoutput(false), verbose(false), msg_output(true) {}
+                     chan_counter(0), win_offsets(0), fileoutput(false), verbose(false), msg_output(true),
+                     max_extract_width(16384), warned_wide(false) {}
     /* detection + bookkeeping of one block; `blockcount` is the reference's counter value during this block */
     void block(int row, const EdgeBlock& e, long blockcount, long& uid_counter, std::vector<ActJob>& jobs, std::vector<ActOp>& ops);
 private:

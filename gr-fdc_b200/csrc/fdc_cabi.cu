@@ -3,6 +3,7 @@
 #include "fdc_cabi_internal.h"
 #include <algorithm>
 #include <cstring>
+#include <cstdlib>
 #include <cmath>
 #include <map>
 #include <string>
@@ -173,7 +174,7 @@ static int chan_enqueue_chunk(fdc_chan* c, const float2* d_in, long nb, float2* 
     } else {
         BigParams p; p.in = d_in; p.mid = d_mid; p.spec = d_spec; p.tw4 = c->tw4;
         p.nblocks = nb; p.hop = c->hop; p.ovl = c->ovl; p.scale = 1.0f / (float)c->N;
-        e = launch_fwd_big(p, c->N, s);
+        e = (tuning().fused && fwd_cluster_supported(c->N)) ? launch_fwd_cluster(p, c->N, s) : launch_fwd_big(p, c->N, s);
     }
     if (e != cudaSuccess) return cuda_fail(e, "forward FFT launch");
     if (c->prof) cudaEventRecord(c->ev(), s);

@@ -20,18 +20,27 @@ namespace {
 [[noreturn]] void rethrow() { throw std::invalid_argument(fdc_last_error()); }
 
 /* the pmt pair of lib/SegmentDetection_impl.cc:446-460 / lib/PowerActivationChannel_impl.cc:222-232, keys in the
- * reference's insertion order */
+ * reference's insertion order: PowerActivationChannel adds rel_cfreq before rel_bw (:226-227), SegmentDetection and
+ * activity_detection_channelizer_vcm rel_bw before rel_cfreq (:454-455).  A GNU Radio 3.7 pmt dict is an association list,
+ * so the order shows in printed and serialised PDUs.  PowerActivationChannel messages are the ones without
+ * vectorstart / vectorend. */
 pmt::pmt_t to_pdu(const fdc_msg& m)
 {
+    const bool pac = m.vectorstart < 0;
     pmt::pmt_t d = pmt::make_dict();
     d = pmt::dict_add(d, pmt::intern("ID"), pmt::intern(m.id));
     d = pmt::dict_add(d, pmt::intern("finalized"), pmt::from_bool(m.finalized != 0));
     if (m.part >= 0) d = pmt::dict_add(d, pmt::intern("part"), pmt::from_long(m.part));
-    d = pmt::dict_add(d, pmt::intern("rel_bw"), pmt::from_double(m.rel_bw));
-    d = pmt::dict_add(d, pmt::intern("rel_cfreq"), pmt::from_double(m.rel_cfreq));
+    if (pac) {
+        d = pmt::dict_add(d, pmt::intern("rel_cfreq"), pmt::from_double(m.rel_cfreq));
+        d = pmt::dict_add(d, pmt::intern("rel_bw"), pmt::from_double(m.rel_bw));
+    } else {
+        d = pmt::dict_add(d, pmt::intern("rel_bw"), pmt::from_double(m.rel_bw));
+        d = pmt::dict_add(d, pmt::intern("rel_cfreq"), pmt::from_double(m.rel_cfreq));
+    }
     d = pmt::dict_add(d, pmt::intern("blockstart"), pmt::from_long(m.blockstart));
     d = pmt::dict_add(d, pmt::intern("blockend"), pmt::from_long(m.blockend));
-    if (m.vectorstart >= 0) {
+    if (!pac) {
         d = pmt::dict_add(d, pmt::intern("vectorstart"), pmt::from_long(m.vectorstart));
         d = pmt::dict_add(d, pmt::intern("vectorend"), pmt::from_long(m.vectorend));
     }

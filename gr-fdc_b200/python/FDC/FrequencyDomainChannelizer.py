@@ -35,6 +35,33 @@ def nextpow2(k):
     return 2 ** int(np.ceil(np.log2(k)))
 
 
+def frequency_conversions(freqmode, fs, centerfrequency):
+    """(mode, get_freq, set_freq, get_bw, set_bw) of the hier block: user frequencies / bandwidths to and from the block's own
+    normalisation (0 .. 1 over the fft-shifted band), python/FrequencyDomainChannelizer.py:70-91; pinned by
+    tests/golden/freqmodes.json (the reference's own lines, executed)."""
+    get_freq = lambda f: (f + 0.5) % 1.0
+    set_freq = lambda f: f - 0.5
+    get_bw = lambda bw: bw % 1.0
+    set_bw = lambda bw: bw
+    if freqmode == FREQMODE.normalized or freqmode == 'normalized':
+        mode = FREQMODE.normalized
+    elif freqmode == FREQMODE.basebandfs or freqmode == 'basebandfs':
+        mode = FREQMODE.basebandfs
+        get_freq = lambda f: (f / fs + 0.5) % 1.0
+        set_freq = lambda f: (f - 0.5) * fs
+        get_bw = lambda bw: (bw / fs) % 1.0
+        set_bw = lambda bw: bw * fs
+    elif freqmode == FREQMODE.centerfreqfs or freqmode == 'centerfreqfs':
+        mode = FREQMODE.centerfreqfs
+        get_freq = lambda f: ((f - centerfrequency) / fs + 0.5) % 1.0
+        set_freq = lambda f: (f - 0.5) * fs + centerfrequency
+        get_bw = lambda bw: (bw / fs) % 1.0
+        set_bw = lambda bw: bw * fs
+    else:
+        raise ValueError('Unknown Frequency mode. Exiting...')
+    return mode, get_freq, set_freq, get_bw, set_bw
+
+
 class FrequencyDomainChannelizer(object):
     def __init__(self, inptype, inpveclen, blocksize, relinvovl,
                  throughput_channels,
@@ -54,26 +81,7 @@ class FrequencyDomainChannelizer(object):
         self.debug = bool(debug)
 
         # frequency conversion lambdas, python/FrequencyDomainChannelizer.py:70-91
-        self.get_freq = lambda f: (f + 0.5) % 1.0
-        self.set_freq = lambda f: f - 0.5
-        self.get_bw = lambda bw: bw % 1.0
-        self.set_bw = lambda bw: bw
-        if freqmode == FREQMODE.normalized or freqmode == 'normalized':
-            self.freqmode = FREQMODE.normalized
-        elif freqmode == FREQMODE.basebandfs or freqmode == 'basebandfs':
-            self.freqmode = FREQMODE.basebandfs
-            self.get_freq = lambda f: (f / fs + 0.5) % 1.0
-            self.set_freq = lambda f: (f - 0.5) * fs
-            self.get_bw = lambda bw: (bw / fs) % 1.0
-            self.set_bw = lambda bw: bw * fs
-        elif freqmode == FREQMODE.centerfreqfs or freqmode == 'centerfreqfs':
-            self.freqmode = FREQMODE.centerfreqfs
-            self.get_freq = lambda f: ((f - centerfrequency) / fs + 0.5) % 1.0
-            self.set_freq = lambda f: (f - 0.5) * fs + centerfrequency
-            self.get_bw = lambda bw: (bw / fs) % 1.0
-            self.set_bw = lambda bw: bw * fs
-        else:
-            raise ValueError('Unknown Frequency mode. Exiting...')
+        self.freqmode, self.get_freq, self.set_freq, self.get_bw, self.set_bw = frequency_conversions(freqmode, fs, centerfrequency)
 
         self.throughput_channels = self._parse(throughput_channels, self.get_channel,
                                                'Throughput channels are invalid. Exiting...',

@@ -39,6 +39,7 @@ def lib():
         L.ref_msg_clear.argtypes = [vp]
         L.ref_msg_meta.restype = i; L.ref_msg_meta.argtypes = [vp, i, vp, i, vp, vp]
         L.ref_msg_data.restype = i; L.ref_msg_data.argtypes = [vp, i, vp]
+        L.ref_msg_keys.restype = i; L.ref_msg_keys.argtypes = [vp, i, vp, i]
         L.ref_psw_tables.argtypes = [vp, vp]; L.ref_psw_state.argtypes = [vp, vp]
         L.ref_pac_state.argtypes = [vp, vp, vp]; L.ref_pac_tables.argtypes = [vp, vp]
         L.ref_segdet_state.argtypes = [vp, vp, vp]; L.ref_segdet_window.argtypes = [vp, i, i, vp]
@@ -100,6 +101,15 @@ class Block:
         return out[: nitems * self.out_itemsize]
 
     # ---- captured PDUs ----
+    def message_keys(self):
+        """dict keys of every captured PDU in the order the block added them"""
+        L = lib(); res = []
+        for k in range(L.ref_msg_count(self.h)):
+            buf = C.create_string_buffer(512)
+            L.ref_msg_keys(self.h, k, buf, 512)
+            res.append(buf.value.decode().split(","))
+        return res
+
     def messages(self, clear=True):
         L = lib(); n = L.ref_msg_count(self.h); res = []
         for k in range(n):

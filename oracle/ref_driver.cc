@@ -59,6 +59,17 @@ extern "C" int ref_msg_meta(gr::sync_block* b, int i, char* id, int idcap, long*
     ints[6] = (long)m->cdr->c32.size();
     return 0;
 }
+/* the dict keys of PDU i in insertion order, comma separated (a GNU Radio 3.7 pmt dict is an association list: the order is
+ * visible to whoever prints or serialises the message) */
+extern "C" int ref_msg_keys(gr::sync_block* b, int i, char* out, int cap)
+{
+    if (i < 0 || i >= (int)b->d_published.size() || cap < 1) return -1;
+    std::string all;
+    const pmt::pmt_t& m = b->d_published[i];
+    for (size_t k = 0; k < m->car->dict.size(); k++) { if (k) all += ","; all += m->car->dict[k].first; }
+    strncpy(out, all.c_str(), cap - 1); out[cap - 1] = 0;
+    return 0;
+}
 extern "C" int ref_msg_data(gr::sync_block* b, int i, float* out)
 {
     if (i < 0 || i >= (int)b->d_published.size()) return -1;

@@ -192,6 +192,50 @@ def test_hier_block_against_reference_flowgraph(FDC, ref):
     compare_messages(ref_msgs, got, ordered=False)
 
 
+@pytest.mark.parametrize("freqmode", ["basebandfs", "centerfreqfs"])
+def test_hier_block_frequency_modes(FDC, ref, freqmode):
+    """the hier block in basebandfs / centerfreqfs mode (python/FrequencyDomainChannelizer.py:70-91,
+    322-345), channel and segment frequencies given in Hz.  Geometry against tests/golden/freqmodes.json (the reference's own
+    lines, executed); samples and PDUs against the reference blocks built from the golden normalised values."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "freqmodes.json")) as fh:
+        case = [c for c in json.load(fh)["cases"] if c["freqmode"] == freqmode and c["blocksize"] == 4096][0]
+    N, R = case["blocksize"], case["relinvovl"]
+    fs, cf = case["fs"], case["centerfrequency"]
+    chans = [tuple(c) for c in case["channels"]]
+    segs = [list(sg) for sg in case["segments"]][:1]
+    blk = FDC.FrequencyDomainChannelizer(8, 1, N, R, chans, chans[:2], 4.0, fs, cf, freqmode, workloads.HANN, True, False, "", True,
+                                         segs, 10.0, 0.01 * fs, 1, 0.2, 0, 1, 8, 8, True)
+    assert [list(p) for p in blk.channel_params] == case["channel_params"]
+    assert blk.throughput_channels == case["normalized_channels"]
+    assert blk.activity_detection_segments == case["normalized_segments"][:1]
+    params = [tuple(p) for p in case["channel_params"]]
+    hop = N - N // R; nblocks = 48
+    rng = np.random.default_rng(5)
+    n = np.arange(nblocks * hop)
+    x = 0.05 * (rng.standard_normal(n.size) + 1j * rng.standard_normal(n.size))
+    for i, (fq, bw) in enumerate(case["normalized_channels"]):   # gated tones at the channel centres (normalised, 0 .. 1 over the shifted band)
+        gate = ((n // hop) % 16 >= 2 * i + 1) & ((n // hop) % 16 < 2 * i + 8)
+        x = x + gate * np.exp(2j * np.pi * (fq - 0.5 + 0.1 * bw) * n)
+    x = x.astype(np.complex64)
+    outs1 = blk.work(x[:20 * hop]); outs2 = blk.work(x[20 * hop:])
+    want, wspec = ref.Chain(N, R, params, workloads.HANN).run(x, nthreads=4, want_spectrum=True)
+    assert rel_l2(np.concatenate([outs1[0].reshape(-1), outs2[0].reshape(-1)]), wspec) < TOL
+    for i in range(len(chans)):
+        assert rel_l2(np.concatenate([outs1[1 + i], outs2[1 + i]]), want[i]) < TOL
+    ref_msgs = []
+    for i, (fq, bw) in enumerate(case["normalized_channels"][:2]):
+        p = ref.PowerActivationChannel(N, fq, bw, R, 4.0, 8, 1, True, False, "", 0, i)
+        p.work(wspec); ref_msgs += p.messages()
+    a, b = case["normalized_segments"][0]
+    s = ref.SegmentDetection(0, N, R, a, b, 10.0, (0.01 * fs / fs) % 1.0, 0.2, 8, 1, True, False, "", True, 0)
+    s.work(wspec); ref_msgs += s.messages()
+    got = blk.messages()
+    assert len(got) == len(ref_msgs) and len(got) > 4
+    compare_messages(ref_msgs, got, ordered=False)
+
+
 def test_hier_block_transformed_input_mode(FDC, ref):
     """inpveclen = blocksize (python/FrequencyDomainChannelizer.py:284-290): the input items are fft-shifted, unnormalised
     spectra; oracle = the reference blocks chained by hand behind the restated multiply_const / inverse fft_vcc stages"""

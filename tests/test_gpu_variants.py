@@ -23,6 +23,7 @@ VARIANTS = {
     "forward_32_points_everywhere": {"FDC_FWD_E32": "2"},
     "four_step_from_4096": {"FDC_FWD_SPLIT": "4096"},
     "one_cta_per_sm": {"FDC_CTAS_PER_SM": "1"},
+    "cluster_fused_forward": {"FDC_FUSED": "1"},
 }
 
 

@@ -108,9 +108,15 @@ def test_activity_blocks_publish_the_same_pdus(ref, grb, which):
         mk = lambda m: m.activity_detection_channelizer_vcm(256, [[0.1, 0.9]], 10.0, 4, 4, True, False, "", False, 0.0625, 1, 0.2, 0)
     a, b = mk(ref), mk(grb)
     ma, mb = [], []
+    ka, kb = [], []
     for lo, hi in chunks:
-        a.work(x[lo:hi]); b.work(x[lo:hi]); ma += a.messages(); mb += b.messages()
+        a.work(x[lo:hi]); b.work(x[lo:hi])
+        ka += a.message_keys(); kb += b.message_keys()
+        ma += a.messages(); mb += b.messages()
     assert [sc.meta_tuple(m) for m in ma] == [sc.meta_tuple(m) for m in mb]
+    # key ORDER of the pmt dicts (PowerActivationChannel: rel_cfreq before rel_bw, the detection blocks the other way round)
+    assert ka == kb and all(k[:2] == ["ID", "finalized"] for k in ka)
+    assert all((k.index("rel_cfreq") < k.index("rel_bw")) == (which == "pac") for k in ka)
     assert len(ma) >= 3
     for p, q in zip(ma, mb):
         if p["data"].size:

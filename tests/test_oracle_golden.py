@@ -105,3 +105,28 @@ def test_live_reference_activity_matches_kats(ref):
     for a, e in ((0, 3), (3, 7), (7, 9), (9, 20)):
         s.work(x[a:e]); msgs += s.messages()
     assert [list(sc.meta_tuple(m)) for m in msgs] == k["segdet_b9"]["msgs"]
+
+
+def test_frequency_modes_against_the_reference_lines():
+    """normalized / basebandfs / centerfreqfs (python/FrequencyDomainChannelizer.py:70-91) and the geometry derived from the
+    converted values (:322-345): tests/golden/freqmodes.json holds what the reference's own source lines return
+    (tests/golden/make_freqmode_golden.py executes them); the mirror's conversions and geometry.py must reproduce it exactly"""
+    import json
+    import geometry
+    from FDC.FrequencyDomainChannelizer import frequency_conversions
+    with open(os.path.join(GOLD, "freqmodes.json")) as fh:
+        cases = json.load(fh)["cases"]
+    assert len(cases) == 9 and {c["freqmode"] for c in cases} == {"normalized", "basebandfs", "centerfreqfs"}
+    for c in cases:
+        mode, get_freq, set_freq, get_bw, set_bw = frequency_conversions(c["freqmode"], c["fs"], c["centerfrequency"])
+        assert mode == c["freqmode_enum"]
+        conv = [[get_freq(f), get_bw(bw)] for f, bw in c["channels"]]
+        assert conv == c["normalized_channels"]                                    # same expressions: bit-identical doubles
+        assert [[get_freq(a), get_freq(b)] for a, b in c["segments"]] == c["normalized_segments"]
+        assert [[set_freq(f), set_bw(bw)] for f, bw in conv] == c["set_freq_bw_of_normalized"]
+        got = [list(geometry.get_opt_channelparams(c["blocksize"], c["relinvovl"], f, bw)) for f, bw in conv]
+        assert got == c["channel_params"], (c["freqmode"], c["blocksize"])
+    # the enum spellings the GRC file passes (grc/FDC_FrequencyDomainChannelizer.xml) and the error of an unknown mode
+    assert frequency_conversions(1, 2.0, 0.0)[0] == 1 and frequency_conversions(2, 2.0, 1.0)[0] == 2
+    with pytest.raises(ValueError, match="Unknown Frequency mode"):
+        frequency_conversions("kHz", 1.0, 0.0)
