@@ -128,18 +128,21 @@ struct fdc_chan {
     DevBuf w_spec[NWORK], w_mid[NWORK], w_ring[NWORK];   /* w_ring: mid | spectrum in one allocation when L2 persistence is on */
     size_t l2_window[NWORK];
     cudaEvent_t ev_start, ev_done[NWORK];
+    cudaEvent_t ev_hist; bool hist_pending; cudaStream_t hist_stream;     /* the history buffer is written asynchronously at the end of a device call */
     /* host path: NSLOT pipelined chunk slots */
     enum { NSLOT = 4 };
     cudaStream_t hs[NSLOT];
     DevBuf h_in[NSLOT], h_out[NSLOT], h_spec[NSLOT], h_mid[NSLOT];
+    PinBuf p_in[NSLOT], p_out[NSLOT];      /* library-owned pinned staging for pageable caller memory */
+    cudaEvent_t h_done[NSLOT];
     long host_chunk;
     /* optional per-kernel timing (fdc_chan_set_profiling): events around K1 and K2 of every chunk */
     bool prof;
     std::vector<cudaEvent_t> prof_ev;      /* triples: before K1, after K1, after K2 */
     std::vector<cudaEvent_t> prof_pool;
-    fdc_chan() : tw4(0), stream(0), ev_start(0), host_chunk(0), prof(false)
+    fdc_chan() : tw4(0), stream(0), ev_start(0), ev_hist(0), hist_pending(false), hist_stream(0), host_chunk(0), prof(false)
     {
-        for (int i = 0; i < NSLOT; i++) hs[i] = 0;
+        for (int i = 0; i < NSLOT; i++) { hs[i] = 0; h_done[i] = 0; }
         for (int i = 0; i < NWORK; i++) { ws[i] = 0; ev_done[i] = 0; l2_window[i] = 0; }
     }
     cudaEvent_t ev()
@@ -163,17 +166,18 @@ static long pick_chunk_blocks(int N)
 
 /* enqueue K1 + K2 for nb blocks; block b reads d_in[b*hop - ovl, b*hop + hop) */
 static int chan_enqueue_chunk(fdc_chan* c, const float2* d_in, long nb, float2* d_spec, float2* d_mid,
-                              float2* d_out, long call_blocks, long call_blk0, long glob_blk0, cudaStream_t s)
+                              float2* d_out, long call_blocks, long call_blk0, long glob_blk0, cudaStream_t s,
+                              const float2* d_hist = 0, long head_blocks = 0)
 {
     cudaError_t e;
     if (c->prof) cudaEventRecord(c->ev(), s);
     if (!c->big) {
         FwdParams p; p.in = d_in; p.spec = d_spec; p.nblocks = nb; p.hop = c->hop; p.ovl = c->ovl; p.N = c->N;
-        p.scale = 1.0f / (float)c->N; p.l2pf = tuning().l2pf ? 1 : 0;
+        p.scale = 1.0f / (float)c->N; p.l2pf = tuning().l2pf ? 1 : 0; p.hist = d_hist; p.head_blocks = d_hist ? head_blocks : 0;
         e = launch_fwd_small(p, s);
     } else {
         BigParams p; p.in = d_in; p.mid = d_mid; p.spec = d_spec; p.tw4 = c->tw4;
-        p.nblocks = nb; p.hop = c->hop; p.ovl = c->ovl; p.scale = 1.0f / (float)c->N;
+        p.nblocks = nb; p.hop = c->hop; p.ovl = c->ovl; p.scale = 1.0f / (float)c->N; p.hist = d_hist; p.head_blocks = d_hist ? head_blocks : 0;
         e = (tuning().fused && fwd_cluster_supported(c->N)) ? launch_fwd_cluster(p, c->N, s) : launch_fwd_big(p, c->N, s);
     }
     if (e != cudaSuccess) return cuda_fail(e, "forward FFT launch");
@@ -265,6 +269,7 @@ fdc_chan* fdc_chan_create(int N, int ovl, int nphase, int nchan, const fdc_chan_
     c->chunk_blocks = pick_chunk_blocks(N);
     bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&c->ev_hist, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < fdc_chan::NWORK && ok; i++)
         ok = cudaStreamCreateWithFlags(&c->ws[i], cudaStreamNonBlocking) == cudaSuccess &&
              cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming) == cudaSuccess;
@@ -291,10 +296,11 @@ void fdc_chan_destroy(fdc_chan* c)
     cudaDeviceSynchronize();
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->ev_start) cudaEventDestroy(c->ev_start);
+    if (c->ev_hist) cudaEventDestroy(c->ev_hist);
     for (int i = 0; i < fdc_chan::NWORK; i++) { if (c->ws[i]) cudaStreamDestroy(c->ws[i]); if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]); }
     for (size_t i = 0; i < c->prof_ev.size(); i++) cudaEventDestroy(c->prof_ev[i]);
     for (size_t i = 0; i < c->prof_pool.size(); i++) cudaEventDestroy(c->prof_pool[i]);
-    for (int i = 0; i < fdc_chan::NSLOT; i++) if (c->hs[i]) cudaStreamDestroy(c->hs[i]);
+    for (int i = 0; i < fdc_chan::NSLOT; i++) { if (c->hs[i]) cudaStreamDestroy(c->hs[i]); if (c->h_done[i]) cudaEventDestroy(c->h_done[i]); }
     delete c;
 }
 int fdc_chan_hop(const fdc_chan* c) { return c ? c->hop : -1; }
@@ -331,7 +337,9 @@ static int chan_save_history(fdc_chan* c, const float2* d_in, long nblocks, cuda
     const long n_new = nblocks * c->hop;
     cudaError_t e;
     if (n_new >= c->ovl) {
-        e = cudaMemcpyAsync(c->d_hist.p, d_in + (n_new - c->ovl), sizeof(float2) * (size_t)c->ovl, cudaMemcpyDeviceToDevice, s);
+        /* into the spare buffer: the kernels of this call read d_hist, and they are ordered before this copy only on `s` */
+        e = cudaMemcpyAsync(c->d_hist2.p, d_in + (n_new - c->ovl), sizeof(float2) * (size_t)c->ovl, cudaMemcpyDeviceToDevice, s);
+        c->d_hist.swap(c->d_hist2);
     } else {
         float2* h = (float2*)c->d_hist.p; float2* h2 = (float2*)c->d_hist2.p;
         e = cudaMemcpyAsync(h2, h + n_new, sizeof(float2) * (size_t)(c->ovl - n_new), cudaMemcpyDeviceToDevice, s);
@@ -357,23 +365,20 @@ int fdc_chan_work_device_slab(fdc_chan* c, const void* d_in_v, long nblocks, voi
     const float2* d_in = (const float2*)d_in_v; float2* d_out = (float2*)d_out_v; float2* d_spectrum = (float2*)d_spectrum_v;
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
     cudaError_t e = cudaSuccess;
-    /* The first nh blocks reach back into the previous call: they are run from a staging copy [history | their samples]
-     * (lib/overlap_save_impl.cc:70-78 keeps the same history); all later blocks read the caller's buffer directly. */
+    /* The first nh blocks reach back into the previous call: their loads take the samples before d_in[0] from the history
+     * buffer (two-segment loaders, fdc_functors.cuh; lib/overlap_save_impl.cc:70-78 keeps the same history).  No staging
+     * copy, no separate launch for them. */
     const long nh = c->ovl ? std::min(nblocks, ((long)c->ovl + c->hop - 1) / c->hop) : 0;
-    if (nh) {
-        if (!c->d_stage.reserve(sizeof(float2) * (size_t)(c->ovl + nh * c->hop))) return cuda_fail(cudaGetLastError(), "history staging");
-        float2* st = (float2*)c->d_stage.p;
-        e = cudaMemcpyAsync(st, c->d_hist.p, sizeof(float2) * (size_t)c->ovl, cudaMemcpyDeviceToDevice, s);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(st + c->ovl, d_in, sizeof(float2) * (size_t)(nh * c->hop), cudaMemcpyDeviceToDevice, s);
-        if (e != cudaSuccess) return cuda_fail(e, "history staging copy");
+    /* the history may still be being written by an earlier call on another stream */
+    if (c->hist_pending && c->hist_stream != s) {
+        if ((e = cudaStreamWaitEvent(s, c->ev_hist, 0)) != cudaSuccess) return cuda_fail(e, "stream wait");
     }
     /* worker streams (profiling serialises everything on the caller's stream so that the per-kernel events are clean) */
     int nw = tuning().streams < 1 ? 1 : (tuning().streams > (int)fdc_chan::NWORK ? (int)fdc_chan::NWORK : tuning().streams);
-    if (c->prof || nblocks <= nh + c->chunk_blocks / 2) nw = 1;
+    if (c->prof || nblocks <= c->chunk_blocks) nw = 1;
     cudaStream_t wk[fdc_chan::NWORK];
     for (int i = 0; i < fdc_chan::NWORK; i++) wk[i] = nw == 1 ? s : c->ws[i];
-    /* the staged head (nh blocks, one chunk) must fit the ring as well: nh > chunk_blocks with overlap above 50 % and small chunks */
-    const long ring = std::max(std::min(nblocks, c->chunk_blocks), nh);
+    const long ring = std::min(nblocks, c->chunk_blocks);
     const bool l2pin = tuning().l2_persist_mb > 0 && !d_spectrum && c->big;
     float2* ring_spec[fdc_chan::NWORK]; float2* ring_mid[fdc_chan::NWORK];
     for (int i = 0; i < nw; i++) {
@@ -404,11 +409,10 @@ int fdc_chan_work_device_slab(fdc_chan* c, const void* d_in_v, long nblocks, voi
     }
     int w = 0;
     for (long b0 = 0; b0 < nblocks; w = (w + 1) % nw) {
-        const bool head = b0 < nh;
-        const long nb = head ? nh : std::min(c->chunk_blocks, nblocks - b0);
-        const float2* in = head ? (const float2*)c->d_stage.p + c->ovl : d_in + b0 * c->hop;
+        const long nb = std::min(c->chunk_blocks, nblocks - b0);
         float2* spec = d_spectrum ? d_spectrum + b0 * c->N : ring_spec[w];
-        if (chan_enqueue_chunk(c, in, nb, spec, ring_mid[w], d_out, slab_blocks, slab_first_block + b0, c->blockcount + b0, wk[w])) return -1;
+        if (chan_enqueue_chunk(c, d_in + b0 * c->hop, nb, spec, ring_mid[w], d_out, slab_blocks, slab_first_block + b0, c->blockcount + b0, wk[w],
+                               (const float2*)c->d_hist.p, std::max(0L, nh - b0))) return -1;
         b0 += nb;
     }
     if (nw > 1) {
@@ -418,6 +422,10 @@ int fdc_chan_work_device_slab(fdc_chan* c, const void* d_in_v, long nblocks, voi
         }
     }
     if (chan_save_history(c, d_in, nblocks, s)) return -1;
+    if (c->ovl) {
+        if ((e = cudaEventRecord(c->ev_hist, s)) != cudaSuccess) return cuda_fail(e, "event record");
+        c->hist_pending = true; c->hist_stream = s;
+    }
     c->blockcount += nblocks;
     return 0;
 }
@@ -531,9 +539,43 @@ int fdc_chan_sync(fdc_chan* c)
     return e == cudaSuccess ? 0 : cuda_fail(e, "fdc_chan_sync");
 }
 
-/* Host buffers in, host buffers out: the call is cut into chunks that are pipelined over NSLOT streams
- * (H2D of chunk i+1 and D2H of chunk i-1 overlap the kernels of chunk i).  Every chunk after the first uploads
- * its own ovl-sample halo from the caller's buffer, so chunks are independent. */
+/* Host buffers in, host buffers out (the GNU Radio work() contract: the scheduler owns the buffers, they are valid only during
+ * the call and they are ordinary pageable memory, lib/overlap_save_impl.cc:62-81).  The call is cut into chunks that are
+ * pipelined over NSLOT slots, each with its own stream, device buffers and -- for pageable caller memory -- a pinned staging
+ * pair owned by the library: worker threads copy the caller's samples into the slot's pinned input while the GPU works on the
+ * previous slots, the DMA engines move pinned <-> device, and the channel rows of a finished slot are copied from its pinned
+ * output into the caller's buffers (copy pool, fdc_host.cc).  Caller memory that is already pinned (fdc_host_alloc or
+ * cudaHostRegister) is used in place.  Every chunk after the first carries its own ovl-sample halo, so chunks are independent;
+ * the first one reads the halo from the history buffer on the device (two-segment loaders). */
+struct HostSlotJob { long b0, nb; bool staged_out; bool busy; };
+
+static bool is_pinned_host(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+/* a finished slot: wait for its D2H and hand the rows to the caller */
+static int host_drain_slot(fdc_chan* c, int slot, HostSlotJob& j, long nblocks, void* const* outs)
+{
+    if (!j.busy) return 0;
+    const cudaError_t e = cudaEventSynchronize(c->h_done[slot]);
+    if (e != cudaSuccess) return cuda_fail(e, "host path: waiting for a slot");
+    if (j.staged_out) {
+        const float2* src = (const float2*)c->p_out[slot].p;
+        for (int i = 0; i < c->nchan; i++) {
+            if (!outs[i]) continue;
+            const long lo = c->chans[i].lout;
+            copy_pool().submit((float2*)outs[i] + j.b0 * lo, src + j.nb * c->chans[i].lout_prefix, sizeof(float2) * (size_t)(j.nb * lo));
+        }
+        copy_pool().wait();
+    }
+    j.busy = false;
+    (void)nblocks;
+    return 0;
+}
+
 int fdc_chan_work_host(fdc_chan* c, const void* in_v, long nblocks, void* const* outs, void* spectrum_v)
 {
     OnDevice on_dev(c ? c->dev : -1);
@@ -546,45 +588,75 @@ int fdc_chan_work_host(fdc_chan* c, const void* in_v, long nblocks, void* const*
     long chunk = ((long)tuning().host_chunk_mb << 20) / ((long)c->hop * (long)sizeof(float2));
     if (chunk < 4) chunk = 4;
     chunk = std::min(nblocks, std::min(chunk, c->chunk_blocks));
+    const bool want_out = outs && c->nchan;
+    const int mode = tuning().host_staging;                 /* 0: never stage, 1: stage pageable memory (default), 2: always stage */
+    const bool stage_in = mode == 2 || (mode == 1 && !is_pinned_host(in));
+    bool stage_out = false;
+    if (want_out) {
+        stage_out = mode == 2;
+        if (mode == 1) for (int i = 0; i < c->nchan && !stage_out; i++) if (outs[i] && !is_pinned_host(outs[i])) stage_out = true;
+    }
     cudaError_t e = cudaSuccess;
     for (int i = 0; i < fdc_chan::NSLOT; i++) {
         if (!c->hs[i] && (e = cudaStreamCreateWithFlags(&c->hs[i], cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "stream");
+        if (!c->h_done[i] && (e = cudaEventCreateWithFlags(&c->h_done[i], cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "event");
         bool ok = c->h_in[i].reserve(sizeof(float2) * (size_t)(c->ovl + chunk * c->hop)) &&
                   c->h_out[i].reserve(sizeof(float2) * (size_t)std::max(1L, chunk * c->lout_total)) &&
                   c->h_spec[i].reserve(sizeof(float2) * (size_t)chunk * c->N) &&
-                  (!c->big || c->h_mid[i].reserve(sizeof(float2) * (size_t)chunk * c->N));
+                  (!c->big || c->h_mid[i].reserve(sizeof(float2) * (size_t)chunk * c->N)) &&
+                  (!stage_in || c->p_in[i].reserve(sizeof(float2) * (size_t)(c->ovl + chunk * c->hop))) &&
+                  (!stage_out || c->p_out[i].reserve(sizeof(float2) * (size_t)std::max(1L, chunk * c->lout_total)));
         if (!ok) return cuda_fail(cudaGetLastError(), "host-path staging buffers");
     }
     /* uniform channel layout in the caller's memory -> one 2-D copy per chunk instead of one per channel */
-    bool uniform = c->nchan > 1 && outs;
+    bool uniform = c->nchan > 1 && want_out && !stage_out;
     if (uniform) {
         for (int i = 0; i < c->nchan && uniform; i++) {
             if (!outs[i] || c->chans[i].lout != c->chans[0].lout) uniform = false;
             else if (i > 0 && (const char*)outs[i] - (const char*)outs[i - 1] != (ptrdiff_t)(sizeof(float2) * nblocks * c->chans[0].lout)) uniform = false;
         }
     }
-    int slot = 0;
+    const long nh = c->ovl ? ((long)c->ovl + c->hop - 1) / c->hop : 0;
+    HostSlotJob jobs[fdc_chan::NSLOT];
+    for (int i = 0; i < fdc_chan::NSLOT; i++) { jobs[i].busy = false; jobs[i].staged_out = false; jobs[i].b0 = jobs[i].nb = 0; }
+    int slot = 0, last_slot = 0;
     for (long b0 = 0; b0 < nblocks; b0 += chunk, slot = (slot + 1) % fdc_chan::NSLOT) {
         const long nb = std::min(chunk, nblocks - b0);
         cudaStream_t s = c->hs[slot];
+        if (host_drain_slot(c, slot, jobs[slot], nblocks, outs)) return -1;         /* the slot's previous chunk */
         float2* d_in = (float2*)c->h_in[slot].p;
-        if (b0 == 0) {
-            if (c->ovl) e = cudaMemcpyAsync(d_in, c->d_hist.p, sizeof(float2) * (size_t)c->ovl, cudaMemcpyDeviceToDevice, s);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(d_in + c->ovl, in, sizeof(float2) * (size_t)(nb * c->hop), cudaMemcpyHostToDevice, s);
-        } else if (b0 * c->hop >= c->ovl) {
-            e = cudaMemcpyAsync(d_in, in + (b0 * c->hop - c->ovl), sizeof(float2) * (size_t)(c->ovl + nb * c->hop), cudaMemcpyHostToDevice, s);
-        } else {
-            /* halo straddles the saved history and this call's first samples (overlap > 50 % only) */
-            const long from_hist = c->ovl - b0 * c->hop;
-            e = cudaMemcpyAsync(d_in, (float2*)c->d_hist.p + (c->ovl - from_hist), sizeof(float2) * (size_t)from_hist, cudaMemcpyDeviceToDevice, s);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(d_in + from_hist, in, sizeof(float2) * (size_t)(b0 * c->hop + nb * c->hop), cudaMemcpyHostToDevice, s);
+        /* samples this chunk uploads: its own hop samples, preceded by as much of the ovl-sample halo as lies inside the caller's
+         * buffer (all of it from the second chunk on when ovl <= chunk * hop); the rest comes from the history buffer */
+        const long first = std::max(0L, b0 * c->hop - c->ovl), count = (b0 + nb) * c->hop - first;
+        const long lead = b0 * c->hop - first;               /* halo samples in front of the chunk's first new sample */
+        float2* d_dst = d_in + (c->ovl - lead);
+        const float2* h_src = in + first;
+        if (stage_in) {
+            copy_pool().submit(c->p_in[slot].p, h_src, sizeof(float2) * (size_t)count);
+            copy_pool().wait();
+            h_src = (const float2*)c->p_in[slot].p;
         }
+        if (b0 < nh && c->hist_pending && (e = cudaStreamWaitEvent(s, c->ev_hist, 0)) != cudaSuccess) return cuda_fail(e, "stream wait");
+        e = cudaMemcpyAsync(d_dst, h_src, sizeof(float2) * (size_t)count, cudaMemcpyHostToDevice, s);
         if (e != cudaSuccess) return cuda_fail(e, "H2D");
-        float2* d_out = (outs && c->nchan) ? (float2*)c->h_out[slot].p : 0;
+        float2* d_out = want_out ? (float2*)c->h_out[slot].p : 0;
+        /* blocks whose window starts before the uploaded samples read the history buffer: only in chunks that begin inside the
+         * first nh blocks of the call; their history is the call's history shifted by the samples already seen */
+        const long head = std::max(0L, nh - b0);
+        if (head > 0 && b0 > 0) {
+            /* overlap above 50 % and a chunk boundary inside the head: the loaders index the history relative to the chunk's
+             * first sample, so the history this chunk sees is [old history | samples before b0] -- assemble it in front of the
+             * uploaded samples instead (rare: ovl > hop and chunk < nh) */
+            const long from_hist = c->ovl - lead;
+            e = cudaMemcpyAsync(d_in, (const float2*)c->d_hist.p + (c->ovl - from_hist), sizeof(float2) * (size_t)from_hist, cudaMemcpyDeviceToDevice, s);
+            if (e != cudaSuccess) return cuda_fail(e, "history copy");
+        }
         if (chan_enqueue_chunk(c, d_in + c->ovl, nb, (float2*)c->h_spec[slot].p, (float2*)c->h_mid[slot].p, d_out, nb, 0,
-                               c->blockcount + b0, s)) return -1;
+                               c->blockcount + b0, s, (b0 == 0) ? (const float2*)c->d_hist.p : 0, (b0 == 0) ? head : 0)) return -1;
         if (d_out) {
-            if (uniform) {
+            if (stage_out) {
+                e = cudaMemcpyAsync(c->p_out[slot].p, d_out, sizeof(float2) * (size_t)(nb * c->lout_total), cudaMemcpyDeviceToHost, s);
+            } else if (uniform) {
                 const size_t lo = (size_t)c->chans[0].lout;
                 e = cudaMemcpy2DAsync((float2*)outs[0] + b0 * lo, sizeof(float2) * nblocks * lo, d_out, sizeof(float2) * nb * lo,
                                       sizeof(float2) * nb * lo, (size_t)c->nchan, cudaMemcpyDeviceToHost, s);
@@ -602,19 +674,26 @@ int fdc_chan_work_host(fdc_chan* c, const void* in_v, long nblocks, void* const*
             e = cudaMemcpyAsync(spectrum + b0 * c->N, c->h_spec[slot].p, sizeof(float2) * (size_t)(nb * c->N), cudaMemcpyDeviceToHost, s);
             if (e != cudaSuccess) return cuda_fail(e, "D2H spectrum");
         }
+        if (b0 + nb >= nblocks && c->ovl) {
+            /* history for the next call = the last ovl samples of [old history | this call's input].  A later chunk holds them in
+             * its device input [halo | samples]; a call of one chunk is the device path's case (short calls slide the history).
+             * Written into the spare buffer and swapped at once: everything enqueued so far has the old pointer. */
+            if (b0 > 0) {
+                e = cudaMemcpyAsync(c->d_hist2.p, d_in + nb * c->hop, sizeof(float2) * (size_t)c->ovl, cudaMemcpyDeviceToDevice, s);
+                if (e != cudaSuccess) return cuda_fail(e, "history save");
+                c->d_hist.swap(c->d_hist2);
+            } else if (chan_save_history(c, d_in + c->ovl, nb, s)) return -1;
+        }
+        if ((e = cudaEventRecord(c->h_done[slot], s)) != cudaSuccess) return cuda_fail(e, "event record");
+        jobs[slot].b0 = b0; jobs[slot].nb = nb; jobs[slot].staged_out = stage_out && d_out; jobs[slot].busy = true;
+        last_slot = slot;
     }
-    /* history for the next call = the last ovl samples of the last chunk's device input [halo | samples]: a device copy on
-     * that chunk's stream into the spare buffer (the first chunk may still be reading the current one), swapped in below */
-    if (c->ovl) {
-        const int last = (slot + fdc_chan::NSLOT - 1) % fdc_chan::NSLOT;
-        const long last_b0 = ((nblocks - 1) / chunk) * chunk, last_nb = nblocks - last_b0;
-        e = cudaMemcpyAsync(c->d_hist2.p, (const float2*)c->h_in[last].p + last_nb * c->hop, sizeof(float2) * (size_t)c->ovl,
-                            cudaMemcpyDeviceToDevice, c->hs[last]);
-        if (e != cudaSuccess) return cuda_fail(e, "history save");
+    /* drain in submission order: oldest first */
+    for (int k = 1; k <= fdc_chan::NSLOT; k++) {
+        const int sl = (last_slot + k) % fdc_chan::NSLOT;
+        if (host_drain_slot(c, sl, jobs[sl], nblocks, outs)) return -1;
     }
-    const int used = (int)std::min((long)fdc_chan::NSLOT, (nblocks + chunk - 1) / chunk);
-    for (int i = 0; i < used; i++) if ((e = cudaStreamSynchronize(c->hs[i])) != cudaSuccess) return cuda_fail(e, "sync");
-    if (c->ovl) c->d_hist.swap(c->d_hist2);
+    c->hist_pending = false;
     c->blockcount += nblocks;
     return 0;
 }

@@ -48,6 +48,10 @@ struct FwdParams {
     int hop, ovl, N;
     float scale;           /* 1/N (a power of two: exact) */
     int l2pf;              /* kernels without a register prefetch: bulk-prefetch the next tile's samples into L2 */
+    /* overlap-save history (lib/overlap_save_impl.cc:70-78): the first head_blocks blocks reach back before in[0]; those
+     * samples are hist[ovl + i] for sample index i < 0 (hist = the last ovl samples of the previous call, zeros at the start).
+     * Tiles that hold such a block take the two-segment loads, all others the plain ones (a tile-uniform branch). */
+    const float2* hist; long head_blocks;
 };
 template <int N, int B> struct FwdLoader {
     typedef const float2* Ctx;
@@ -62,6 +66,13 @@ template <int N, int B> struct FwdLoader {
     }
     template <int R, int STRIDE> FDC_HD float2 fetch(const Ctx& c, int t) const { return fdc_ldg(c + t * STRIDE); }
     template <int R, int STRIDE> FDC_HD float2 finish(const Ctx&, int, float2 raw) const { return raw; }
+    static constexpr bool HAS_HEAD = true;
+    FDC_HD bool is_head() const { return tile * B < p.head_blocks; }
+    template <int R, int STRIDE> FDC_HD float2 fetch_head(const Ctx& c, int t) const
+    {
+        const long i = (c - p.in) + t * STRIDE;            /* sample index relative to in[0] */
+        return i < 0 ? p.hist[p.ovl + i] : fdc_ldg(p.in + i);
+    }
 };
 template <int N, int B> struct FwdStorer {
     typedef float2* Ctx;
@@ -89,6 +100,7 @@ template <int N, int B> struct FwdTiles {
     {
         if (!p.l2pf || tid != 0) return;
         const long blk0 = (long)t.outer * B;
+        if (blk0 < p.head_blocks) return;                  /* the samples before in[0] live in the history buffer */
         const long nb = p.nblocks - blk0 < B ? p.nblocks - blk0 : B;
         if (nb <= 0) return;
         const char* a = reinterpret_cast<const char*>(p.in + (blk0 * p.hop - p.ovl));
@@ -115,6 +127,7 @@ struct BigParams {
     long nblocks;
     int hop, ovl;
     float scale;
+    const float2* hist; long head_blocks;     /* as in FwdParams */
 };
 template <int N1, int N2, int B> struct ColLoader {     /* signal = column n2, element index = n1 */
     typedef const float2* Ctx;
@@ -123,6 +136,13 @@ template <int N1, int N2, int B> struct ColLoader {     /* signal = column n2, e
     FDC_HD Ctx begin(int batch, int j) const { return p.in + (blk * p.hop - p.ovl + (long)N2 * j + (ctile * B + batch)); }
     template <int R, int STRIDE> FDC_HD float2 fetch(const Ctx& c, int t) const { return fdc_ldg(c + (long)t * STRIDE * N2); }
     template <int R, int STRIDE> FDC_HD float2 finish(const Ctx&, int, float2 raw) const { return raw; }
+    static constexpr bool HAS_HEAD = true;
+    FDC_HD bool is_head() const { return blk < p.head_blocks; }
+    template <int R, int STRIDE> FDC_HD float2 fetch_head(const Ctx& c, int t) const
+    {
+        const long i = (c - p.in) + (long)t * STRIDE * N2;
+        return i < 0 ? p.hist[p.ovl + i] : fdc_ldg(p.in + i);
+    }
 };
 /* The four-step twiddles a column CTA needs are the same for every block (it keeps its column tile), so they are
  * copied once into shared memory, laid out [t][butterfly] = exactly the order the last pass consumes them: every

@@ -3,6 +3,13 @@
  * evaluation order because bin indices and table values are compared bit for bit.
  * Compile with -ffp-contract=off. */
 #include "fdc_host.h"
+#include <algorithm>
+#include <condition_variable>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <mutex>
+#include <thread>
 #include <cmath>
 #include <complex>
 #include <stdexcept>
@@ -88,5 +95,81 @@ int nextpow2_int(double v) { return 1 << (int)std::ceil(std::log2(v)); }
 
 /* 10^(dB/10), lib/PowerActivationChannel_impl.cc:377-381, lib/SegmentDetection_impl.cc:84 */
 float db_to_ratio(float db) { return (float)std::pow(10.0, (double)db / 10.0); }
+
+
+/* ---- copy pool ---------------------------------------------------------------------------------- */
+struct CopyPool::Impl {
+    struct Piece { char* d; const char* s; size_t n; };
+    std::vector<std::thread> th;
+    std::mutex m; std::condition_variable cv, idle;
+    std::deque<Piece> q; size_t inflight; bool stop;
+    Impl() : inflight(0), stop(false) {}
+    bool run_one(std::unique_lock<std::mutex>& lk)
+    {
+        if (q.empty()) return false;
+        const Piece p = q.front(); q.pop_front();
+        lk.unlock();
+        memcpy(p.d, p.s, p.n);
+        lk.lock();
+        if (--inflight == 0) idle.notify_all();
+        return true;
+    }
+    void worker()
+    {
+        std::unique_lock<std::mutex> lk(m);
+        while (true) {
+            cv.wait(lk, [&] { return stop || !q.empty(); });
+            if (stop && q.empty()) return;
+            run_one(lk);
+        }
+    }
+};
+CopyPool::CopyPool(int threads) : d(new Impl)
+{
+    for (int i = 0; i < threads; i++) d->th.emplace_back([this] { d->worker(); });
+}
+CopyPool::~CopyPool()
+{
+    { std::lock_guard<std::mutex> g(d->m); d->stop = true; }
+    d->cv.notify_all();
+    for (size_t i = 0; i < d->th.size(); i++) d->th[i].join();
+    delete d;
+}
+int CopyPool::threads() const { return (int)d->th.size(); }
+void CopyPool::submit(void* dst, const void* src, size_t bytes)
+{
+    if (!bytes) return;
+    const size_t piece = 512u << 10;
+    if (d->th.empty() || bytes <= piece / 2) { memcpy(dst, src, bytes); return; }       /* small copies are not worth a hand-over */
+    {
+        std::lock_guard<std::mutex> g(d->m);
+        for (size_t off = 0; off < bytes; off += piece) {
+            Impl::Piece p; p.d = (char*)dst + off; p.s = (const char*)src + off; p.n = std::min(piece, bytes - off);
+            d->q.push_back(p); d->inflight++;
+        }
+    }
+    d->cv.notify_all();
+}
+void CopyPool::wait()
+{
+    std::unique_lock<std::mutex> lk(d->m);
+    while (d->run_one(lk)) {}                               /* the caller copies too */
+    d->idle.wait(lk, [&] { return d->inflight == 0; });
+}
+CopyPool& copy_pool()
+{
+    /* leaked on purpose: worker threads must not be joined from a static destructor at interpreter shutdown */
+    static CopyPool* pool = 0;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        int n = 0;
+        const char* v = getenv("FDC_COPY_THREADS");
+        if (v && *v) n = atoi(v);
+        else { const unsigned hc = std::thread::hardware_concurrency(); n = hc > 4 ? (int)std::min(12u, hc - 2) - 1 : 1; }
+        if (n < 0) n = 0;
+        pool = new CopyPool(n);
+    });
+    return *pool;
+}
 
 }  // namespace fdc

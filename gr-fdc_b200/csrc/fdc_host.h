@@ -10,5 +10,21 @@ void psw_tables(int blocksize, int relinvovl, float passbw, float stopbw, int wi
 void psw_check_args(float passbw, float stopbw);
 int nextpow2_int(double v);
 float db_to_ratio(float db);
+
+/* Copy pool of the host path: a few worker threads that move caller memory <-> the library's pinned staging slots in parallel
+ * (one thread copies 10-15 GB/s, PCIe moves 25 + 50 GB/s).  submit() cuts a copy into pieces, wait() returns when every
+ * submitted piece is done; the calling thread works through the queue as well.  One pool per process. */
+class CopyPool {
+public:
+    explicit CopyPool(int threads);
+    ~CopyPool();
+    void submit(void* dst, const void* src, size_t bytes);
+    void wait();
+    int threads() const;
+private:
+    struct Impl; Impl* d;
+    CopyPool(const CopyPool&); CopyPool& operator=(const CopyPool&);
+};
+CopyPool& copy_pool();
 }
 #endif

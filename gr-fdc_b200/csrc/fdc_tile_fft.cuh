@@ -90,6 +90,10 @@ constexpr int ilog2(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
 template <class S, class = void> struct storer_has_variant { static constexpr bool value = false; };
 template <class S> struct storer_has_variant<S, decltype((void)S::HAS_VARIANT)> { static constexpr bool value = S::HAS_VARIANT; };
 
+/* loaders whose first tiles read through a second segment (the overlap-save history): HAS_HEAD, is_head(), fetch_head() */
+template <class Ld, class = void> struct loader_has_head { static constexpr bool value = false; };
+template <class Ld> struct loader_has_head<Ld, decltype((void)Ld::HAS_HEAD)> { static constexpr bool value = Ld::HAS_HEAD; };
+
 template <int L_, int B_, int DIR, bool LOAD_BF, bool STORE_BF, int E_ = 16>
 struct TileFFT {
     static constexpr int L = L_, B = B_, E = E_;               /* E points per thread (16, or 8 for twice the warps) */
@@ -133,6 +137,18 @@ struct TileFFT {
     template <class Loader> static FDC_HD void fetch(int tid, float2* raw, const Loader& ld)
     {
         typedef Pass<0> PS;
+        if constexpr (loader_has_head<Loader>::value) {
+            if (ld.is_head()) {                             /* tile-uniform: only the first tile(s) of a call */
+#pragma unroll
+                for (int u = 0; u < PS::U; u++) {
+                    int batch, j; PS::map(tid, u, batch, j);
+                    const typename Loader::Ctx c = ld.begin(batch, j);
+#pragma unroll
+                    for (int t = 0; t < PS::R; t++) raw[u * PS::R + t] = ld.template fetch_head<PS::R, PS::NBF>(c, t);
+                }
+                return;
+            }
+        }
 #pragma unroll
         for (int u = 0; u < PS::U; u++) {
             int batch, j; PS::map(tid, u, batch, j);
