@@ -420,6 +420,9 @@ def main():
     ap.add_argument("--chunk", type=int, default=0, help="override blocks per K1->K2 round trip")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-sustained", action="store_true", help="skip the >= 2 s sustained leg")
+    ap.add_argument("--sustain-seconds", type=float, default=2.0)
+    ap.add_argument("--no-readings", action="store_true", help="cfg4 only: skip the second reading of the config (true 75 %% overlap)")
     args = ap.parse_args()
     claim_stdout()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -505,6 +508,28 @@ def main():
     ms = float(t.item())
     value = world * K * nb * cfg.hop / (ms * 1e-3) / 1e6
 
+    # ---- sustained leg: the same step repeated for >= 2 s of device time, clocks sampled inside it (the K-step region above is
+    # a few milliseconds: a burst at boost clocks; this is the number to quote as sustained) ----
+    sustained = None
+    if not args.no_sustained:
+        reps = max(K, int(np.ceil(args.sustain_seconds * 1e3 / max(ms / K, 1e-3))))
+        bracket()
+        ssamp = ClockSampler(local); ssamp.start()
+        s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(reps):
+            step()
+        s1.record()
+        bracket()
+        sms = s0.elapsed_time(s1)
+        ssamp.stop_flag = True; ssamp.join()
+        ts = torch.tensor([sms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        sms = float(ts.item())
+        sustained = {"value": world * reps * nb * cfg.hop / (sms * 1e-3) / 1e6, "unit": "Msamples/s", "steps": reps, "seconds": sms * 1e-3,
+                     "clocks": ssamp.result()}
+
     # ---- per-kernel roofline (separate pass with events around each kernel) ----
     peaks, peak_src = measured_peaks()
     chan.set_profiling(True)
@@ -526,19 +551,25 @@ def main():
     ach = kern[dom]["GBps_algorithmic"]
     kern[dom]["launches"] = int(chunks) * (fwd_kernels if dom == "forward_fft" else len(set(p[1] for p in cfg.params)))
     kern[dom]["avg_launch_ms"] = kern[dom]["ms"] / max(1, kern[dom]["launches"])
-    traffic = None
+    # DRAM traffic of the dominant kernel: dram__bytes_read.sum + dram__bytes_write.sum of one steady-state step captured IN the
+    # pipeline (ncu --cache-control none --replay-mode application, all launches of a step; profiles/README.md), per launch
+    traffic = None; traffic_step = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as fh:
-            tj = json.load(fh).get(cfg.name, {}).get(dom)
-        if tj:                                   # DRAM bytes of one launch = one chunk of blocks (ncu --set full capture, see profiles/)
-            traffic = tj["dram_bytes_per_block"] * min(nb, chan.chunk_blocks)
+            tj = json.load(fh).get(cfg.name, {})
+        if tj.get(dom) and tj.get("blocks_per_step"):
+            traffic_step = {k: tj[k]["dram_bytes_per_step"] * nb / tj["blocks_per_step"] for k in ("forward_fft", "channel_extract") if k in tj}
+            traffic = traffic_step[dom] / max(1, kern[dom]["launches"] / PK)
     path_gbs = value * 1e6 / world * cfg.bytes_per_sample() / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": ach / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": (out_bytes if dom == "channel_extract" else in_bytes) / max(1, int(chunks)),
+                "algorithmic_bytes_per_launch": (out_bytes if dom == "channel_extract" else in_bytes) / max(1, kern[dom]["launches"]),
+                "algorithmic_bytes_per_step": {"forward_fft": in_bytes / PK, "channel_extract": out_bytes / PK, "path": (in_bytes + out_bytes) / PK},
+                "dram_bytes_per_step": traffic_step,
                 "launches_per_step": launches / K, "kernels": kern,
                 "path": {"bytes_per_sample": cfg.bytes_per_sample(), "achieved": path_gbs, "frac": path_gbs / peaks["hbm_gbs"],
+                         "sustained_frac": (sustained["value"] * 1e6 / world * cfg.bytes_per_sample() / 1e9 / peaks["hbm_gbs"]) if sustained else None,
                          "frac_of_8TBps_nominal": path_gbs / 8000.0,
                          "flop_per_sample": cfg.flops_per_sample(), "tflops_fp32": value * 1e6 / world * cfg.flops_per_sample() / 1e12}}
 
@@ -572,7 +603,43 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * EK * nb_e * cfg.hop / float(tt.item()) / 1e6, "unit": "Msamples/s",
                "h2d_bytes_per_step": nbytes_in, "d2h_bytes_per_step": nbytes_out, "steps": EK, "blocks_per_step": nb_e,
-               "api": "fdc_chan_work_host (pinned host in/out, 4-slot H2D/compute/D2H pipeline)", "cpu_affinity": numa}
+               "api": "fdc_chan_work_host (pinned host in/out used in place, 4-slot H2D/compute/D2H pipeline)", "cpu_affinity": numa}
+        # the same call with ordinary pageable buffers (what a GNU Radio scheduler hands to work()): the library stages them through
+        # its own pinned slots with its copy pool
+        x_pg = np.array(xin); o_pg = np.empty(nb_e * cfg.out_per_block * 2, dtype=np.float32)
+        outs_pg = []; off = 0
+        for lo in chan.lout:
+            outs_pg.append(o_pg.ctypes.data + 4 * off); off += 2 * nb_e * lo
+        ptrs_pg = (ctypes.c_void_p * len(outs_pg))(*outs_pg)
+        for _ in range(2):
+            FDC._cabi.check(L.fdc_chan_work_host(chan._h, ctypes.c_void_p(x_pg.ctypes.data), nb_e, ctypes.cast(ptrs_pg, ctypes.c_void_p), None))
+        bracket()
+        t0 = time.perf_counter()
+        for _ in range(EK):
+            FDC._cabi.check(L.fdc_chan_work_host(chan._h, ctypes.c_void_p(x_pg.ctypes.data), nb_e, ctypes.cast(ptrs_pg, ctypes.c_void_p), None))
+        bracket()
+        tp = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        e2e["pageable"] = {"value": world * EK * nb_e * cfg.hop / float(tp.item()) / 1e6, "unit": "Msamples/s",
+                           "api": "fdc_chan_work_host on pageable numpy buffers (staged through library-owned pinned slots, copy pool of %d threads + caller)" % L.fdc_copy_threads()}
+        # ... and with those same buffers page-locked once by the caller (fdc_host_register): DMA in place, no staging
+        reg = L.fdc_host_register(ctypes.c_void_p(x_pg.ctypes.data), x_pg.nbytes) == 0 and L.fdc_host_register(ctypes.c_void_p(o_pg.ctypes.data), o_pg.nbytes) == 0
+        if reg:
+            for _ in range(2):
+                FDC._cabi.check(L.fdc_chan_work_host(chan._h, ctypes.c_void_p(x_pg.ctypes.data), nb_e, ctypes.cast(ptrs_pg, ctypes.c_void_p), None))
+            bracket()
+            t0 = time.perf_counter()
+            for _ in range(EK):
+                FDC._cabi.check(L.fdc_chan_work_host(chan._h, ctypes.c_void_p(x_pg.ctypes.data), nb_e, ctypes.cast(ptrs_pg, ctypes.c_void_p), None))
+            bracket()
+            tr = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+            e2e["registered"] = {"value": world * EK * nb_e * cfg.hop / float(tr.item()) / 1e6, "unit": "Msamples/s",
+                                 "api": "the same pageable buffers after fdc_host_register (page-locked in place once, as a flowgraph would do with its stream buffers)"}
+            L.fdc_host_unregister(ctypes.c_void_p(x_pg.ctypes.data)); L.fdc_host_unregister(ctypes.c_void_p(o_pg.ctypes.data))
+        del x_pg, o_pg
         L.fdc_host_free(h_in); L.fdc_host_free(h_out)
 
     # ---- optional: NCCL gather of the channel outputs to the sink rank ----
@@ -622,6 +689,35 @@ def main():
         except Exception as exc:                          # peer access not available on this box: keep the NCCL number
             gather["fused_peer_store"] = {"unavailable": str(exc)[:200]}
 
+    # ---- the config's other reading (BASELINE configs[3] says "75 % overlap"; the reference can only express overlap 1/R):
+    # a short leg of the true-75 %-overlap workload (hop = N/4: 3x the transforms per input sample, compute bound) in the same line
+    readings = None
+    if args.workload == "cfg4" and not args.no_readings:
+        cfg_b = WORKLOADS["cfg4_ovl75"]()
+        nb_b = blocks_per_step(cfg_b)
+        chan_b = make_gpu_chain(FDC, cfg_b)
+        d_in_b = torch.randn(nb_b * cfg_b.hop * 2, dtype=torch.float32, device=dev, generator=gen)
+        d_out_b = torch.empty(nb_b * cfg_b.out_per_block * 2, dtype=torch.float32, device=dev)
+        for _ in range(3):
+            chan_b.work_device(d_in_b.data_ptr(), nb_b, d_out_b.data_ptr(), 0, stream)
+        bracket()
+        KB = max(5, min(K, 10))
+        b0 = torch.cuda.Event(enable_timing=True); b1 = torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(KB):
+            chan_b.work_device(d_in_b.data_ptr(), nb_b, d_out_b.data_ptr(), 0, stream)
+        b1.record(); bracket()
+        tb = torch.tensor([b0.elapsed_time(b1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        vb = world * KB * nb_b * cfg_b.hop / (float(tb.item()) * 1e-3) / 1e6
+        readings = {"R4_hop_49152 (value; what the reference's hier block can express)": value,
+                    "true_75pct_overlap_hop_16384": {"value": vb, "unit": "Msamples/s", "steps": KB, "blocks_per_step_per_gpu": nb_b,
+                                                     "flop_per_sample": cfg_b.flops_per_sample(),
+                                                     "tflops_fp32": vb * 1e6 / world * cfg_b.flops_per_sample() / 1e12,
+                                                     "hbm_frac": vb * 1e6 / world * cfg_b.bytes_per_sample() / 1e9 / peaks["hbm_gbs"]}}
+        del chan_b, d_in_b, d_out_b
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_reference_run(cfg)
@@ -635,7 +731,9 @@ def main():
                            "chunk_blocks": chan.chunk_blocks, "sharding": "time (contiguous runs of blocks per rank, halo recomputed)",
                            "l2_policy": "inputs larger than L2 (%.0f MB in, %.0f MB out per step)" %
                                         (8e-6 * nb * cfg.hop, 8e-6 * nb * cfg.out_per_block)},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
+                "clocks": clocks, "sustained": sustained, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
+        if readings:
+            line["readings"] = readings
         if gather:
             line["gather"] = gather
         emit(line)

@@ -59,6 +59,19 @@ void* fdc_host_alloc(size_t bytes)
     return p;
 }
 void fdc_host_free(void* p) { if (p) cudaFreeHost(p); }
+int fdc_copy_threads(void) { return copy_pool().threads(); }
+int fdc_host_register(void* p, size_t bytes)
+{
+    if (!require_device()) return -1;
+    if (!p || !bytes) return fail("fdc_host_register: bad arguments");
+    const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterDefault);
+    return e == cudaSuccess ? 0 : cuda_fail(e, "cudaHostRegister");
+}
+int fdc_host_unregister(void* p)
+{
+    const cudaError_t e = cudaHostUnregister(p);
+    return e == cudaSuccess ? 0 : cuda_fail(e, "cudaHostUnregister");
+}
 unsigned long long fdc_launch_count(void) { return launch_count(); }
 void* fdc_dev_alloc(size_t bytes)
 {
@@ -594,7 +607,13 @@ int fdc_chan_work_host(fdc_chan* c, const void* in_v, long nblocks, void* const*
     bool stage_out = false;
     if (want_out) {
         stage_out = mode == 2;
-        if (mode == 1) for (int i = 0; i < c->nchan && !stage_out; i++) if (outs[i] && !is_pinned_host(outs[i])) stage_out = true;
+        /* one driver query per call, not per channel: the first and the last connected output decide (the ports of a block
+         * are allocated the same way) */
+        if (mode == 1) {
+            const void* first_out = 0; const void* last_out = 0;
+            for (int i = 0; i < c->nchan; i++) if (outs[i]) { if (!first_out) first_out = outs[i]; last_out = outs[i]; }
+            stage_out = first_out && (!is_pinned_host(first_out) || (last_out != first_out && !is_pinned_host(last_out)));
+        }
     }
     cudaError_t e = cudaSuccess;
     for (int i = 0; i < fdc_chan::NSLOT; i++) {

@@ -36,6 +36,9 @@ SIGNATURES = {
     "fdc_set_device": (_i, [_i]),
     "fdc_host_alloc": (_vp, [C.c_size_t]),
     "fdc_host_free": (None, [_vp]),
+    "fdc_copy_threads": (_i, []),
+    "fdc_host_register": (_i, [_vp, C.c_size_t]),
+    "fdc_host_unregister": (_i, [_vp]),
     "fdc_launch_count": (C.c_ulonglong, []),
     "fdc_dev_alloc": (_vp, [C.c_size_t]),
     "fdc_dev_free": (None, [_vp]),

@@ -36,8 +36,18 @@ int fdc_api_version(void);
 const char* fdc_last_error(void);                 /* thread local, never NULL */
 int fdc_device_count(void);                        /* number of CUDA devices, <= 0 if none */
 int fdc_set_device(int device);                    /* device used by contexts created afterwards on this thread */
-void* fdc_host_alloc(size_t bytes);                /* pinned host memory for the *_host entry points */
+/* Host buffers of the *_host entry points.  GNU Radio's work() hands over scheduler-owned, pageable buffers
+ * (lib/overlap_save_impl.cc:62-81): the library stages them through pinned slots it owns (a ring of 4 per context) with a
+ * small pool of copy threads, so the caller needs nothing special.  Memory from fdc_host_alloc (or any page-locked
+ * memory) is recognised and used in place: no staging copy. */
+void* fdc_host_alloc(size_t bytes);                /* pinned host memory */
 void fdc_host_free(void* p);
+int fdc_copy_threads(void);                        /* worker threads of the staging copy pool (FDC_COPY_THREADS) */
+/* Page-lock memory the caller owns for as long as it stays registered (e.g. the scheduler's stream buffers, once, when the
+ * flowgraph starts): the *_host entry points then move it by DMA in place, at the speed of fdc_host_alloc memory.  The
+ * caller must unregister before freeing or remapping the range. */
+int fdc_host_register(void* p, size_t bytes);
+int fdc_host_unregister(void* p);
 /* plain device memory + blocking copies, so that a host language without a CUDA binding can keep a call's
  * spectrum on the GPU between fdc_chan_work_device and the activity-gated blocks' *_work_device */
 void* fdc_dev_alloc(size_t bytes);

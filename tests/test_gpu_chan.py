@@ -150,6 +150,56 @@ def test_multichunk_device_path_matches_reference(FDC, ref, case, nblocks, chunk
     assert worst < TOL, worst
 
 
+def test_host_buffers_pageable_pinned_registered_agree(FDC):
+    """fdc_chan_work_host with the caller's buffers (a) pageable: staged through the library's pinned slots by the copy pool,
+    (b) from fdc_host_alloc: used in place, (c) pageable but registered with fdc_host_register: used in place -- bit-identical
+    outputs, several calls (history carried), more chunks than slots"""
+    import ctypes
+    cfg = workloads.cfg2()
+    L = FDC._cabi.lib()
+    calls = (3, 150, 40)                              # 150 blocks = 7 host chunks of 21 blocks on 4 slots
+    x = workloads.noise_input(sum(calls) * cfg.hop, 77)
+
+    def run(kind):
+        g = make_gpu_chain(FDC, cfg)
+        res = [[] for _ in range(cfg.nchan)]
+        pos = 0
+        for nb in calls:
+            nin, nout = 8 * nb * cfg.hop, 8 * nb * cfg.out_per_block
+            keep = []
+            if kind == "pinned":
+                h_in, h_out = L.fdc_host_alloc(nin), L.fdc_host_alloc(nout)
+                assert h_in and h_out
+            else:
+                a = np.empty(nin, dtype=np.uint8); b = np.empty(nout, dtype=np.uint8); keep = [a, b]
+                h_in, h_out = a.ctypes.data, b.ctypes.data
+                if kind == "registered":
+                    FDC._cabi.check(L.fdc_host_register(ctypes.c_void_p(h_in), nin)); FDC._cabi.check(L.fdc_host_register(ctypes.c_void_p(h_out), nout))
+            ctypes.memmove(h_in, x[pos * cfg.hop:(pos + nb) * cfg.hop].ctypes.data, nin)
+            outs = []; off = 0
+            for lo in g.lout:
+                outs.append(h_out + off); off += 8 * nb * lo
+            ptrs = (ctypes.c_void_p * len(outs))(*outs)
+            FDC._cabi.check(L.fdc_chan_work_host(g._h, ctypes.c_void_p(h_in), nb, ctypes.cast(ptrs, ctypes.c_void_p), None))
+            got = np.ctypeslib.as_array(ctypes.cast(h_out, ctypes.POINTER(ctypes.c_uint8)), shape=(nout,)).copy().view(np.complex64)
+            off = 0
+            for i, lo in enumerate(g.lout):
+                res[i].append(got[off:off + nb * lo]); off += nb * lo
+            if kind == "pinned":
+                L.fdc_host_free(h_in); L.fdc_host_free(h_out)
+            elif kind == "registered":
+                FDC._cabi.check(L.fdc_host_unregister(ctypes.c_void_p(h_in))); FDC._cabi.check(L.fdc_host_unregister(ctypes.c_void_p(h_out)))
+            pos += nb
+            del keep
+        return [np.concatenate(r) for r in res]
+
+    a, b, c = run("pageable"), run("pinned"), run("registered")
+    for i in range(cfg.nchan):
+        assert np.array_equal(a[i].view(np.uint32), b[i].view(np.uint32)), i
+        assert np.array_equal(a[i].view(np.uint32), c[i].view(np.uint32)), i
+    assert L.fdc_copy_threads() >= 0
+
+
 def test_device_path_equals_host_path(FDC):
     import torch
     cfg = workloads.cfg2()
