@@ -422,6 +422,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-sustained", action="store_true", help="skip the >= 2 s sustained leg")
     ap.add_argument("--sustain-seconds", type=float, default=2.0)
+    ap.add_argument("--no-sinks", action="store_true", help="N > 1: keep every rank's outputs local (compute-only weak scaling)")
     ap.add_argument("--no-readings", action="store_true", help="cfg4 only: skip the second reading of the config (true 75 %% overlap)")
     args = ap.parse_args()
     claim_stdout()
@@ -472,8 +473,45 @@ def main():
     stream = tstream.cuda_stream
     assert stream != 0
 
-    def step():
+    # N > 1: the outputs are part of the step.  Channel-sharded sinks (FDC.sharded.ChannelSinks): rank k owns 1/N of the channels,
+    # every rank's extract kernel stores each channel's rows into its owner's buffer over NVLink peer memory (an all-to-all fused
+    # into the kernel).  `value` is then the gather-inclusive rate; the compute-only rate is reported beside it.
+    sinks = None; sinks_note = None
+    if world > 1 and not args.no_sinks:
+        from FDC import sharded
+        try:
+            sinks = sharded.ChannelSinks(chan, nb, rank, world)
+        except Exception as exc:                          # no peer access on this box: fall back to local outputs, say so
+            sinks_note = "channel-sharded sinks unavailable: " + str(exc)[:160]
+        ok = torch.tensor([1 if sinks else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if sinks and int(ok.item()) == 0:
+            sinks.close(); sinks = None; sinks_note = "channel-sharded sinks unavailable on another rank"
+
+    def step_local():
         chan.work_device(d_in.data_ptr(), nb, d_out.data_ptr(), 0, stream)
+
+    def step():
+        if sinks:
+            sinks.step(d_in.data_ptr(), nb, stream)
+        else:
+            step_local()
+
+    def nvlink_bytes():
+        """(tx, rx) data bytes of this GPU's NVLinks so far (nvidia-smi nvlink -gt d), None when unavailable"""
+        try:
+            import subprocess
+            out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(local)], capture_output=True, text=True, timeout=20).stdout
+            tx = rx = 0
+            for ln in out.splitlines():
+                ln = ln.strip()
+                if "Data Tx" in ln:
+                    tx += int(ln.split(":")[-1].split()[0])
+                elif "Data Rx" in ln:
+                    rx += int(ln.split(":")[-1].split()[0])
+            return (tx * 1024, rx * 1024) if (tx or rx) else None
+        except Exception:
+            return None
 
     def bracket():
         if world > 1:
@@ -514,6 +552,7 @@ def main():
     if not args.no_sustained:
         reps = max(K, int(np.ceil(args.sustain_seconds * 1e3 / max(ms / K, 1e-3))))
         bracket()
+        nv0 = nvlink_bytes() if world > 1 else None
         ssamp = ClockSampler(local); ssamp.start()
         s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
         s0.record()
@@ -529,13 +568,18 @@ def main():
         sms = float(ts.item())
         sustained = {"value": world * reps * nb * cfg.hop / (sms * 1e-3) / 1e6, "unit": "Msamples/s", "steps": reps, "seconds": sms * 1e-3,
                      "clocks": ssamp.result()}
+        nv1 = nvlink_bytes() if nv0 else None
+        if nv0 and nv1:
+            exp = 8.0 * reps * nb * cfg.out_per_block * (world - 1) / world if sinks else 0.0
+            sustained["nvlink_rank0"] = {"tx_GBps": (nv1[0] - nv0[0]) / (sms * 1e-3) / 1e9, "rx_GBps": (nv1[1] - nv0[1]) / (sms * 1e-3) / 1e9,
+                                         "expected_tx_GBps": exp / (sms * 1e-3) / 1e9, "source": "nvidia-smi nvlink -gt d, rank 0's GPU, over the sustained leg"}
 
     # ---- per-kernel roofline (separate pass with events around each kernel) ----
     peaks, peak_src = measured_peaks()
     chan.set_profiling(True)
     PK = max(3, min(K, 10))
     for _ in range(PK):
-        step()
+        step_local()
     ms_fwd, ms_ext, chunks = chan.get_profile()
     chan.set_profiling(False)
     in_bytes = 8.0 * nb * cfg.hop * PK
@@ -572,6 +616,22 @@ def main():
                          "sustained_frac": (sustained["value"] * 1e6 / world * cfg.bytes_per_sample() / 1e9 / peaks["hbm_gbs"]) if sustained else None,
                          "frac_of_8TBps_nominal": path_gbs / 8000.0,
                          "flop_per_sample": cfg.flops_per_sample(), "tflops_fp32": value * 1e6 / world * cfg.flops_per_sample() / 1e12}}
+
+    # ---- N > 1: the compute-only rate (outputs stay on the rank that made them) beside the gather-inclusive `value` ----
+    compute_only = None
+    if world > 1 and sinks:
+        for _ in range(3):
+            step_local()
+        bracket()
+        c0 = torch.cuda.Event(enable_timing=True); c1 = torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(K):
+            step_local()
+        c1.record(); bracket()
+        tc = torch.tensor([c0.elapsed_time(c1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        compute_only = {"value": world * K * nb * cfg.hop / (float(tc.item()) * 1e-3) / 1e6, "unit": "Msamples/s", "steps": K,
+                        "note": "every rank keeps its outputs in its own HBM: no bytes cross NVLink"}
 
     # ---- e2e: host buffers through the C ABI ----
     e2e = None
@@ -729,14 +789,22 @@ def main():
                 "config": {"workload": cfg.name, "fft": cfg.N, "overlap": cfg.ovl, "hop": cfg.hop, "channels": cfg.nchan,
                            "slice_len": cfg.params[0][1], "out_per_block": cfg.out_per_block, "blocks_per_step_per_gpu": nb,
                            "chunk_blocks": chan.chunk_blocks, "sharding": "time (contiguous runs of blocks per rank, halo recomputed)",
+                           "outputs": ("channel-sharded sinks: rank k owns channels with owner k, all ranks' extract kernels store into the owners' "
+                                       "buffers over NVLink peer memory inside the timed region (%d B of %d B per sample leave each GPU)" %
+                                       (int(8 * cfg.out_per_block / cfg.hop * (world - 1) / world), int(8 * cfg.out_per_block / cfg.hop))) if sinks
+                                      else ("local to each rank" + ("; " + sinks_note if sinks_note else "")),
                            "l2_policy": "inputs larger than L2 (%.0f MB in, %.0f MB out per step)" %
                                         (8e-6 * nb * cfg.hop, 8e-6 * nb * cfg.out_per_block)},
                 "clocks": clocks, "sustained": sustained, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
         if readings:
             line["readings"] = readings
+        if compute_only:
+            line["compute_only"] = compute_only
         if gather:
             line["gather"] = gather
         emit(line)
+    if sinks:
+        bracket(); sinks.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

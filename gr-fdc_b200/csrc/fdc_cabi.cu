@@ -131,7 +131,14 @@ struct fdc_chan {
     long lout_total;
     long blockcount;
     long chunk_blocks;                 /* blocks per K1->K2 round trip: spectrum ring sized to stay in L2 */
-    DevBuf d_chans, d_tables, d_hist, d_hist2, d_stage;
+    DevBuf d_chans, d_tables, d_hist, d_hist2;
+    std::vector<int> launch_order;     /* d_chans[k] describes channel launch_order[k] */
+    int nsinks;
+    /* channel-sharded sinks by DMA (FDC_SINK_DMA=1, default): the extract kernel writes a chunk's rows into a local staging slab,
+     * the copy engines move every owner's part over NVLink while the next chunks are transformed */
+    std::vector<void*> sink_bases; std::vector<int> sink_first, sink_count, sink_local;     /* owner k holds channels [first, first + count) */
+    std::vector<long> sink_prefix_total;                                                    /* items per block of owner k */
+    DevBuf w_out[4]; cudaStream_t cs[4]; cudaEvent_t ev_x[4], ev_c[4]; bool copies_pending[4];
     const float2* tw4;                 /* four-step twiddles (big N) */
     cudaStream_t stream;
     /* device path: chunks alternate between NWORK worker streams, each with its own spectrum / intermediate ring, so
@@ -153,10 +160,10 @@ struct fdc_chan {
     bool prof;
     std::vector<cudaEvent_t> prof_ev;      /* triples: before K1, after K1, after K2 */
     std::vector<cudaEvent_t> prof_pool;
-    fdc_chan() : tw4(0), stream(0), ev_start(0), ev_hist(0), hist_pending(false), hist_stream(0), host_chunk(0), prof(false)
+    fdc_chan() : nsinks(0), tw4(0), stream(0), ev_start(0), ev_hist(0), hist_pending(false), hist_stream(0), host_chunk(0), prof(false)
     {
         for (int i = 0; i < NSLOT; i++) { hs[i] = 0; h_done[i] = 0; }
-        for (int i = 0; i < NWORK; i++) { ws[i] = 0; ev_done[i] = 0; l2_window[i] = 0; }
+        for (int i = 0; i < NWORK; i++) { ws[i] = 0; ev_done[i] = 0; l2_window[i] = 0; cs[i] = 0; ev_x[i] = 0; ev_c[i] = 0; copies_pending[i] = false; }
     }
     cudaEvent_t ev()
     {
@@ -180,7 +187,7 @@ static long pick_chunk_blocks(int N)
 /* enqueue K1 + K2 for nb blocks; block b reads d_in[b*hop - ovl, b*hop + hop) */
 static int chan_enqueue_chunk(fdc_chan* c, const float2* d_in, long nb, float2* d_spec, float2* d_mid,
                               float2* d_out, long call_blocks, long call_blk0, long glob_blk0, cudaStream_t s,
-                              const float2* d_hist = 0, long head_blocks = 0)
+                              const float2* d_hist = 0, long head_blocks = 0, const ExtractParams::Sink* sinks = 0, int nsinks = 0)
 {
     cudaError_t e;
     if (c->prof) cudaEventRecord(c->ev(), s);
@@ -195,13 +202,14 @@ static int chan_enqueue_chunk(fdc_chan* c, const float2* d_in, long nb, float2* 
     }
     if (e != cudaSuccess) return cuda_fail(e, "forward FFT launch");
     if (c->prof) cudaEventRecord(c->ev(), s);
-    if (!d_out) { if (c->prof) cudaEventRecord(c->ev(), s); return 0; }
+    if (!d_out && !nsinks) { if (c->prof) cudaEventRecord(c->ev(), s); return 0; }
     for (size_t g = 0; g < c->groups.size(); g++) {
         ExtractParams q; q.spec = d_spec; q.spec_stride = c->N; q.tables = (const float2*)c->d_tables.p;
         q.chans = (const ChanDev*)c->d_chans.p + c->groups[g].second.first;
         q.nsel = c->groups[g].second.second; q.ny = 0; q.out = d_out;
         q.tma_ok = ((uintptr_t)d_spec % 16 == 0) && (c->N % 2 == 0) && c->group_even_f[g];
-        q.l2pf = (tuning().l2pf && q.tma_ok) ? 1 : 0; q.bpt = 1;
+        q.l2pf = (tuning().l2pf && q.tma_ok) ? 1 : 0; q.bpt = 1; q.nsinks = nsinks;
+        for (int k = 0; k < nsinks; k++) q.sink[k] = sinks[k];
         q.nb = nb; q.call_blocks = call_blocks; q.call_blk0 = call_blk0; q.glob_phase0 = (int)(glob_blk0 % c->nphase); q.nphase = c->nphase;
         q.phase_mask = (c->nphase & (c->nphase - 1)) == 0 ? c->nphase - 1 : -1;
         e = launch_extract(q, c->groups[g].first, s);
@@ -287,6 +295,7 @@ fdc_chan* fdc_chan_create(int N, int ovl, int nphase, int nchan, const fdc_chan_
         ok = cudaStreamCreateWithFlags(&c->ws[i], cudaStreamNonBlocking) == cudaSuccess &&
              cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming) == cudaSuccess;
     /* device copy of the channel descriptors in launch order (grouped by l, ascending f) */
+    c->launch_order = sel;
     std::vector<ChanDev> ordered(sel.size());
     for (size_t i = 0; i < sel.size(); i++) ordered[i] = c->chans[(size_t)sel[i]];
     ok = ok && c->d_chans.upload(ordered.data(), sizeof(ChanDev) * ordered.size());
@@ -310,7 +319,13 @@ void fdc_chan_destroy(fdc_chan* c)
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->ev_start) cudaEventDestroy(c->ev_start);
     if (c->ev_hist) cudaEventDestroy(c->ev_hist);
-    for (int i = 0; i < fdc_chan::NWORK; i++) { if (c->ws[i]) cudaStreamDestroy(c->ws[i]); if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]); }
+    for (int i = 0; i < fdc_chan::NWORK; i++) {
+        if (c->ws[i]) cudaStreamDestroy(c->ws[i]);
+        if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
+        if (c->cs[i]) cudaStreamDestroy(c->cs[i]);
+        if (c->ev_x[i]) cudaEventDestroy(c->ev_x[i]);
+        if (c->ev_c[i]) cudaEventDestroy(c->ev_c[i]);
+    }
     for (size_t i = 0; i < c->prof_ev.size(); i++) cudaEventDestroy(c->prof_ev[i]);
     for (size_t i = 0; i < c->prof_pool.size(); i++) cudaEventDestroy(c->prof_pool[i]);
     for (int i = 0; i < fdc_chan::NSLOT; i++) { if (c->hs[i]) cudaStreamDestroy(c->hs[i]); if (c->h_done[i]) cudaEventDestroy(c->h_done[i]); }
@@ -367,8 +382,62 @@ int fdc_chan_work_device(fdc_chan* c, const void* d_in_v, long nblocks, void* d_
     return fdc_chan_work_device_slab(c, d_in_v, nblocks, d_out_v, nblocks, 0, d_spectrum_v, stream);
 }
 
+static int chan_work_device(fdc_chan* c, const void* d_in_v, long nblocks, void* d_out_v, long slab_blocks, long slab_first_block,
+                            void* d_spectrum_v, void* stream, bool use_sinks);
+
 int fdc_chan_work_device_slab(fdc_chan* c, const void* d_in_v, long nblocks, void* d_out_v, long slab_blocks, long slab_first_block,
                               void* d_spectrum_v, void* stream)
+{
+    return chan_work_device(c, d_in_v, nblocks, d_out_v, slab_blocks, slab_first_block, d_spectrum_v, stream, false);
+}
+
+/* Channel-sharded sinks (one process per GPU; FDC/sharded.py ChannelSinks): sink k is the output buffer of the GPU that owns
+ * the channels with owner[c] == k, laid out channel-major like the output of fdc_chan_work_device_slab but holding only those
+ * channels.  The extract kernel of EVERY rank stores each channel's rows straight into its owner's buffer -- its own memory
+ * or peer memory mapped with fdc_ipc_open -- so the exchange is an all-to-all of peer stores that overlaps the butterflies:
+ * every GPU receives 1/world of every rank's output instead of one GPU receiving everything. */
+int fdc_chan_set_sinks(fdc_chan* c, int nsinks, void* const* d_bases, const int* owner, int local_sink)
+{
+    OnDevice on_dev(c ? c->dev : -1);
+    if (!c) return fail("null context");
+    if (nsinks < 1 || nsinks > FDC_MAX_SINKS || !d_bases || !owner) return fail("fdc_chan_set_sinks: need 1 .. 16 sinks");
+    std::vector<long> run((size_t)nsinks, 0);
+    for (int i = 0; i < c->nchan; i++) {
+        if (owner[i] < 0 || owner[i] >= nsinks) return fail("fdc_chan_set_sinks: channel owner out of range");
+        c->chans[(size_t)i].owner = owner[i];
+        c->chans[(size_t)i].sink_prefix = run[(size_t)owner[i]];
+        run[(size_t)owner[i]] += c->chans[(size_t)i].lout;
+    }
+    for (int k = 0; k < nsinks; k++) if (run[(size_t)k] && !d_bases[k]) return fail("fdc_chan_set_sinks: a sink that owns channels has no buffer");
+    c->sink_bases.assign(d_bases, d_bases + nsinks);
+    c->sink_first.assign((size_t)nsinks, 0); c->sink_count.assign((size_t)nsinks, 0);
+    bool contiguous = true;
+    for (int i = 0; i < c->nchan; i++) {
+        const int k = owner[i];
+        if (c->sink_count[(size_t)k] == 0) c->sink_first[(size_t)k] = i;
+        else if (c->sink_first[(size_t)k] + c->sink_count[(size_t)k] != i) contiguous = false;
+        c->sink_count[(size_t)k]++;
+    }
+    if (!contiguous) c->sink_first.clear();            /* scattered ownership: the kernel stores into the sinks itself */
+    cudaDeviceSynchronize();
+    std::vector<ChanDev> ordered(c->launch_order.size());
+    for (size_t i = 0; i < ordered.size(); i++) ordered[i] = c->chans[(size_t)c->launch_order[i]];
+    if (!c->d_chans.upload(ordered.data(), sizeof(ChanDev) * ordered.size())) return cuda_fail(cudaGetLastError(), "fdc_chan_set_sinks");
+    c->sink_prefix_total = run;
+    /* the sink in this GPU's own memory is stored into directly by the kernel; the others are peer memory */
+    c->sink_local.assign((size_t)nsinks, 0);
+    if (local_sink >= 0 && local_sink < nsinks) c->sink_local[(size_t)local_sink] = 1;
+    c->nsinks = nsinks;
+    return 0;
+}
+int fdc_chan_work_device_sinks(fdc_chan* c, const void* d_in, long nblocks, long slab_blocks, long slab_first_block, void* stream)
+{
+    if (c && c->nsinks < 1) return fail("fdc_chan_work_device_sinks: call fdc_chan_set_sinks first");
+    return chan_work_device(c, d_in, nblocks, 0, slab_blocks, slab_first_block, 0, stream, true);
+}
+
+static int chan_work_device(fdc_chan* c, const void* d_in_v, long nblocks, void* d_out_v, long slab_blocks, long slab_first_block,
+                            void* d_spectrum_v, void* stream, bool use_sinks)
 {
     OnDevice on_dev(c ? c->dev : -1);
     if (!c) return fail("null context");
@@ -420,13 +489,73 @@ int fdc_chan_work_device_slab(fdc_chan* c, const void* d_in_v, long nblocks, voi
         if ((e = cudaEventRecord(c->ev_start, s)) != cudaSuccess) return cuda_fail(e, "event record");
         for (int i = 0; i < nw; i++) if ((e = cudaStreamWaitEvent(wk[i], c->ev_start, 0)) != cudaSuccess) return cuda_fail(e, "stream wait");
     }
+    /* Sinks.  FDC_SINK_DMA=0: the extract kernel stores every channel's rows into its owner's buffer itself (peer stores over
+     * NVLink for remote owners).  FDC_SINK_DMA=1: rows of REMOTE owners go to a compact local staging slab per owner and the copy
+     * engines forward them behind the kernels (one 2-D copy per owner and chunk, a copy stream per worker stream); rows of the
+     * local owner are stored directly in both modes. */
+    const bool sink_dma = use_sinks && tuning().sink_dma;
+    ExtractParams::Sink sk[FDC_MAX_SINKS];
+    std::vector<long> stage_off((size_t)(use_sinks ? c->nsinks : 0), 0);
+    if (sink_dma) {
+        long total = 0;
+        for (int k = 0; k < c->nsinks; k++) { stage_off[(size_t)k] = total; if (!c->sink_local[(size_t)k]) total += ring * c->sink_prefix_total[(size_t)k]; }
+        for (int i = 0; i < nw; i++) {
+            if (!c->w_out[i].reserve(sizeof(float2) * (size_t)std::max(1L, total))) return cuda_fail(cudaGetLastError(), "sink staging slab");
+            if (!c->cs[i] && ((e = cudaStreamCreateWithFlags(&c->cs[i], cudaStreamNonBlocking)) != cudaSuccess ||
+                              (e = cudaEventCreateWithFlags(&c->ev_x[i], cudaEventDisableTiming)) != cudaSuccess ||
+                              (e = cudaEventCreateWithFlags(&c->ev_c[i], cudaEventDisableTiming)) != cudaSuccess)) return cuda_fail(e, "sink copy stream");
+        }
+    }
     int w = 0;
     for (long b0 = 0; b0 < nblocks; w = (w + 1) % nw) {
         const long nb = std::min(c->chunk_blocks, nblocks - b0);
         float2* spec = d_spectrum ? d_spectrum + b0 * c->N : ring_spec[w];
+        float2* stage = sink_dma ? (float2*)c->w_out[w].p : 0;
+        bool staged = false;
+        for (int k = 0; use_sinks && k < c->nsinks; k++) {
+            if (sink_dma && !c->sink_local[(size_t)k] && c->sink_prefix_total[(size_t)k]) {
+                sk[k].base = stage + stage_off[(size_t)k]; sk[k].blocks = nb; sk[k].blk0 = 0; staged = true;
+            } else {
+                sk[k].base = (float2*)c->sink_bases[(size_t)k]; sk[k].blocks = slab_blocks; sk[k].blk0 = slab_first_block + b0;
+            }
+        }
+        /* the staging slab of this worker is free once the copies of the chunk that used it last are done */
+        if (staged && c->copies_pending[w] && (e = cudaStreamWaitEvent(wk[w], c->ev_c[w], 0)) != cudaSuccess) return cuda_fail(e, "stream wait");
         if (chan_enqueue_chunk(c, d_in + b0 * c->hop, nb, spec, ring_mid[w], d_out, slab_blocks, slab_first_block + b0, c->blockcount + b0, wk[w],
-                               (const float2*)c->d_hist.p, std::max(0L, nh - b0))) return -1;
+                               (const float2*)c->d_hist.p, std::max(0L, nh - b0), sk, use_sinks ? c->nsinks : 0)) return -1;
+        if (staged) {
+            if ((e = cudaEventRecord(c->ev_x[w], wk[w])) != cudaSuccess || (e = cudaStreamWaitEvent(c->cs[w], c->ev_x[w], 0)) != cudaSuccess)
+                return cuda_fail(e, "sink copy ordering");
+            for (int k = 0; k < c->nsinks && e == cudaSuccess; k++) {
+                if (c->sink_local[(size_t)k] || !c->sink_prefix_total[(size_t)k]) continue;
+                const float2* src = stage + stage_off[(size_t)k];
+                float2* base = (float2*)c->sink_bases[(size_t)k];
+                bool uniform = !c->sink_first.empty();
+                const int c0 = uniform ? c->sink_first[(size_t)k] : 0, cn = uniform ? c->sink_count[(size_t)k] : 0;
+                for (int i = c0 + 1; i < c0 + cn; i++) if (c->chans[(size_t)i].lout != c->chans[(size_t)c0].lout) uniform = false;
+                if (uniform) {
+                    /* one 2-D copy: a row per channel, nb * lout items wide, into rows [slab_first_block + b0, +nb) of the owner's slabs */
+                    const size_t lo = (size_t)c->chans[(size_t)c0].lout;
+                    e = cudaMemcpy2DAsync(base + (size_t)(slab_first_block + b0) * lo, sizeof(float2) * (size_t)slab_blocks * lo, src,
+                                          sizeof(float2) * (size_t)nb * lo, sizeof(float2) * (size_t)nb * lo, (size_t)cn, cudaMemcpyDefault, c->cs[w]);
+                } else {
+                    for (int i = 0; i < c->nchan && e == cudaSuccess; i++) {
+                        const ChanDev& ch = c->chans[(size_t)i];
+                        if (ch.owner != k) continue;
+                        e = cudaMemcpyAsync(base + (size_t)slab_blocks * (size_t)ch.sink_prefix + (size_t)(slab_first_block + b0) * (size_t)ch.lout,
+                                            src + (size_t)nb * (size_t)ch.sink_prefix, sizeof(float2) * (size_t)nb * (size_t)ch.lout, cudaMemcpyDefault, c->cs[w]);
+                    }
+                }
+            }
+            if (e != cudaSuccess) return cuda_fail(e, "sink copy");
+            if ((e = cudaEventRecord(c->ev_c[w], c->cs[w])) != cudaSuccess) return cuda_fail(e, "event record");
+            c->copies_pending[w] = true;
+        }
         b0 += nb;
+    }
+    if (sink_dma) {
+        for (int i = 0; i < nw; i++)
+            if (c->copies_pending[i] && (e = cudaStreamWaitEvent(s, c->ev_c[i], 0)) != cudaSuccess) return cuda_fail(e, "stream wait");
     }
     if (nw > 1) {
         for (int i = 0; i < nw; i++) {
@@ -465,7 +594,7 @@ int fdc_chan_work_spectrum_device(fdc_chan* c, const void* d_spec_in_v, long nbl
             ExtractParams q; q.spec = spec; q.spec_stride = c->N; q.tables = (const float2*)c->d_tables.p;
             q.chans = (const ChanDev*)c->d_chans.p + c->groups[g].second.first; q.nsel = c->groups[g].second.second; q.ny = 0; q.out = d_out;
             q.tma_ok = ((uintptr_t)spec % 16 == 0) && (c->N % 2 == 0) && c->group_even_f[g];
-            q.l2pf = (tuning().l2pf && q.tma_ok) ? 1 : 0; q.bpt = 1;
+            q.l2pf = (tuning().l2pf && q.tma_ok) ? 1 : 0; q.bpt = 1; q.nsinks = 0;
             q.nb = nb; q.call_blocks = nblocks; q.call_blk0 = b0; q.glob_phase0 = (int)((c->blockcount + b0) % c->nphase); q.nphase = c->nphase;
             q.phase_mask = (c->nphase & (c->nphase - 1)) == 0 ? c->nphase - 1 : -1;
             e = launch_extract(q, c->groups[g].first, s);

@@ -209,11 +209,13 @@ template <int N1, int N2, int B> struct RowTiles {      /* tile = blk * (N1/B) +
  * A CTA handles B channels that are neighbours in frequency on ONE block: their slices overlap, so the spectrum is
  * read from L2 once and the second use hits in L1. */
 struct ChanDev {
-    int f, lout, shift, pad0;
+    int f, lout, shift, owner;   /* owner: index of the sink this channel's rows go to (channel-sharded sinks), else 0 */
     long tab_off;          /* float2 offset of table[0][0] in `tables` */
     long lout_prefix;      /* sum of lout over the channels before this one */
+    long sink_prefix;      /* sum of lout over the earlier channels of the same owner */
     float gain; int pad1;
 };
+#define FDC_MAX_SINKS 16
 struct ExtractParams {
     const float2* spec; long spec_stride;   /* rows of the spectrum (ring) holding this chunk */
     const float2* tables;
@@ -229,7 +231,22 @@ struct ExtractParams {
     int l2pf;              /* bulk-prefetch the next tile's slices into L2 while this tile is transformed (needs tma_ok) */
     int bpt;               /* packed tiles (few channels of this length): a tile holds all nsel channels of bpt consecutive blocks */
     int phase_mask;        /* nphase - 1 when nphase is a power of two (the hier block's relinvovl always is), else -1 */
+    /* channel-sharded sinks (multi-GPU, FDC/sharded.py ChannelSinks): channel c's rows go to sink[owner_c] -- the buffer of the
+     * GPU that owns the channel (own memory, or peer memory mapped over NVLink), or a local staging slab that the copy engines
+     * forward to the owner.  Every sink is laid out like `out` but holds only its owner's channels: blocks rows per channel,
+     * this launch's blocks starting at row blk0.  nsinks == 0: everything goes to `out`. */
+    int nsinks;
+    struct Sink { float2* base; long blocks, blk0; } sink[FDC_MAX_SINKS];
 };
+/* first item of block b of channel ch in its output buffer */
+FDC_HD float2* chan_out_row(const ExtractParams& p, const ChanDev& ch, long b)
+{
+    if (p.nsinks) {
+        const ExtractParams::Sink& k = p.sink[ch.owner];
+        return k.base + (k.blocks * ch.sink_prefix + (k.blk0 + b) * ch.lout);
+    }
+    return p.out + (p.call_blocks * ch.lout_prefix + (p.call_blk0 + b) * ch.lout);
+}
 /* x mod nphase without an integer division when nphase is a power of two */
 FDC_HD unsigned phase_mod(const ExtractParams& p, unsigned x) { return p.phase_mask >= 0 ? (x & (unsigned)p.phase_mask) : x % (unsigned)p.nphase; }
 template <int L, int B> struct ExtractLoader {
@@ -266,7 +283,7 @@ template <int L, int B> struct ExtractStorer {
         if (s >= p.nsel) return c;
         const ChanDev& ch = p.chans[s];
         c.skip = L - ch.lout - o; c.gain = ch.gain;
-        c.dst = p.out + (p.call_blocks * ch.lout_prefix + (p.call_blk0 + b) * ch.lout - (L - ch.lout) + o);
+        c.dst = chan_out_row(p, ch, b) - (L - ch.lout) + o;
         return c;
     }
     /* gain 1 (a power-of-two gain is folded into the table at create time) skips the multiply: uniform branch per butterfly */
@@ -382,7 +399,7 @@ template <int L, int B> struct PackedExtractStorer {
         if (!g.valid) return c;
         const ChanDev& ch = p.chans[g.s];
         c.skip = L - ch.lout - o; c.gain = ch.gain;
-        c.dst = p.out + (p.call_blocks * ch.lout_prefix + (p.call_blk0 + g.blk) * ch.lout - (L - ch.lout) + o);
+        c.dst = chan_out_row(p, ch, g.blk) - (L - ch.lout) + o;
         return c;
     }
     static constexpr bool HAS_VARIANT = true;

@@ -238,6 +238,18 @@ class Channelizer(object):
                                               int(slab_first_block), C.c_void_p(d_spectrum) if d_spectrum else None,
                                               C.c_void_p(stream) if stream else None), "fdc_chan_work_device_slab")
 
+    def set_sinks(self, bases, owner, local_sink=-1):
+        """channel-sharded sinks: bases[k] = device address of sink k's buffer as seen from this GPU, owner[i] = sink of channel i,
+        local_sink = the sink that lies in this GPU's own memory"""
+        arr = (C.c_void_p * len(bases))(*[int(b) if b else None for b in bases])
+        own = (C.c_int * len(owner))(*[int(o) for o in owner])
+        check(lib().fdc_chan_set_sinks(self._h, len(bases), C.cast(arr, C.c_void_p), C.cast(own, C.c_void_p), int(local_sink)), "fdc_chan_set_sinks")
+
+    def work_device_sinks(self, d_in, nblocks, slab_blocks, slab_first_block, stream=0):
+        """like work_device_slab, every channel's rows going to its owner's sink (FDC.sharded.ChannelSinks)"""
+        check(lib().fdc_chan_work_device_sinks(self._h, C.c_void_p(d_in), int(nblocks), int(slab_blocks), int(slab_first_block),
+                                               C.c_void_p(stream) if stream else None), "fdc_chan_work_device_sinks")
+
     def work_spectrum_device(self, d_spectra, nblocks, d_out, d_spectrum=0, stream=0):
         """inpveclen > 1 mode: already transformed (fft-shifted, unnormalised) spectra in, channel outputs out."""
         check(lib().fdc_chan_work_spectrum_device(self._h, C.c_void_p(d_spectra), int(nblocks), C.c_void_p(d_out) if d_out else None,

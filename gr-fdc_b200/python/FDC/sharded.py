@@ -130,6 +130,71 @@ class PeerSink(object):
         self.ptr = self._local = None
 
 
+def channel_owners(louts, world):
+    """Deal the channels out over `world` sinks in contiguous runs of (nearly) equal output volume: owner[i] for every channel and
+    the number of output items per block each sink receives.  Contiguous runs keep neighbouring channels (which share spectrum
+    bins and usually a downstream consumer) on one GPU."""
+    louts = [int(v) for v in louts]
+    total = sum(louts)
+    owner, per_sink, acc, k = [], [0] * world, 0, 0
+    for lo in louts:
+        # move on to the next sink when this one has its share (never leave a later sink without channels to take)
+        while k < world - 1 and acc + lo / 2.0 > total * (k + 1) / float(world):
+            k += 1
+        owner.append(k); per_sink[k] += lo; acc += lo
+    return owner, per_sink
+
+
+class ChannelSinks(object):
+    """Channel-sharded sinks of a time-sharded channelizer (one process per GPU).  Rank k owns the channels with owner[i] == k and
+    holds ONE buffer for them: channel-major slabs of world * blocks_per_rank rows.  Every rank maps every other rank's buffer
+    (CUDA IPC, peer access over NVLink) and its extract kernel stores each channel's rows [rank * blocks_per_rank, ...) straight
+    into the owner's buffer: an all-to-all of peer stores fused into the kernel; each GPU receives (world-1)/world of ONE GPU's
+    output instead of a single sink rank receiving (world-1) GPUs' worth (PeerSink, NCCL gather).  After a step and a barrier,
+    rank k holds the complete, stream-ordered output of its channels."""
+
+    def __init__(self, chan, blocks_per_rank, rank, world, group=None):
+        import ctypes as C
+        import torch.distributed as dist
+        from ._cabi import lib, check, handle
+        self.rank, self.world, self.blocks_per_rank = rank, world, int(blocks_per_rank)
+        self.slab_blocks = world * self.blocks_per_rank
+        self.owner, self.per_sink = channel_owners(chan.lout, world)
+        self.my_channels = [i for i, o in enumerate(self.owner) if o == rank]
+        self.nbytes = 8 * self.slab_blocks * max(1, self.per_sink[rank])
+        self._local = lib().fdc_dev_alloc(self.nbytes)
+        if not self._local:
+            raise RuntimeError("sink allocation failed")
+        h = C.create_string_buffer(64)
+        check(lib().fdc_ipc_export(C.c_void_p(self._local), h), "fdc_ipc_export")
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(h.raw), group=group)
+        self._hbufs, self.bases = [], []
+        for r in range(world):
+            if r == rank:
+                self.bases.append(self._local)
+            else:
+                hb = C.create_string_buffer(handles[r], 64); self._hbufs.append(hb)
+                self.bases.append(handle(lib().fdc_ipc_open(hb), "fdc_ipc_open").value)
+        chan.set_sinks(self.bases, self.owner, rank)
+        self.chan = chan
+
+    def first_block(self):
+        return self.rank * self.blocks_per_rank
+
+    def step(self, d_in, nblocks, stream=0):
+        self.chan.work_device_sinks(d_in, nblocks, self.slab_blocks, self.first_block(), stream)
+
+    def close(self):
+        from ._cabi import lib
+        for r, b in enumerate(self.bases):
+            if r != self.rank and b:
+                lib().fdc_ipc_close(b)
+        if self._local:
+            lib().fdc_dev_free(self._local)
+        self.bases, self._local = [], None
+
+
 class ShardedActivity(object):
     """An activity-gated block (PowerActivationChannel, SegmentDetection, activity_detection_channelizer_vcm) on a
     time-sharded stream.  The reference blocks carry state from block to block (lib/PowerActivationChannel_impl.cc:137-177,

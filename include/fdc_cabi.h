@@ -115,6 +115,17 @@ int fdc_chan_work_device_slab(fdc_chan* c, const void* d_in, long nblocks, void*
 int fdc_ipc_export(const void* d_ptr, void* handle64);
 void* fdc_ipc_open(const void* handle64);
 int fdc_ipc_close(void* d_ptr);
+/* Channel-sharded sinks for a time-sharded stream on several GPUs (the reference has one flowgraph and one sink
+ * per channel, python/FrequencyDomainChannelizer.py:312 -- with N GPUs the channels are dealt out over the ranks, each rank
+ * feeding the sinks of its own channels).  d_bases[k] is sink k's buffer as seen from THIS GPU (local, or fdc_ipc_open of the
+ * owner's export); owner[i] in [0, nsinks) names the sink of channel i.  Sink k holds only its channels, channel-major:
+ * slab_blocks * lout_i items per channel in channel order, this call's blocks in rows [slab_first_block, +nblocks).  The
+ * extract kernel stores every channel's rows straight into its owner's memory (peer stores over NVLink for remote owners):
+ * an all-to-all that overlaps the transforms, every GPU receiving 1/N of each rank's output.  local_sink: the index of the
+ * sink that lies in this GPU's own memory (-1: none; with FDC_SINK_DMA=1 the rows of all OTHER sinks are written to a local
+ * staging slab and forwarded by the copy engines behind the kernels instead of being stored by the SMs). */
+int fdc_chan_set_sinks(fdc_chan* c, int nsinks, void* const* d_bases, const int* owner, int local_sink);
+int fdc_chan_work_device_sinks(fdc_chan* c, const void* d_in, long nblocks, long slab_blocks, long slab_first_block, void* stream);
 /* The hier block's inpveclen > 1 mode (python/FrequencyDomainChannelizer.py:284-290): the input items are vectors that are
  * already transformed (fft-shifted, unnormalised spectra of N bins).  Runs normalize_input (x 1/N, :216) and the
  * per-channel chains; overlap-save and the forward FFT are skipped.  d_spectrum (optional) receives the normalised

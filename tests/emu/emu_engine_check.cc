@@ -209,12 +209,12 @@ template <int L, int E = 16, bool PACK = false> static void check_extract(int N,
     for (int i = 0; i < nchan; i++) {
         ChanDev& c = chans[i];
         c.f = (int)(((long)i * (N - L)) / std::max(1, nchan - 1)); c.lout = L - L / 4 - (i % 3 == 1 ? 1 : 0); if (c.lout < 1) c.lout = 1;
-        c.shift = (c.f + i) % nphase; c.tab_off = (i % 2) * (long)nphase * L; c.lout_prefix = prefix; c.gain = (float)(1 + i % 4); c.pad0 = c.pad1 = 0;
+        c.shift = (c.f + i) % nphase; c.tab_off = (i % 2) * (long)nphase * L; c.lout_prefix = prefix; c.gain = (float)(1 + i % 4); c.owner = 0; c.sink_prefix = 0; c.pad1 = 0;
         prefix += c.lout;
     }
     std::vector<float2> out((size_t)(call_blocks * prefix), make_float2(-9.f, -9.f));
     const std::vector<float2> tw = pass_twiddles(L, E);
-    ExtractParams p; p.l2pf = 0; p.spec = spec.data(); p.spec_stride = N; p.tables = tables.data(); p.chans = chans.data();
+    ExtractParams p; p.l2pf = 0; p.nsinks = 0; p.spec = spec.data(); p.spec_stride = N; p.tables = tables.data(); p.chans = chans.data();
     p.nsel = nchan; p.ny = (nchan + B - 1) / B; p.out = out.data(); p.nb = nb; p.call_blocks = call_blocks; p.call_blk0 = call_blk0;
     p.glob_phase0 = glob_phase0; p.nphase = nphase; p.tma_ok = 0; p.phase_mask = (nphase & (nphase - 1)) == 0 ? nphase - 1 : -1;
     p.bpt = 1;
@@ -265,11 +265,11 @@ template <int L> static void check_extract_staged(int N, int nchan, long nb, int
     for (int i = 0; i < nchan; i++) {
         ChanDev& c = chans[i];
         c.f = (int)((((long)i * (N - L)) / std::max(1, nchan - 1)) & ~1L); c.lout = L - L / 4; c.shift = (c.f / 2 + i) % nphase;
-        c.tab_off = (i % 2) * (long)nphase * L; c.lout_prefix = prefix; c.gain = 1.0f; c.pad0 = c.pad1 = 0; prefix += c.lout;
+        c.tab_off = (i % 2) * (long)nphase * L; c.lout_prefix = prefix; c.gain = 1.0f; c.owner = 0; c.sink_prefix = 0; c.pad1 = 0; prefix += c.lout;
     }
     std::vector<float2> out((size_t)(nb * prefix));
     const std::vector<float2> tw = pass_twiddles(L, 32);
-    ExtractParams p; p.l2pf = 0; p.spec = spec.data(); p.spec_stride = N; p.tables = tables.data(); p.chans = chans.data(); p.nsel = nchan;
+    ExtractParams p; p.l2pf = 0; p.nsinks = 0; p.spec = spec.data(); p.spec_stride = N; p.tables = tables.data(); p.chans = chans.data(); p.nsel = nchan;
     p.ny = (nchan + B - 1) / B; p.out = out.data(); p.nb = nb; p.call_blocks = nb; p.call_blk0 = 0; p.glob_phase0 = 0; p.nphase = nphase; p.tma_ok = 1; p.phase_mask = (nphase & (nphase - 1)) == 0 ? nphase - 1 : -1;
     ExtractStageTiles<L, B> tiles{p, stage.data()};
     std::vector<float2> smem(ENG::SMEM_ELEMS);

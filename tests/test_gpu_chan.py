@@ -308,6 +308,42 @@ def test_slab_placement_builds_one_stream_ordered_buffer(FDC):
         make_gpu_chain(FDC, cfg).work_device_slab(d_in.data_ptr(), per, d_all.data_ptr(), per, 1)
 
 
+@pytest.mark.parametrize("case,world", [("cfg2", 3), ("example4096", 2), ("cfg1", 8)])
+def test_channel_sharded_sinks_hold_their_channels_in_stream_order(FDC, case, world):
+    """fdc_chan_set_sinks / fdc_chan_work_device_sinks (FDC.sharded.ChannelSinks on one GPU: `world` time-sharded contexts, `world`
+    sink buffers, all local): after every rank has run its blocks, sink k holds exactly the channels it owns, complete and in
+    stream order, bit-identical to one context fed the whole stream"""
+    import torch
+    from FDC import sharded
+    cfg = {"cfg2": workloads.cfg2, "cfg1": workloads.cfg1, "example4096": lambda: workloads.cfg_example(4096, 4, workloads.HANN)}[case]()
+    per = 7
+    nblocks = per * world
+    x = workloads.tones_input(cfg, nblocks * cfg.hop, seed=29) + workloads.noise_input(nblocks * cfg.hop, 30) * np.float32(0.1)
+    whole, _ = make_gpu_chain(FDC, cfg).work_host(x)
+    louts = [p[2] for p in cfg.params]
+    owner, per_sink = sharded.channel_owners(louts, world)
+    assert owner == sorted(owner) and len(owner) == cfg.nchan                                            # contiguous runs
+    sinks = [torch.full((max(1, nblocks * per_sink[k]) * 2,), float("nan"), dtype=torch.float32, device="cuda") for k in range(world)]
+    for r in range(world):
+        g = make_gpu_chain(FDC, cfg)
+        halo, new = sharded.shard_input(x, cfg.hop, cfg.ovl, r * per, per)
+        g.seek(r * per, halo)
+        g.set_sinks([t.data_ptr() for t in sinks], owner, r)          # sink r is 'local': the others go through the staging slab + copies
+        d_in = torch.from_numpy(np.ascontiguousarray(new).view(np.float32).copy()).cuda()
+        g.work_device_sinks(d_in.data_ptr(), per, nblocks, r * per, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+    for k in range(world):
+        got = sinks[k].cpu().numpy().view(np.complex64)
+        off = 0
+        for i in [i for i, o in enumerate(owner) if o == k]:
+            n = nblocks * louts[i]
+            assert np.array_equal(got[off:off + n].view(np.uint32), whole[i].view(np.uint32)), (k, i)
+            off += n
+        assert off == nblocks * per_sink[k]
+    with pytest.raises(FDC.FDCError, match="set_sinks first"):
+        make_gpu_chain(FDC, cfg).work_device_sinks(d_in.data_ptr(), per, nblocks, 0)
+
+
 def test_empty_and_ragged_calls(FDC, ref):
     """edge cases of the work() contract: zero items, a context without channels (spectrum only), calls of one block, and
     outputs independent of how the same stream is cut into calls (the reference keeps history and counters across calls)"""

@@ -24,6 +24,7 @@ VARIANTS = {
     "four_step_from_4096": {"FDC_FWD_SPLIT": "4096"},
     "one_cta_per_sm": {"FDC_CTAS_PER_SM": "1"},
     "cluster_fused_forward": {"FDC_FUSED": "1"},
+    "sinks_forwarded_by_the_copy_engines": {"FDC_SINK_DMA": "1"},
 }
 
 
@@ -31,7 +32,7 @@ VARIANTS = {
 def test_variant_parity(name):
     env = dict(os.environ); env.update(VARIANTS[name])
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_chan.py"), "-m", "gpu", "-x", "-q",
-                        "-k", "golden or chain_matches or sliding or device_path or time_sharded or fft_vcc"],
+                        "-k", "golden or chain_matches or sliding or device_path or time_sharded or fft_vcc or sinks"],
                        env=env, capture_output=True, text=True, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
     assert " passed" in r.stdout

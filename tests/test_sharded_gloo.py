@@ -186,3 +186,19 @@ def test_sharded_activity_bookkeeping(world):
         assert len(want) >= 3, name
         assert got[name] == want, name
         assert got["group_" + name] == want, name
+
+
+def test_channel_owners_partition():
+    """FDC.sharded.channel_owners: contiguous runs, every channel owned, volumes balanced to within one channel"""
+    from FDC import sharded
+    rng = np.random.default_rng(3)
+    for trial in range(200):
+        n = int(rng.integers(1, 300)); world = int(rng.integers(1, 9))
+        louts = [int(v) for v in rng.choice([24, 48, 96, 192, 384, 768], size=n)]
+        owner, per_sink = sharded.channel_owners(louts, world)
+        assert len(owner) == n and owner == sorted(owner) and owner[0] >= 0 and owner[-1] < world
+        assert per_sink == [sum(lo for lo, o in zip(louts, owner) if o == k) for k in range(world)]
+        assert sum(per_sink) == sum(louts)
+        if n >= 4 * world:
+            assert max(per_sink) - min(per_sink) <= 2 * max(louts), (louts, world, per_sink)
+    assert sharded.channel_owners([384] * 256, 8)[1] == [12288] * 8
