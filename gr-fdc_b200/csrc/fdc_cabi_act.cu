@@ -53,7 +53,8 @@ struct ActEngine {
     int N; int dev; int verbose; std::string logfile;
     cudaStream_t s;
     DevBuf d_in, d_hist, d_tab, d_jobs, d_out, d_P, d_cnt, d_rr, d_ri, d_fi, d_pw;
-    PinBuf h_out, h_misc;
+    PinBuf h_res, h_misc;
+    PinBuf& h_out_buf() { return h_res; }
     /* buffered output blocks of one active channel (the reference's `data` deque of vectors).  Blocks extracted in the current
      * call are only REFERENCED (they sit in the call's result buffer); what is still buffered when the call ends is copied into
      * `data`.  A burst that is published in the call it was extracted in is therefore copied once, into the message arena. */
@@ -78,6 +79,13 @@ struct ActEngine {
                 if (out) { memcpy(out, segs[seg_head].first, sizeof(cfloat) * segs[seg_head].second); out += segs[seg_head].second; }
             }
             if (seg_head == segs.size()) { segs.clear(); seg_head = 0; }
+        }
+        /* the first nb buffered blocks as ONE run of the current call's result buffer, if they are one (null otherwise) */
+        const cfloat* view(size_t nb) const
+        {
+            if (nowned || nb == 0 || seg_head + nb > segs.size()) return 0;
+            for (size_t k = seg_head; k + 1 < seg_head + nb; k++) if (segs[k].first + segs[k].second != segs[k + 1].first) return 0;
+            return segs[seg_head].first;
         }
         /* end of the call: the result buffer is about to be reused */
         void keep()
@@ -105,6 +113,20 @@ struct ActEngine {
         void reset() { for (size_t i = 0; i < chunks.size(); i++) chunks[i]->used = 0; cur = 0; }
     } arena;
     void msg_clear() { msgs.clear(); arena.reset(); }
+    /* PDUs that are views of the pinned result buffer and have not been collected yet (no msg_clear since): copy them into the
+     * arena before the buffer is overwritten by the next call.  A consumer that drains the messages after every work() call --
+     * the GNU Radio wrapper publishes inside work(), the Python blocks dispatch after it -- never pays for this copy. */
+    void rescue_views()
+    {
+        const cfloat* lo = (const cfloat*)h_res.p; const cfloat* hi = lo ? lo + h_res.cap / sizeof(cfloat) : lo;
+        for (size_t i = 0; i < msgs.size(); i++) {
+            OutMsg& m = msgs[i];
+            if (!m.ptr || !m.n || m.ptr < lo || m.ptr >= hi) continue;
+            cfloat* keep = arena.alloc(m.n);
+            memcpy(keep, m.ptr, sizeof(cfloat) * m.n);
+            m.ptr = keep;
+        }
+    }
     std::map<long, Pending> pending;
     std::vector<OutMsg> msgs;
     long uid_counter;
@@ -125,11 +147,24 @@ struct ActEngine {
     /* run extraction jobs [j0, j1) of a call from the spectrum rows at d_rows (row `row0` of the call is d_rows[0]; the row before
      * it is `d_prev`, the saved history block when that is null); results land in h_out, job j at dst[j] (job order) */
     int extract(const float2* d_rows, const float2* d_prev, const std::vector<ActJob>& jobs, size_t j0, size_t j1, int row0,
-                std::vector<long>& dst, long* total_out, cudaStream_t st, float2* d_dst = 0)
+                std::vector<long>& dst, long* total_out, cudaStream_t st, float2* d_dst = 0, bool group_by_channel = false)
     {
         dst.assign(jobs.size(), 0);
         long total = 0;
-        for (size_t i = j0; i < j1; i++) { dst[i] = total; total += jobs[i].L - jobs[i].skip; }
+        if (group_by_channel && j1 > j0) {
+            /* results laid out channel by channel (uid), blocks of a channel in order: a burst that is published in the call it was
+             * extracted in is then ONE contiguous run of the result buffer and the PDU can point at it (no copy into the arena) */
+            long lo = jobs[j0].uid, hi = jobs[j0].uid;
+            for (size_t i = j0; i < j1; i++) { lo = std::min(lo, jobs[i].uid); hi = std::max(hi, jobs[i].uid); }
+            if (hi - lo < (long)(4 * (j1 - j0)) + 1024) {
+                std::vector<long> run((size_t)(hi - lo + 2), 0);
+                for (size_t i = j0; i < j1; i++) run[(size_t)(jobs[i].uid - lo) + 1] += jobs[i].L - jobs[i].skip;
+                for (size_t k = 1; k < run.size(); k++) run[k] += run[k - 1];
+                for (size_t i = j0; i < j1; i++) { long& r = run[(size_t)(jobs[i].uid - lo)]; dst[i] = r; r += jobs[i].L - jobs[i].skip; }
+                total = run[run.size() - 1];
+            } else group_by_channel = false;
+        }
+        if (!group_by_channel) for (size_t i = j0; i < j1; i++) { dst[i] = total; total += jobs[i].L - jobs[i].skip; }
         *total_out = total;
         if (j1 <= j0 || logic_only) return 0;
         /* group by IFFT length */
@@ -143,9 +178,10 @@ struct ActEngine {
             ej[k].row = j.row - row0; ej[k].start = j.start; ej[k].tab_off = (int)j.tab_off; ej[k].skip = j.skip; ej[k].dst_off = dst[order[k]];
             if (ej[k].row < -1) return fail("activity extract: job refers to a row this shard does not hold");
         }
+        if (!d_dst) rescue_views();
         /* d_dst: the caller's device buffer (possibly peer memory of the sink rank), results stay on the device */
         if (!d_jobs.upload(ej.data(), sizeof(ExtractJob) * ej.size()) ||
-            (!d_dst && (!d_out.reserve(sizeof(float2) * (size_t)total) || !h_out.reserve(sizeof(float2) * (size_t)total))))
+            (!d_dst && (!d_out.reserve(sizeof(float2) * (size_t)total) || !h_out_buf().reserve(sizeof(float2) * (size_t)total))))
             return cuda_fail(cudaGetLastError(), "activity extract buffers");
         size_t k = 0;
         while (k < order.size()) {
@@ -157,7 +193,7 @@ struct ActEngine {
             if (ce != cudaSuccess) return cuda_fail(ce, "activity extract launch");
             k = e;
         }
-        cudaError_t ce = d_dst ? cudaSuccess : cudaMemcpyAsync(h_out.p, d_out.p, sizeof(float2) * (size_t)total, cudaMemcpyDeviceToHost, st);
+        cudaError_t ce = d_dst ? cudaSuccess : cudaMemcpyAsync(h_out_buf().p, d_out.p, sizeof(float2) * (size_t)total, cudaMemcpyDeviceToHost, st);
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
         if (ce != cudaSuccess) return cuda_fail(ce, "activity extract D2H");
         return 0;
@@ -193,9 +229,14 @@ struct ActEngine {
                 OutMsg m; m.meta = *o.meta;
                 m.n = ntake * (size_t)o.blocksamples;
                 const bool wanted = m.meta.publish || !m.meta.filename.empty();
-                cfloat* dstp = (wanted && m.n) ? arena.alloc(m.n) : 0;
-                m.ptr = dstp;
-                q.take(ntake, (size_t)o.blocksamples, dstp);
+                /* only results in the engine's own pinned buffer may be handed out as views (shard_assemble replays the caller's memory) */
+                const cfloat* direct = (wanted && m.n && res == (const cfloat*)h_res.p) ? q.view(ntake) : 0;
+                if (direct) { m.ptr = direct; q.take(ntake, (size_t)o.blocksamples, 0); }       /* a view of the pinned result buffer */
+                else {
+                    cfloat* dstp = (wanted && m.n) ? arena.alloc(m.n) : 0;
+                    m.ptr = dstp;
+                    q.take(ntake, (size_t)o.blocksamples, dstp);
+                }
                 if (!m.meta.filename.empty()) {
                     FILE* fh = fopen(m.meta.filename.c_str(), "wb");
                     if (!fh) std::cerr << "Cannot write to file " << m.meta.filename << std::endl;
@@ -211,8 +252,8 @@ struct ActEngine {
     int finish(const float2* d_rows, std::vector<ActJob>& jobs, const std::vector<ActOp>& ops, cudaStream_t st)
     {
         std::vector<long> dst; long total = 0;
-        if (extract(d_rows, 0, jobs, 0, jobs.size(), 0, dst, &total, st)) return -1;
-        replay((const cfloat*)h_out.p, dst, jobs, ops);
+        if (extract(d_rows, 0, jobs, 0, jobs.size(), 0, dst, &total, st, 0, true)) return -1;
+        replay((const cfloat*)h_out_buf().p, dst, jobs, ops);
         return 0;
     }
 
@@ -265,7 +306,7 @@ struct ActEngine {
         std::vector<long> dst; long total = 0;
         if (extract((const float2*)d_rows, (const float2*)d_prev, sh.jobs, (size_t)sh.job_first[(size_t)first_row],
                     (size_t)sh.job_first[(size_t)(first_row + nrows)], first_row, dst, &total, st)) return -1;
-        if (!logic_only && total > 0 && out_host) memcpy(out_host, h_out.p, sizeof(float2) * (size_t)total);
+        if (!logic_only && total > 0 && out_host) memcpy(out_host, h_out_buf().p, sizeof(float2) * (size_t)total);
         return total;
     }
     long shard_extract_device(int first_row, int nrows, const void* d_rows, const void* d_prev, void* stream, void* d_dst)
@@ -283,13 +324,14 @@ struct ActEngine {
         OnDevice on_dev(dev);
         cudaStream_t st = stream ? (cudaStream_t)stream : s;
         if (nsamples > 0) {
-            if (!h_out.reserve(sizeof(float2) * (size_t)nsamples)) return cuda_fail(cudaGetLastError(), "assemble buffer");
-            cudaError_t ce = cudaMemcpyAsync(h_out.p, d_results, sizeof(float2) * (size_t)nsamples, cudaMemcpyDeviceToHost, st);
+            rescue_views();
+            if (!h_out_buf().reserve(sizeof(float2) * (size_t)nsamples)) return cuda_fail(cudaGetLastError(), "assemble buffer");
+            cudaError_t ce = cudaMemcpyAsync(h_out_buf().p, d_results, sizeof(float2) * (size_t)nsamples, cudaMemcpyDeviceToHost, st);
             if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
             if (ce != cudaSuccess) return cuda_fail(ce, "assemble D2H");
         }
         static const float2 none = {0.0f, 0.0f};           /* a null result pointer means "drop the call" to shard_assemble */
-        return shard_assemble(h_out.p ? h_out.p : (const void*)&none, nsamples);
+        return shard_assemble(h_out_buf().p ? h_out_buf().p : (const void*)&none, nsamples);
     }
     int shard_assemble(const void* results, long nsamples)
     {
@@ -593,9 +635,9 @@ int fdc_segdet_work_device(fdc_segdet* b, int n, const void* d_in, void* stream)
     for (int i = 0; i < n; i++) { b->st.block(i, edges[(size_t)i], b->blockcount, b->e.uid_counter, jobs, ops); b->blockcount++; }
     pc.lap();
     std::vector<long> dst; long total = 0;
-    if (b->e.extract(rows, 0, jobs, 0, jobs.size(), 0, dst, &total, st)) return -1;
+    if (b->e.extract(rows, 0, jobs, 0, jobs.size(), 0, dst, &total, st, 0, true)) return -1;
     pc.lap();
-    b->e.replay((const cfloat*)b->e.h_out.p, dst, jobs, ops);
+    b->e.replay((const cfloat*)b->e.h_out_buf().p, dst, jobs, ops);
     pc.lap();
     if (act_timing())
         fprintf(stderr, "SegmentDetection %d blocks: measure %.3f ms, bookkeeping %.3f ms, extract %.3f ms (%zu jobs, %ld samples), replay %.3f ms (%zu msgs)\n",

@@ -192,7 +192,9 @@ typedef struct {
     long blockstart, blockend;
     long vectorstart, vectorend;   /* -1: key absent (PowerActivationChannel) */
     long nsamples;
-    const float* data;     /* nsamples complex floats, owned by the block until the next msg_clear/destroy */
+    const float* data;     /* nsamples complex floats, owned by the block until the next msg_clear / destroy.  A burst extracted and
+                            * published in one call is a view of that call's pinned result buffer (no copy); re-fetch the messages
+                            * (msg_get) after a later work() call if they were not cleared: uncollected views are moved then */
 } fdc_msg;
 
 /* FDC.PowerActivationChannel, include/FDC/PowerActivationChannel.h:49, lib/PowerActivationChannel_impl.cc */
