@@ -241,13 +241,19 @@ def run_cfg3_sharded(args, rank, world, local):
     sd = [FDC.SegmentDetection(*sd_args(i, a, b)) for i, (a, b) in enumerate(segs)]
     pc = [FDC.PowerActivationChannel(N, f, bw, R, 6.0, 128, 1, True, False, "", 0, i) for i, (f, bw) in enumerate(pac)]
     pool = ThreadPoolExecutor(max_workers=max(1, min(len(sd) + len(pc), (os.cpu_count() or 1) // world)))
-    sink = None
-    if os.environ.get("FDC_BENCH_NCCL_GATHER", "0") != "1":
+    sink = None; owners = None
+    mode = os.environ.get("FDC_BENCH_ACT_SINK", "owners")          # owners | rank0 | nccl
+    if mode == "owners":
+        try:      # block instances dealt out over the ranks: every rank receives and assembles the bursts of the instances it owns
+            owners = sharded.PeerBuffers(256 << 20, rank, world)
+        except Exception as exc:
+            sys.stderr.write("peer buffers unavailable (%s), using the NCCL gather\n" % exc)
+    elif mode == "rank0":
         try:      # the gather fused into the extract kernel: burst samples are stored straight into rank 0's buffer over NVLink
             sink = sharded.PeerSink(0, 0, rank, world, dst=0, nbytes=256 << 20)
         except Exception as exc:        # no peer access on this box: NCCL gather
             sys.stderr.write("peer sink unavailable (%s), using the NCCL gather\n" % exc)
-    grp = sharded.ShardedActivityGroup(sd + pc, rank, world, dst=0, pool=pool, sink=sink, arrays=True)
+    grp = sharded.ShardedActivityGroup(sd + pc, rank, world, dst=0, pool=pool, sink=sink, arrays=True, owners=owners)
     d_in = torch.from_numpy(x.view(np.float32).copy()).cuda(local)
     d_spec = torch.empty(nloc * N * 2, dtype=torch.float32, device=d_in.device)
     own = d_spec.data_ptr() + 8 * N * (first[rank] - lo)
@@ -259,8 +265,9 @@ def run_cfg3_sharded(args, rank, world, local):
         front.sync()
         res = grp.work(total, own, prev)
         if res is not None:
-            for recs, data, offsets in res:
-                stats["pdus"] += int(recs.size); stats["samples"] += int(data.size)
+            for r_ in res:
+                if r_ is not None:
+                    stats["pdus"] += int(r_[0].size); stats["samples"] += int(r_[1].size)
 
     for _ in range(W):
         step()
@@ -277,6 +284,9 @@ def run_cfg3_sharded(args, rank, world, local):
     dt = float(dt.item())
     launches = torch.tensor([int(L.fdc_launch_count() - l0)], dtype=torch.int64, device=d_in.device)
     dist.all_reduce(launches)
+    st = torch.tensor([stats["pdus"], stats["samples"]], dtype=torch.int64, device=d_in.device)
+    dist.all_reduce(st)                                  # the PDUs are published on the ranks that own the block instances
+    stats["pdus"], stats["samples"] = int(st[0].item()), int(st[1].item())
     sampler.stop_flag = True; sampler.join()
     if rank == 0:
         value = K * total * hop / dt / 1e6
@@ -289,7 +299,9 @@ def run_cfg3_sharded(args, rank, world, local):
                            "pdus_per_step": stats["pdus"] / K, "burst_samples_per_step": stats["samples"] / K,
                            "sink_phase_ms_per_step": {k: round(v / K * 1e3, 3) for k, v in grp.phase_seconds.items()},
                            "exchange": "all-gather of the detection records (a few bytes per block); burst samples " +
-                                       ("stored by the extract kernels straight into rank 0's buffer (CUDA IPC peer memory), then a barrier" if sink is not None
+                                       ("stored by the extract kernels straight into the buffer of the rank that owns the block instance (instance i -> rank i mod N, "
+                                        "CUDA IPC peer memory), then a barrier; every rank assembles the PDUs of its instances" if owners is not None else
+                                        "stored by the extract kernels straight into rank 0's buffer (CUDA IPC peer memory), then a barrier" if sink is not None
                                         else "gathered to rank 0 (NCCL)"),
                            "timing": "wall clock, max over ranks (host state machines are part of the path), barrier + device synchronise on both sides",
                            "l2_policy": "input %.0f MB per step and GPU" % (8e-6 * nb * hop)},

@@ -6,6 +6,7 @@
  *   4. replay of the ops on the extracted blocks -> PDUs / files in the reference's order (host) */
 #include "fdc_cabi_internal.h"
 #include "fdc_act_state.h"
+#include "fdc_host.h"
 #include <algorithm>
 #include <cfloat>
 #include <cstdio>
@@ -366,13 +367,18 @@ struct ActEngine {
     }
     long msg_copy_data(float* out) const
     {
-        long total = 0;
+        long total = 0; size_t big = 0;
         for (size_t i = 0; i < msgs.size(); i++) {
             const OutMsg& m = msgs[i];
             if (m.logic_samples >= 0 || m.n == 0) continue;
-            if (out) memcpy(out + 2 * total, m.ptr, sizeof(cfloat) * m.n);
+            if (out) {
+                /* tens of MB per call on a busy segment: the copy pool's streaming copies instead of one thread's memcpy */
+                if (m.n >= 2048) { copy_pool().submit(out + 2 * total, m.ptr, sizeof(cfloat) * m.n); big++; }
+                else memcpy(out + 2 * total, m.ptr, sizeof(cfloat) * m.n);
+            }
             total += (long)m.n;
         }
+        if (big) copy_pool().wait();
         return total;
     }
     int msg_get(int i, fdc_msg* out) const

@@ -195,6 +195,41 @@ class ChannelSinks(object):
         self.bases, self._local = [], None
 
 
+class PeerBuffers(object):
+    """One plain device buffer per rank, every rank mapping all of them (CUDA IPC, peer access over NVLink): ptrs[r] is rank r's
+    buffer as seen from this GPU.  Used by ShardedActivityGroup to deal the activity-gated block instances out over the ranks:
+    rank r receives the burst samples of the instances it owns and assembles their PDUs."""
+
+    def __init__(self, nbytes, rank, world, group=None):
+        import ctypes as C
+        import torch.distributed as dist
+        from ._cabi import lib, check, handle
+        self.rank, self.world, self.nbytes = rank, world, int(nbytes)
+        self._local = lib().fdc_dev_alloc(self.nbytes)
+        if not self._local:
+            raise RuntimeError("peer buffer allocation failed")
+        h = C.create_string_buffer(64)
+        check(lib().fdc_ipc_export(C.c_void_p(self._local), h), "fdc_ipc_export")
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(h.raw), group=group)
+        self._hbufs, self.ptrs = [], []
+        for r in range(world):
+            if r == rank:
+                self.ptrs.append(self._local)
+            else:
+                hb = C.create_string_buffer(handles[r], 64); self._hbufs.append(hb)
+                self.ptrs.append(handle(lib().fdc_ipc_open(hb), "fdc_ipc_open").value)
+
+    def close(self):
+        from ._cabi import lib
+        for r, p in enumerate(self.ptrs):
+            if r != self.rank and p:
+                lib().fdc_ipc_close(p)
+        if self._local:
+            lib().fdc_dev_free(self._local)
+        self.ptrs, self._local = [], None
+
+
 class ShardedActivity(object):
     """An activity-gated block (PowerActivationChannel, SegmentDetection, activity_detection_channelizer_vcm) on a
     time-sharded stream.  The reference blocks carry state from block to block (lib/PowerActivationChannel_impl.cc:137-177,
@@ -224,12 +259,17 @@ class ShardedActivityGroup(object):
     blocks' samples per call.  `pool` (a concurrent.futures executor) runs the per-block local phases concurrently, as
     GNU Radio's thread-per-block scheduler would; the collectives are issued from the calling thread only."""
 
-    def __init__(self, blocks, rank, world, dst=0, group=None, pool=None, sink=None, arrays=False):
+    def __init__(self, blocks, rank, world, dst=0, group=None, pool=None, sink=None, arrays=False, owners=None):
         """sink: a PeerSink(nbytes=...) made by all ranks -- the extract kernels then store the burst samples straight into
         the sink rank's buffer (peer memory over NVLink) and the gather of the samples is a barrier; calls whose samples do
-        not fit the buffer fall back to the NCCL gather."""
+        not fit the buffer fall back to the NCCL gather.
+        owners: a PeerBuffers made by all ranks -- block instance i is then OWNED by rank i % world: the extract kernels of all
+        ranks store instance i's burst samples into its owner's buffer and the owner assembles and publishes its PDUs (the PDU
+        assembly, serial on one sink rank otherwise, is spread over the ranks).  work() returns the messages of the owned
+        instances and None for the others."""
         self.blocks, self.rank, self.world, self.dst, self.group = list(blocks), int(rank), int(world), int(dst), group
         self.sink = sink
+        self.owners = owners
         self.arrays = bool(arrays)          # work() returns messages_arrays(reuse=True) per block instead of lists of dicts
         self._map = pool.map if pool is not None else (lambda f, it: list(map(f, it)))
         self.phase_seconds = {}                 # wall clock per phase, accumulated over calls (for measurements)
@@ -254,7 +294,28 @@ class ShardedActivityGroup(object):
         total = [sum(sz) for sz in sizes]
         t.append(time.perf_counter())
         out = None
-        if self.sink is not None and 8 * sum(total) <= self.sink.nbytes:
+        own_of = [i % self.world for i in idx]
+        per_owner = [sum(total[i] for i in idx if own_of[i] == r) for r in range(self.world)]
+        if self.owners is not None and 8 * max(per_owner + [0]) <= self.owners.nbytes:
+            # instance-major layout in each owner's buffer, an instance's ranks in rank order: what shard_assemble wants
+            base, run = [], [0] * self.world
+            for i in idx:
+                base.append(run[own_of[i]]); run[own_of[i]] += total[i]
+            list(self._map(lambda i: self.blocks[i].shard_extract_device(first[me], count[me], d_rows, d_prev,
+                                                                         self.owners.ptrs[own_of[i]] + 8 * (base[i] + sum(sizes[i][:me])), stream), idx))
+            t.append(time.perf_counter())
+            dist.barrier(group=self.group)                                          # every rank's stores have landed
+            t.append(time.perf_counter())
+
+            def assemble_own(i):
+                b = self.blocks[i]
+                if own_of[i] != me:
+                    b.shard_assemble(None)
+                    return None
+                b.shard_assemble_device(self.owners.ptrs[me] + 8 * base[i], total[i], stream)
+                return b.messages_arrays(reuse=True) if self.arrays else b.messages()
+            out = list(self._map(assemble_own, idx))
+        elif self.sink is not None and 8 * sum(total) <= self.sink.nbytes:
             # block-major layout in the sink's buffer, a block's ranks in rank order: what shard_assemble wants
             base = np.concatenate([[0], np.cumsum(total)]).tolist()
             list(self._map(lambda i: self.blocks[i].shard_extract_device(first[me], count[me], d_rows, d_prev,
