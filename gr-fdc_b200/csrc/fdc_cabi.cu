@@ -145,8 +145,7 @@ struct fdc_chan {
      * that the tail of one chunk's kernels overlaps the head of the next chunk's */
     enum { NWORK = 4 };
     cudaStream_t ws[NWORK];
-    DevBuf w_spec[NWORK], w_mid[NWORK], w_ring[NWORK];   /* w_ring: mid | spectrum in one allocation when L2 persistence is on */
-    size_t l2_window[NWORK];
+    DevBuf w_spec[NWORK], w_mid[NWORK];
     cudaEvent_t ev_start, ev_done[NWORK];
     cudaEvent_t ev_hist; bool hist_pending; cudaStream_t hist_stream;     /* the history buffer is written asynchronously at the end of a device call */
     /* host path: NSLOT pipelined chunk slots */
@@ -163,7 +162,7 @@ struct fdc_chan {
     fdc_chan() : nsinks(0), tw4(0), stream(0), ev_start(0), ev_hist(0), hist_pending(false), hist_stream(0), host_chunk(0), prof(false)
     {
         for (int i = 0; i < NSLOT; i++) { hs[i] = 0; h_done[i] = 0; }
-        for (int i = 0; i < NWORK; i++) { ws[i] = 0; ev_done[i] = 0; l2_window[i] = 0; cs[i] = 0; ev_x[i] = 0; ev_c[i] = 0; copies_pending[i] = false; }
+        for (int i = 0; i < NWORK; i++) { ws[i] = 0; ev_done[i] = 0; cs[i] = 0; ev_x[i] = 0; ev_c[i] = 0; copies_pending[i] = false; }
     }
     cudaEvent_t ev()
     {
@@ -461,26 +460,9 @@ static int chan_work_device(fdc_chan* c, const void* d_in_v, long nblocks, void*
     cudaStream_t wk[fdc_chan::NWORK];
     for (int i = 0; i < fdc_chan::NWORK; i++) wk[i] = nw == 1 ? s : c->ws[i];
     const long ring = std::min(nblocks, c->chunk_blocks);
-    const bool l2pin = tuning().l2_persist_mb > 0 && !d_spectrum && c->big;
     float2* ring_spec[fdc_chan::NWORK]; float2* ring_mid[fdc_chan::NWORK];
     for (int i = 0; i < nw; i++) {
         const size_t rb = sizeof(float2) * (size_t)ring * c->N;
-        if (l2pin) {
-            /* experiment: keep the K1 -> K2 hand-over (intermediate + spectrum rings) in the persisting part of L2 */
-            if (!c->w_ring[i].reserve(2 * rb)) return cuda_fail(cudaGetLastError(), "hand-over ring");
-            ring_mid[i] = (float2*)c->w_ring[i].p; ring_spec[i] = ring_mid[i] + (size_t)ring * c->N;
-            if (c->l2_window[i] != 2 * rb) {
-                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)tuning().l2_persist_mb << 20);
-                cudaStreamAttrValue av; memset(&av, 0, sizeof(av));
-                av.accessPolicyWindow.base_ptr = c->w_ring[i].p; av.accessPolicyWindow.num_bytes = 2 * rb;
-                av.accessPolicyWindow.hitRatio = 1.0f; av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-                av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-                const cudaError_t pe = cudaStreamSetAttribute(wk[i], cudaStreamAttributeAccessPolicyWindow, &av);
-                if (pe != cudaSuccess) return cuda_fail(pe, "L2 access policy window");
-                c->l2_window[i] = 2 * rb;
-            }
-            continue;
-        }
         if (!d_spectrum && !c->w_spec[i].reserve(rb)) return cuda_fail(cudaGetLastError(), "spectrum ring");
         if (c->big && !c->w_mid[i].reserve(rb)) return cuda_fail(cudaGetLastError(), "four-step intermediate");
         ring_spec[i] = (float2*)c->w_spec[i].p; ring_mid[i] = (float2*)c->w_mid[i].p;

@@ -294,38 +294,6 @@ template <int L, int B> struct ExtractStorer {
         if (t * NS >= c.skip) c.dst[t * NS] = UNIT ? v : cscale(v, c.gain);
     }
 };
-/* The same extract fed from a shared-memory stage [signal][l] that the TMA engine fills one tile ahead
- * (fdc_tma.cuh): src(s) is the global address of signal s's slice (16-byte aligned: even f), fetch reads the stage. */
-template <int L, int B> struct ExtractStageLoader {
-    struct Ctx { const float2* x; const float2* w; };
-    static constexpr bool HAS_FINISH = true;
-    const ExtractParams& p; int ytile; long b; unsigned bphase; const float2* stage;
-    FDC_HD int signal(int batch) const { const int s = ytile * B + batch; return s >= p.nsel ? p.nsel - 1 : s; }
-    FDC_HD const float2* src(int batch) const { return p.spec + (b * p.spec_stride + p.chans[signal(batch)].f); }
-    FDC_HD Ctx begin(int batch, int j) const
-    {
-        Ctx c;
-        const ChanDev& ch = p.chans[signal(batch)];
-        const unsigned phase = phase_mod(p, bphase * (unsigned)ch.shift);
-        c.x = stage + (batch * L + j);
-        c.w = p.tables + (ch.tab_off + (long)phase * L + j);
-        return c;
-    }
-    template <int R, int STRIDE> FDC_HD float2 fetch(const Ctx& c, int t) const { return c.x[((t + R / 2) % R) * STRIDE]; }
-    template <int R, int STRIDE> FDC_HD float2 finish(const Ctx& c, int t, float2 raw) const
-    {
-        return cmul(raw, fdc_ldg(c.w + ((t + R / 2) % R) * STRIDE));
-    }
-};
-template <int L, int B> struct ExtractStageTiles {
-    const ExtractParams& p; const float2* stage;
-    FDC_HD int ninner() const { return p.ny; }
-    FDC_HD ExtractStageLoader<L, B> loader(TilePos t) const
-    {
-        return ExtractStageLoader<L, B>{p, t.inner, (long)t.outer, phase_mod(p, (unsigned)p.glob_phase0 + (unsigned)t.outer), stage};
-    }
-    FDC_HD ExtractStorer<L, B> storer(TilePos t) const { return ExtractStorer<L, B>{p, t.inner, (long)t.outer}; }
-};
 template <int L, int B> struct ExtractTiles {           /* tile = block * ny + channel tile */
     const ExtractParams& p;
     FDC_HD int ninner() const { return p.ny; }

@@ -49,18 +49,6 @@ k_extract32(const ExtractParams p, const float2* __restrict__ tw, long ntiles)
 {
     tile_kernel_body<TileFFT<L, B, -1, false, false, 32>, false>(ExtractTiles<L, B>{p}, tw, ntiles);
 }
-/* the same with the next tile's slices staged in shared memory by the TMA engine (cp.async.bulk + mbarrier) while the
- * current tile is transformed: 3 CTAs per SM (the stage costs 32 KB), loads off the critical path */
-template <int L, int B>
-__global__ void __launch_bounds__(128, 3)
-k_extract32t(const ExtractParams p, const float2* __restrict__ tw, long ntiles)
-{
-    typedef TileFFT<L, B, -1, false, false, 32> ENG;
-    float2* smem = reinterpret_cast<float2*>(fdc_smem_raw);
-    float2* stage = smem + ((ENG::SMEM_ELEMS + tw_smem_elems(ENG::L, ENG::E) + 1) & ~1);          /* 16-byte aligned */
-    uint64_t* bar = reinterpret_cast<uint64_t*>(stage + L * B);
-    tile_fft_loop_staged<ENG>(smem, stage, bar, tw, ExtractStageTiles<L, B>{p, stage}, (long)blockIdx.x, (long)gridDim.x, ntiles);
-}
 template <int L, int B>
 __global__ void __launch_bounds__((TileFFT<L, B, -1, false, false>::T), min_ctas(TileFFT<L, B, -1, false, false>::T, false, L))
 k_jobs(const JobParams p, const float2* __restrict__ tw, long ntiles)
@@ -136,23 +124,9 @@ template <int L> static cudaError_t go_extract32(const ExtractParams& p0, cudaSt
     FDC_CHECK(persistent_grid(k_extract32<L, B>, ENG::T, tile_smem_bytes<ENG>(), ntiles, 1, &grid, tuning().ctas_ext));
     return launch_tile_kernel(k_extract32<L, B>, grid, ENG::T, tile_smem_bytes<ENG>(), s, p, twiddle_table(L, 32), ntiles);
 }
-template <int L> static cudaError_t go_extract32t(const ExtractParams& p0, cudaStream_t s)
-{
-    constexpr int B = 4096 / L;
-    typedef TileFFT<L, B, -1, false, false, 32> ENG;
-    constexpr size_t smem = sizeof(float2) * (size_t)(((ENG::SMEM_ELEMS + tw_smem_elems(ENG::L, ENG::E) + 1) & ~1) + L * B) + 16;
-    ExtractParams p = p0;
-    p.ny = (p.nsel + B - 1) / B;
-    const long ntiles = p.nb * p.ny;
-    unsigned grid = 1;
-    FDC_CHECK(persistent_grid(k_extract32t<L, B>, ENG::T, smem, ntiles, 1, &grid, tuning().ctas_ext));
-    return launch_tile_kernel(k_extract32t<L, B>, grid, ENG::T, smem, s, p, twiddle_table(L, 32), ntiles);
-}
 template <int L> static cudaError_t go_extract_pf(const ExtractParams& p, cudaStream_t s)
 {
     if constexpr (L == 512 || L == 1024) {
-        /* bulk copies need 16-byte aligned slices: the caller says whether every slice of the group starts on an even bin */
-        if (tuning().extract_e32 > 1 && p.tma_ok) return go_extract32t<L>(p, s);
         if (tuning().extract_e32) return go_extract32<L>(p, s);
     }
     if constexpr (L >= 64 && L <= 2048) {

@@ -23,7 +23,7 @@ static int env_int(const char* name, int dflt)
 }
 const Tuning& tuning()
 {
-    static const Tuning t = { env_int("FDC_PREFETCH", 1), env_int("FDC_CTAS_PER_SM", 0), env_int("FDC_STREAMS", 3), env_int("FDC_EXTRACT_E8", -1), env_int("FDC_CTAS_FWD", 0), env_int("FDC_CTAS_EXT", 0), env_int("FDC_PDL", 1), env_int("FDC_FWD_SPLIT", 32768), env_int("FDC_HOST_CHUNK_MB", 8), env_int("FDC_EXTRACT_E32", 1), env_int("FDC_FWD_E32", 1), env_int("FDC_L2_PERSIST_MB", 0), env_int("FDC_L2PF", 1), env_int("FDC_PACK", 1), env_int("FDC_FUSED", 0), env_int("FDC_HOST_STAGING", 1), env_int("FDC_SINK_DMA", 0) };
+    static const Tuning t = { env_int("FDC_PREFETCH", 1), env_int("FDC_CTAS_PER_SM", 0), env_int("FDC_STREAMS", 3), env_int("FDC_EXTRACT_E8", -1), env_int("FDC_CTAS_FWD", 0), env_int("FDC_CTAS_EXT", 0), env_int("FDC_PDL", 1), env_int("FDC_FWD_SPLIT", 32768), env_int("FDC_HOST_CHUNK_MB", 8), env_int("FDC_EXTRACT_E32", 1), env_int("FDC_FWD_E32", 1), env_int("FDC_L2PF", 1), env_int("FDC_PACK", 1), env_int("FDC_FUSED", 0), env_int("FDC_HOST_STAGING", 1), env_int("FDC_SINK_DMA", 0) };
     return t;
 }
 
@@ -180,23 +180,36 @@ cudaError_t launch_scale(const float2* in, float2* out, long n, float k, cudaStr
 }
 
 /* ---- K3 ------------------------------------------------------------------------------------------ */
-/* one thread per (block, power bin): D sequential |x|^2 additions, the order of the generic VOLK accumulator.
- * A warp covers 32 adjacent power bins = 32*D contiguous spectrum bins; the tile is staged through shared
- * memory with coalesced loads so that HBM/L2 sees full lines. */
+/* P[b][i] = sum_{k < D} |X_b[start + i D + k]|^2 in the order of the generic VOLK accumulator (k ascending, every product and
+ * sum rounded on its own).  A warp owns 32 adjacent power bins = 32 D contiguous spectrum bins and walks them in 32 x 32 tiles:
+ * for every bin row the 32 lanes load 32 consecutive spectrum bins (one coalesced 256-byte request), square them and park the
+ * 32 x 32 powers in shared memory; then lane r adds row r's 32 values sequentially.  |x|^2 of an element does not depend on
+ * the order, the running sum keeps it: bit-identical to one thread walking its D bins, without its stride-D loads. */
 __global__ void __launch_bounds__(256) k_group_power(const float2* __restrict__ spec, long spec_stride, int start, int D,
                                                      int M, int mean, float* __restrict__ P)
 {
+    __shared__ float tile[8][32][33];
     const long b = blockIdx.y;
     const float2* row = spec + b * spec_stride + start;
     const float norm = 1.0f / (float)D;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
-        const float2* x = row + (long)i * D;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i0 = (blockIdx.x * 8 + warp) * 32; i0 < M; i0 += gridDim.x * 256) {
+        const int rows = M - i0 < 32 ? M - i0 : 32;
         float acc = 0.0f;
-        for (int k = 0; k < D; k++) {
-            const float2 v = __ldg(x + k);
-            acc = fdc_add(acc, fdc_add(fdc_mul(v.x, v.x), fdc_mul(v.y, v.y)));
+        for (int k0 = 0; k0 < D; k0 += 32) {
+            const int kn = D - k0 < 32 ? D - k0 : 32;
+            for (int r = 0; r < rows; r++) {
+                if (lane < kn) {
+                    const float2 v = __ldg(row + ((long)(i0 + r) * D + k0 + lane));
+                    tile[warp][r][lane] = fdc_add(fdc_mul(v.x, v.x), fdc_mul(v.y, v.y));
+                }
+            }
+            __syncwarp();
+            if (lane < rows)
+                for (int k = 0; k < kn; k++) acc = fdc_add(acc, tile[warp][lane][k]);
+            __syncwarp();
         }
-        P[b * M + i] = mean ? fdc_mul(acc, norm) : acc;
+        if (lane < rows) P[b * M + i0 + lane] = mean ? fdc_mul(acc, norm) : acc;
     }
 }
 cudaError_t launch_group_power(const float2* spec, long spec_stride, long nblocks, int start, int D, int M, int mean,
@@ -205,7 +218,7 @@ cudaError_t launch_group_power(const float2* spec, long spec_stride, long nblock
     if (nblocks <= 0 || M <= 0) return cudaSuccess;
     for (long b0 = 0; b0 < nblocks; b0 += 65535) {
         const long nb = nblocks - b0 < 65535 ? nblocks - b0 : 65535;
-        int gx = (M + 255) / 256; if (gx > 1024) gx = 1024;
+        int gx = (M + 255) / 256; if (gx > 1024) gx = 1024;      /* a CTA takes 8 x 32 power bins per round */
         k_group_power<<<dim3((unsigned)gx, (unsigned)nb), 256, 0, s>>>(spec + b0 * spec_stride, spec_stride, start, D, M, mean,
                                                                       P + b0 * M);
         count_launch();
@@ -265,25 +278,34 @@ cudaError_t launch_edges(const float* P, long nblocks, int M, float T, float inv
     return cudaGetLastError();
 }
 
-/* one thread per block: strictly sequential sum over the measurement band (lib/PowerActivationChannel_impl.cc:289-291).
- * std::real(x * conj(x)) is a*a - b*(-b): two rounded products and one rounded sum. */
+/* pwr[b] = sum over the measurement band [m0, m1), strictly sequential (lib/PowerActivationChannel_impl.cc:289-291);
+ * std::real(x * conj(x)) is a*a - b*(-b): two rounded products and one rounded sum per element.  One warp per block: the lanes
+ * load 32 consecutive bins at a time (coalesced, the next chunk in flight while the current one is added) and the running sum
+ * takes the 32 element powers in bin order through shuffles -- the same additions in the same order as a single thread, without
+ * its chain of dependent, uncoalesced loads (a scheduler hands over 1 - 8 blocks per call: latency is what counts). */
 __global__ void __launch_bounds__(128) k_band_power(const float2* __restrict__ spec, long spec_stride, long nblocks, int m0,
                                                     int m1, float* __restrict__ pwr)
 {
-    const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long b = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (b >= nblocks) return;
+    const int lane = threadIdx.x & 31;
     const float2* x = spec + b * spec_stride;
     float acc = 0.0f;
-    for (int i = m0; i < m1; i++) {
-        const float2 v = __ldg(x + i);
-        acc = fdc_add(acc, fdc_sub(fdc_mul(v.x, v.x), fdc_mul(v.y, -v.y)));
+    float2 nx = make_float2(0.f, 0.f);
+    if (m0 + lane < m1) nx = __ldg(x + m0 + lane);
+    for (int i0 = m0; i0 < m1; i0 += 32) {
+        const float2 v = nx;
+        if (i0 + 32 + lane < m1) nx = __ldg(x + i0 + 32 + lane);
+        const float p = fdc_sub(fdc_mul(v.x, v.x), fdc_mul(v.y, -v.y));
+        const int n = m1 - i0 < 32 ? m1 - i0 : 32;
+        for (int j = 0; j < n; j++) acc = fdc_add(acc, __shfl_sync(0xffffffffu, p, j));
     }
-    pwr[b] = acc;
+    if (lane == 0) pwr[b] = acc;
 }
 cudaError_t launch_band_power(const float2* spec, long spec_stride, long nblocks, int m0, int m1, float* pwr, cudaStream_t s)
 {
     if (nblocks <= 0) return cudaSuccess;
-    k_band_power<<<(unsigned)((nblocks + 127) / 128), 128, 0, s>>>(spec, spec_stride, nblocks, m0, m1, pwr);
+    k_band_power<<<(unsigned)((nblocks + 3) / 4), 128, 0, s>>>(spec, spec_stride, nblocks, m0, m1, pwr);       /* 4 warps = 4 blocks per CTA */
     count_launch();
     return cudaGetLastError();
 }

@@ -340,54 +340,6 @@ __device__ __forceinline__ void tile_fft_loop(float2* smem, const float2* tw_glo
         if (ENG::NP > 1) __syncthreads();          /* the exchange buffer is reused by the next tile */
     }
 }
-/* Persistent tile loop with a TMA-staged input tile: Tiles::loader(pos).src(s) names the B contiguous slices of a tile;
- * one thread issues their bulk copies into `stage` for tile i+1 right after every thread has taken tile i out of the stage
- * (one barrier), so the copies run during tile i's butterflies.  No registers are spent on the prefetch. */
-template <class ENG, class Tiles>
-__device__ __forceinline__ void tile_fft_loop_staged(float2* smem, float2* stage, uint64_t* bar, const float2* tw_global, const Tiles& tiles,
-                                                     long first, long stride, long ntiles)
-{
-    constexpr bool TWS = tw_in_smem(ENG::L, ENG::E);
-    constexpr uint32_t SLICE_BYTES = sizeof(float2) * ENG::L;
-    const float2* tw = tw_global;
-    cudaTriggerProgrammaticLaunchCompletion();
-    if (threadIdx.x == 0) mbar_init(bar, 1);
-    if constexpr (TWS) {
-        float2* tws = smem + ENG::SMEM_ELEMS;
-        for (int i = threadIdx.x; i < ENG::TWSIZE; i += ENG::T) tws[i] = tw_global[i];
-        tw = tws;
-    }
-    __syncthreads();
-    cudaGridDependencySynchronize();
-    if (first >= ntiles) return;
-    const int ninner = tiles.ninner();
-    const TilePos step = tile_split(stride, ninner);
-    TilePos pos = tile_split(first, ninner);
-    if (threadIdx.x == 0) {
-        mbar_arrive_expect_tx(bar, SLICE_BYTES * ENG::B);
-        const auto ld = tiles.loader(pos);
-        for (int s = 0; s < ENG::B; s++) tma_bulk_g2s(stage + s * ENG::L, ld.src(s), SLICE_BYTES, bar);
-    }
-    uint32_t parity = 0;
-    for (long tile = first;;) {
-        const long next = tile + stride;
-        const TilePos npos = tile_advance(pos, step, ninner);
-        float2 v[ENG::E];
-        mbar_wait(bar, parity); parity ^= 1u;
-        ENG::fetch(threadIdx.x, v, tiles.loader(pos));
-        ENG::finish(threadIdx.x, v, tiles.loader(pos));
-        __syncthreads();                                   /* the stage is free again */
-        if (next < ntiles && threadIdx.x == 0) {
-            mbar_arrive_expect_tx(bar, SLICE_BYTES * ENG::B);
-            const auto ld = tiles.loader(npos);
-            for (int s = 0; s < ENG::B; s++) tma_bulk_g2s(stage + s * ENG::L, ld.src(s), SLICE_BYTES, bar);
-        }
-        tile_fft_from<ENG, 0, TWS>(v, smem, tw, tiles.storer(pos));
-        if (next >= ntiles) break;
-        tile = next; pos = npos;
-        if (ENG::NP > 1) __syncthreads();
-    }
-}
 #endif
 
 }  // namespace fdc

@@ -1,8 +1,8 @@
-/* fdc_tma.cuh -- bulk asynchronous copies global -> shared memory (TMA engine, cp.async.bulk) completing on an
- * mbarrier: the "TMA-staged tile" used by the 32-point extract, which has no registers left for a prefetch tile.
- * One elected thread arms the barrier with the byte count and issues one copy per channel slice; the data lands in
- * shared memory while the CTA computes the previous tile; every thread then waits on the barrier's phase bit.
- * Device only (sm_90+); under the host emulator the same staging is a memcpy (tests/emu). */
+/* fdc_tma.cuh -- the bulk (TMA engine) instructions the kernels use: cp.async.bulk.prefetch.L2 pulls the next tile's
+ * operands into L2 with ONE instruction of one thread (no registers, no completion to wait for) while the CTA transforms the
+ * current tile; the mbarrier / cp.async.bulk global -> shared helpers are kept for staging experiments (a TMA-staged
+ * extract tile was measured at 65 against 80 Gsample/s for the register-staged one on cfg4 and removed,
+ * profiles/r2_sweep_engine_variants_packed.txt).  Device only (sm_90+). */
 #ifndef FDC_TMA_CUH
 #define FDC_TMA_CUH
 #if defined(__CUDACC__)

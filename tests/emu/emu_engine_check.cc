@@ -252,54 +252,6 @@ template <int L, int E = 16, bool PACK = false> static void check_extract(int N,
     report(name, stray ? 1.0 : worst, 3e-6);
 }
 
-/* ---- K2 with the TMA-staged input tile: the bulk copies are memcpys here ---- */
-template <int L> static void check_extract_staged(int N, int nchan, long nb, int nphase)
-{
-    constexpr int B = 4096 / L;
-    typedef TileFFT<L, B, -1, false, false, 32> ENG;
-    std::vector<float2> spec((size_t)nb * N), tables((size_t)2 * nphase * L), stage((size_t)L * B);
-    for (auto& v : spec) { v.x = frand(); v.y = frand(); }
-    for (auto& v : tables) { v.x = frand(); v.y = frand(); }
-    std::vector<ChanDev> chans(nchan);
-    long prefix = 0;
-    for (int i = 0; i < nchan; i++) {
-        ChanDev& c = chans[i];
-        c.f = (int)((((long)i * (N - L)) / std::max(1, nchan - 1)) & ~1L); c.lout = L - L / 4; c.shift = (c.f / 2 + i) % nphase;
-        c.tab_off = (i % 2) * (long)nphase * L; c.lout_prefix = prefix; c.gain = 1.0f; c.owner = 0; c.sink_prefix = 0; c.pad1 = 0; prefix += c.lout;
-    }
-    std::vector<float2> out((size_t)(nb * prefix));
-    const std::vector<float2> tw = pass_twiddles(L, 32);
-    ExtractParams p; p.l2pf = 0; p.nsinks = 0; p.spec = spec.data(); p.spec_stride = N; p.tables = tables.data(); p.chans = chans.data(); p.nsel = nchan;
-    p.ny = (nchan + B - 1) / B; p.out = out.data(); p.nb = nb; p.call_blocks = nb; p.call_blk0 = 0; p.glob_phase0 = 0; p.nphase = nphase; p.tma_ok = 1; p.phase_mask = (nphase & (nphase - 1)) == 0 ? nphase - 1 : -1;
-    ExtractStageTiles<L, B> tiles{p, stage.data()};
-    std::vector<float2> smem(ENG::SMEM_ELEMS);
-    std::vector<std::array<float2, 32>> regs(ENG::T);
-    for (long tile = 0; tile < nb * p.ny; tile++) {
-        const TilePos pos = tile_split(tile, p.ny);
-        auto ld = tiles.loader(pos); auto st = tiles.storer(pos);
-        for (int s = 0; s < B; s++) memcpy(stage.data() + (size_t)s * L, ld.src(s), sizeof(float2) * L);
-        for (int tid = 0; tid < ENG::T; tid++) ENG::fetch(tid, regs[tid].data(), ld);
-        Run<ENG, 0, decltype(ld), decltype(st)>::go(regs, smem.data(), tw.data(), ld, st);
-    }
-    double worst = 0;
-    for (int i = 0; i < nchan; i++)
-        for (long b = 0; b < nb; b++) {
-            const ChanDev& c = chans[i];
-            const int phase = (int)(((b % nphase) * c.shift) % nphase);
-            std::vector<cd> a(L);
-            for (int n = 0; n < L; n++) {
-                const int m = (n + L / 2) % L;
-                const float2 x = spec[(size_t)b * N + c.f + m], w = tables[(size_t)(c.tab_off + (long)phase * L + m)];
-                a[n] = cd(x.x, x.y) * cd(w.x, w.y);
-            }
-            fft64(a, +1);
-            std::vector<cd> want(a.begin() + (L - c.lout), a.end());
-            worst = std::max(worst, rel_err(want, out.data() + (size_t)(nb * c.lout_prefix + b * c.lout)));
-        }
-    char name[128]; snprintf(name, sizeof name, "extract staged L=%d N=%d nchan=%d nb=%ld", L, N, nchan, nb);
-    report(name, worst, 3e-6);
-}
-
 /* ---- activity-gated job list ---- */
 template <int L> static void check_jobs(int N, int njobs)
 {
@@ -354,7 +306,6 @@ int main()
     check_extract<64, 16, true>(1024, 16, 11, 2); check_extract<64, 8, true>(1024, 16, 7, 4); check_extract<256, 16, true>(4096, 3, 17, 4);
     check_extract<128, 8, true>(2048, 5, 9, 3); check_extract<1024, 32, true>(4096, 1, 9, 4); check_extract<512, 32, true>(8192, 3, 6, 4);
     check_extract<2, 16, true>(64, 5, 700, 4);
-    check_extract_staged<512>(8192, 19, 3, 4); check_extract_staged<1024>(8192, 6, 2, 4);
     check_jobs<64>(1024, 70); check_jobs<512>(4096, 11); check_jobs<16>(256, 300);
     printf("%s\n", g_fail ? "EMU FAILED" : "EMU OK");
     return g_fail ? 1 : 0;

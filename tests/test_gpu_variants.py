@@ -16,7 +16,6 @@ VARIANTS = {
     "extract_8_points_per_thread": {"FDC_EXTRACT_E8": "1"},
     "extract_8_points_per_thread_prefetch": {"FDC_EXTRACT_E8": "1", "FDC_PREFETCH": "3"},
     "extract_16_points_per_thread": {"FDC_EXTRACT_E32": "0"},
-    "extract_32_points_tma_staged": {"FDC_EXTRACT_E32": "2"},
     "extract_without_l2_prefetch": {"FDC_L2PF": "0"},
     "extract_one_block_per_tile": {"FDC_PACK": "0"},
     "forward_16_points_per_thread": {"FDC_FWD_E32": "0"},
