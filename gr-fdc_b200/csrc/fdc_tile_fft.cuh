@@ -206,6 +206,10 @@ struct TileFFT {
 
     /* ---- butterflies ---------------------------------------------------------------------------------------- */
     /* TWS: tw points to a shared-memory copy of the table (plain loads); otherwise read-only global loads */
+    /* Pass twiddles.  FDC_TWGEN: only W^k and every 8th power come from the table, the powers in between are generated with one
+     * complex multiply each (cur *= W^k): two packed instructions instead of a 64-bit shared-memory load per element.  The
+     * kernels are bound by the L1 / shared-memory data path (238 B per input sample go through it on cfg4), not by
+     * the FP32 pipe; anchors every 8 powers keep the accumulated rounding below 7 ulp of the twiddle. */
     template <int P, bool TWS> static FDC_HD void twiddle_bfly(int tid, float2* v, const float2* tw)
     {
         typedef Pass<P> PS;
@@ -214,9 +218,20 @@ struct TileFFT {
             if (P > 0) {
                 int batch, j; PS::map(tid, u, batch, j);
                 const float2* twp = tw + PS::TWOFF + (j % PS::NS);
+#if defined(FDC_TWGEN)
+                constexpr bool GEN = PS::R >= 8;
+#else
+                constexpr bool GEN = false;
+#endif
+                float2 w1 = make_float2(1.f, 0.f), cur = w1;
 #pragma unroll
                 for (int t = 1; t < PS::R; t++) {
-                    const float2 w = TWS ? twp[(t - 1) * PS::NS] : fdc_ldg(twp + (t - 1) * PS::NS);
+                    float2 w;
+                    if (!GEN || t == 1 || t % 8 == 0) {
+                        w = TWS ? twp[(t - 1) * PS::NS] : fdc_ldg(twp + (t - 1) * PS::NS);
+                        if (t == 1) w1 = w;
+                    } else w = cmul(cur, w1);
+                    cur = w;
                     const float2 a = v[u * PS::R + t];
                     v[u * PS::R + t] = DIR > 0 ? cmul(a, w) : cmulc(a, w);
                 }

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "lib", "libfdc_b200.so"))
+LIB_PATH = os.environ.get("FDC_LIB_PATH") or os.path.normpath(os.path.join(_HERE, "..", "..", "lib", "libfdc_b200.so"))     # FDC_LIB_PATH: an experimental build (tools/)
 _lib = None
 
 
