@@ -153,6 +153,7 @@ struct fdc_chan {
     cudaStream_t hs[NSLOT];
     DevBuf h_in[NSLOT], h_out[NSLOT], h_spec[NSLOT], h_mid[NSLOT];
     PinBuf p_in[NSLOT], p_out[NSLOT];      /* library-owned pinned staging for pageable caller memory */
+    std::vector<void*> drain_dst; std::vector<const void*> drain_src; std::vector<size_t> drain_bytes;
     cudaEvent_t h_done[NSLOT];
     long host_chunk;
     /* optional per-kernel timing (fdc_chan_set_profiling): events around K1 and K2 of every chunk */
@@ -688,11 +689,17 @@ static int host_drain_slot(fdc_chan* c, int slot, HostSlotJob& j, long nblocks, 
     if (e != cudaSuccess) return cuda_fail(e, "host path: waiting for a slot");
     if (j.staged_out) {
         const float2* src = (const float2*)c->p_out[slot].p;
+        /* one row per channel: few large rows are cut into pieces, thousands of small ones are grouped into tasks */
+        std::vector<void*>& vd = c->drain_dst; std::vector<const void*>& vs = c->drain_src; std::vector<size_t>& vb = c->drain_bytes;
+        vd.clear(); vs.clear(); vb.clear();
         for (int i = 0; i < c->nchan; i++) {
             if (!outs[i]) continue;
             const long lo = c->chans[i].lout;
-            copy_pool().submit((float2*)outs[i] + j.b0 * lo, src + j.nb * c->chans[i].lout_prefix, sizeof(float2) * (size_t)(j.nb * lo));
+            const size_t bytes = sizeof(float2) * (size_t)(j.nb * lo);
+            if (bytes >= (128u << 10)) copy_pool().submit((float2*)outs[i] + j.b0 * lo, src + j.nb * c->chans[i].lout_prefix, bytes);
+            else { vd.push_back((float2*)outs[i] + j.b0 * lo); vs.push_back(src + j.nb * c->chans[i].lout_prefix); vb.push_back(bytes); }
         }
+        if (!vd.empty()) copy_pool().submit_many(vd.data(), vs.data(), vb.data(), vd.size());
         copy_pool().wait();
     }
     j.busy = false;

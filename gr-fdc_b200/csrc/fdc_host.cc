@@ -122,7 +122,8 @@ static void stream_copy(void* d, const void* s, size_t n) { memcpy(d, s, n); }
 #endif
 
 struct CopyPool::Impl {
-    struct Piece { char* d; const char* s; size_t n; };
+    /* one contiguous copy, or (many != 0) a run of small copies described by arrays the submitter keeps alive until wait() */
+    struct Piece { char* d; const char* s; size_t n; void* const* md; const void* const* ms; const size_t* mb; size_t many; };
     std::vector<std::thread> th;
     std::mutex m; std::condition_variable cv, idle;
     std::deque<Piece> q; size_t inflight; bool stop;
@@ -132,7 +133,8 @@ struct CopyPool::Impl {
         if (q.empty()) return false;
         const Piece p = q.front(); q.pop_front();
         lk.unlock();
-        stream_copy(p.d, p.s, p.n);
+        if (p.many) for (size_t i = 0; i < p.many; i++) stream_copy(p.md[i], p.ms[i], p.mb[i]);
+        else stream_copy(p.d, p.s, p.n);
         lk.lock();
         if (--inflight == 0) idle.notify_all();
         return true;
@@ -167,7 +169,21 @@ void CopyPool::submit(void* dst, const void* src, size_t bytes)
     std::lock_guard<std::mutex> g(d->m);
     for (size_t off = 0; off < bytes; off += piece) {
         Impl::Piece p; p.d = (char*)dst + off; p.s = (const char*)src + off; p.n = std::min(piece, bytes - off);
+        p.md = 0; p.ms = 0; p.mb = 0; p.many = 0;
         d->q.push_back(p); d->inflight++;
+    }
+}
+void CopyPool::submit_many(void* const* dst, const void* const* src, const size_t* bytes, size_t n)
+{
+    const size_t target = 256u << 10;
+    std::lock_guard<std::mutex> g(d->m);
+    size_t i = 0;
+    while (i < n) {
+        size_t j = i, acc = 0;
+        while (j < n && (acc < target || j == i)) acc += bytes[j++];
+        Impl::Piece p; p.d = 0; p.s = 0; p.n = 0; p.md = dst + i; p.ms = src + i; p.mb = bytes + i; p.many = j - i;
+        d->q.push_back(p); d->inflight++;
+        i = j;
     }
 }
 void CopyPool::wait()

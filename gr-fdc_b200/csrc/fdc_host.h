@@ -19,6 +19,9 @@ public:
     explicit CopyPool(int threads);
     ~CopyPool();
     void submit(void* dst, const void* src, size_t bytes);
+    /* n small copies dst[i] <- src[i] (bytes[i] each) as a few tasks of about 256 KiB: a channelizer with thousands of
+     * narrow channels hands every chunk back as thousands of few-KiB rows */
+    void submit_many(void* const* dst, const void* const* src, const size_t* bytes, size_t n);
     void wait();
     int threads() const;
 private:

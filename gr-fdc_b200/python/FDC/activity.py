@@ -26,7 +26,7 @@ class _MsgBlock(_SyncBlock):
         return getattr(lib(), "fdc_%s_%s" % (self._prefix, name))
 
     def __del__(self):
-        L = _cabi.loaded() if _cabi is not None else None
+        L = _cabi.loaded() if (_cabi is not None and getattr(_cabi, "loaded", None) is not None) else None
         if L is not None and getattr(self, "_h", None):
             getattr(L, "fdc_%s_destroy" % self._prefix)(self._h); self._h = None
 

@@ -52,7 +52,7 @@ class overlap_save(_SyncBlock):
         self._h = handle(lib().fdc_overlap_save_create(self.itemsize, self.outputlen, self.overlaplen), "overlap_save")
 
     def __del__(self):
-        L = _cabi.loaded() if _cabi is not None else None
+        L = _cabi.loaded() if (_cabi is not None and getattr(_cabi, "loaded", None) is not None) else None     # module globals are None at interpreter shutdown
         if L is not None and getattr(self, "_h", None):
             L.fdc_overlap_save_destroy(self._h); self._h = None
 
@@ -78,7 +78,7 @@ class vector_cut_vxx(_SyncBlock):
         self._h = handle(lib().fdc_vector_cut_create(self.itemsize, self.veclen, self.offset, self.blocklen), "vector_cut_vxx")
 
     def __del__(self):
-        L = _cabi.loaded() if _cabi is not None else None
+        L = _cabi.loaded() if (_cabi is not None and getattr(_cabi, "loaded", None) is not None) else None     # module globals are None at interpreter shutdown
         if L is not None and getattr(self, "_h", None):
             L.fdc_vector_cut_destroy(self._h); self._h = None
 
@@ -105,7 +105,7 @@ class phase_shifting_windowing_vcc(_SyncBlock):
                                               int(windowtype)), "phase_shifting_windowing_vcc")
 
     def __del__(self):
-        L = _cabi.loaded() if _cabi is not None else None
+        L = _cabi.loaded() if (_cabi is not None and getattr(_cabi, "loaded", None) is not None) else None     # module globals are None at interpreter shutdown
         if L is not None and getattr(self, "_h", None):
             L.fdc_psw_destroy(self._h); self._h = None
 
@@ -144,7 +144,7 @@ class fft_vcc(_SyncBlock):
         self._h = handle(lib().fdc_fft_create(self.n, int(bool(forward)), int(bool(shift))), "fft_vcc")
 
     def __del__(self):
-        L = _cabi.loaded() if _cabi is not None else None
+        L = _cabi.loaded() if (_cabi is not None and getattr(_cabi, "loaded", None) is not None) else None     # module globals are None at interpreter shutdown
         if L is not None and getattr(self, "_h", None):
             L.fdc_fft_destroy(self._h); self._h = None
 
@@ -194,7 +194,7 @@ class Channelizer(object):
         self._h = handle(lib().fdc_chan_create(self.N, self.ovl, self.nphase, self.nchan, C.cast(arr, C.c_void_p)), "fdc_chan_create")
 
     def __del__(self):
-        L = _cabi.loaded() if _cabi is not None else None
+        L = _cabi.loaded() if (_cabi is not None and getattr(_cabi, "loaded", None) is not None) else None     # module globals are None at interpreter shutdown
         if L is not None and getattr(self, "_h", None):
             L.fdc_chan_destroy(self._h); self._h = None
 
