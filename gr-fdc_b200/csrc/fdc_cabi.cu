@@ -187,17 +187,17 @@ static long pick_chunk_blocks(int N)
 /* enqueue K1 + K2 for nb blocks; block b reads d_in[b*hop - ovl, b*hop + hop) */
 static int chan_enqueue_chunk(fdc_chan* c, const float2* d_in, long nb, float2* d_spec, float2* d_mid,
                               float2* d_out, long call_blocks, long call_blk0, long glob_blk0, cudaStream_t s,
-                              const float2* d_hist = 0, long head_blocks = 0, const ExtractParams::Sink* sinks = 0, int nsinks = 0)
+                              const float2* d_hist = 0, long head_blocks = 0, const ExtractParams::Sink* sinks = 0, int nsinks = 0, long head_off = 0)
 {
     cudaError_t e;
     if (c->prof) cudaEventRecord(c->ev(), s);
     if (!c->big) {
         FwdParams p; p.in = d_in; p.spec = d_spec; p.nblocks = nb; p.hop = c->hop; p.ovl = c->ovl; p.N = c->N;
-        p.scale = 1.0f / (float)c->N; p.l2pf = tuning().l2pf ? 1 : 0; p.hist = d_hist; p.head_blocks = d_hist ? head_blocks : 0;
+        p.scale = 1.0f / (float)c->N; p.l2pf = tuning().l2pf ? 1 : 0; p.hist = d_hist; p.head_blocks = d_hist ? head_blocks : 0; p.head_off = head_off;
         e = launch_fwd_small(p, s);
     } else {
         BigParams p; p.in = d_in; p.mid = d_mid; p.spec = d_spec; p.tw4 = c->tw4;
-        p.nblocks = nb; p.hop = c->hop; p.ovl = c->ovl; p.scale = 1.0f / (float)c->N; p.hist = d_hist; p.head_blocks = d_hist ? head_blocks : 0;
+        p.nblocks = nb; p.hop = c->hop; p.ovl = c->ovl; p.scale = 1.0f / (float)c->N; p.hist = d_hist; p.head_blocks = d_hist ? head_blocks : 0; p.head_off = head_off;
         e = (tuning().fused && fwd_cluster_supported(c->N)) ? launch_fwd_cluster(p, c->N, s) : launch_fwd_big(p, c->N, s);
     }
     if (e != cudaSuccess) return cuda_fail(e, "forward FFT launch");
@@ -505,7 +505,7 @@ static int chan_work_device(fdc_chan* c, const void* d_in_v, long nblocks, void*
         /* the staging slab of this worker is free once the copies of the chunk that used it last are done */
         if (staged && c->copies_pending[w] && (e = cudaStreamWaitEvent(wk[w], c->ev_c[w], 0)) != cudaSuccess) return cuda_fail(e, "stream wait");
         if (chan_enqueue_chunk(c, d_in + b0 * c->hop, nb, spec, ring_mid[w], d_out, slab_blocks, slab_first_block + b0, c->blockcount + b0, wk[w],
-                               (const float2*)c->d_hist.p, std::max(0L, nh - b0), sk, use_sinks ? c->nsinks : 0)) return -1;
+                               (const float2*)c->d_hist.p, std::max(0L, nh - b0), sk, use_sinks ? c->nsinks : 0, b0 * c->hop)) return -1;
         if (staged) {
             if ((e = cudaEventRecord(c->ev_x[w], wk[w])) != cudaSuccess || (e = cudaStreamWaitEvent(c->cs[w], c->ev_x[w], 0)) != cudaSuccess)
                 return cuda_fail(e, "sink copy ordering");

@@ -50,8 +50,10 @@ struct FwdParams {
     int l2pf;              /* kernels without a register prefetch: bulk-prefetch the next tile's samples into L2 */
     /* overlap-save history (lib/overlap_save_impl.cc:70-78): the first head_blocks blocks reach back before in[0]; those
      * samples are hist[ovl + i] for sample index i < 0 (hist = the last ovl samples of the previous call, zeros at the start).
-     * Tiles that hold such a block take the two-segment loads, all others the plain ones (a tile-uniform branch). */
-    const float2* hist; long head_blocks;
+     * Tiles that hold such a block take the two-segment loads, all others the plain ones (a tile-uniform branch).
+     * head_off: samples of the same call that lie in front of in[0] (a later chunk of the call: in[-head_off .. 0) is the
+     * caller's buffer, the history starts before that). */
+    const float2* hist; long head_blocks; long head_off;
 };
 template <int N, int B> struct FwdLoader {
     typedef const float2* Ctx;
@@ -71,7 +73,7 @@ template <int N, int B> struct FwdLoader {
     template <int R, int STRIDE> FDC_HD float2 fetch_head(const Ctx& c, int t) const
     {
         const long i = (c - p.in) + t * STRIDE;            /* sample index relative to in[0] */
-        return i < 0 ? p.hist[p.ovl + i] : fdc_ldg(p.in + i);
+        return i < -p.head_off ? p.hist[p.ovl + i + p.head_off] : fdc_ldg(p.in + i);
     }
 };
 template <int N, int B> struct FwdStorer {
@@ -100,7 +102,7 @@ template <int N, int B> struct FwdTiles {
     {
         if (!p.l2pf || tid != 0) return;
         const long blk0 = (long)t.outer * B;
-        if (blk0 < p.head_blocks) return;                  /* the samples before in[0] live in the history buffer */
+        if (blk0 < p.head_blocks) return;                  /* part of these samples lives in the history buffer */
         const long nb = p.nblocks - blk0 < B ? p.nblocks - blk0 : B;
         if (nb <= 0) return;
         const char* a = reinterpret_cast<const char*>(p.in + (blk0 * p.hop - p.ovl));
@@ -127,7 +129,7 @@ struct BigParams {
     long nblocks;
     int hop, ovl;
     float scale;
-    const float2* hist; long head_blocks;     /* as in FwdParams */
+    const float2* hist; long head_blocks; long head_off;     /* as in FwdParams */
 };
 template <int N1, int N2, int B> struct ColLoader {     /* signal = column n2, element index = n1 */
     typedef const float2* Ctx;
@@ -141,7 +143,7 @@ template <int N1, int N2, int B> struct ColLoader {     /* signal = column n2, e
     template <int R, int STRIDE> FDC_HD float2 fetch_head(const Ctx& c, int t) const
     {
         const long i = (c - p.in) + (long)t * STRIDE * N2;
-        return i < 0 ? p.hist[p.ovl + i] : fdc_ldg(p.in + i);
+        return i < -p.head_off ? p.hist[p.ovl + i + p.head_off] : fdc_ldg(p.in + i);
     }
 };
 /* The four-step twiddles a column CTA needs are the same for every block (it keeps its column tile), so they are

@@ -127,7 +127,7 @@ template <int N, int E = 16> static void check_fwd_small(int ovl, long nblocks)
     std::vector<float2> hist(buf.begin(), buf.begin() + ovl), stream(buf);
     for (int i = 0; i < ovl; i++) stream[(size_t)i] = make_float2(1e30f, -1e30f);
     FwdParams p; p.in = stream.data() + ovl; p.spec = spec.data(); p.nblocks = nblocks; p.hop = hop; p.ovl = ovl; p.N = N; p.scale = 1.0f / N; p.l2pf = 0;
-    p.hist = hist.data(); p.head_blocks = ovl ? (ovl + hop - 1) / hop : 0;
+    p.hist = hist.data(); p.head_blocks = ovl ? (ovl + hop - 1) / hop : 0; p.head_off = 0;
     run_tiles<ENG>(FwdTiles<N, B>{p}, (nblocks + B - 1) / B, tw.data());
     double worst = 0;
     for (long b = 0; b < nblocks; b++) {
@@ -162,7 +162,7 @@ template <int N1, int N2> static void check_fwd_big(int ovl, long nblocks)
     std::vector<float2> hist(buf.begin(), buf.begin() + ovl), stream(buf);
     for (int i = 0; i < ovl; i++) stream[(size_t)i] = make_float2(1e30f, -1e30f);      /* must come from the history buffer */
     BigParams p; p.in = stream.data() + ovl; p.mid = mid.data(); p.spec = spec.data(); p.tw4 = tw4.data(); p.nblocks = nblocks;
-    p.hop = hop; p.ovl = ovl; p.scale = 1.0f / N; p.hist = hist.data(); p.head_blocks = ovl ? (ovl + hop - 1) / hop : 0;
+    p.hop = hop; p.ovl = ovl; p.scale = 1.0f / N; p.hist = hist.data(); p.head_blocks = ovl ? (ovl + hop - 1) / hop : 0; p.head_off = 0;
     /* a persistent column CTA keeps one column tile and its twiddle slice; the emulator walks all tiles with "one CTA",
      * so the slice is rebuilt per column tile: run the tiles of one column tile at a time */
     {

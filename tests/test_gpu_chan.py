@@ -264,6 +264,39 @@ def test_sliding_window_overlap_above_half(FDC, N, ovl):
         assert rel_l2(np.concatenate(got[i]), want[i]) < TOL
 
 
+@pytest.mark.parametrize("N,ovl,chunk", [(1024, 768, 1), (1024, 896, 4), (2048, 1920, 5)])
+def test_overlap_above_half_with_chunks_shorter_than_the_history(FDC, N, ovl, chunk):
+    """overlap > 50 % with chunks of fewer blocks than reach back into the previous call (nh = ceil(ovl / hop) up to 15):
+    device path (history through the two-segment loads of the first chunks) and host path (chunk boundaries inside the head, pageable
+    buffers through the staging slots) against the fp64 restatement"""
+    import torch
+    from oracle import fdc_numpy as fnp
+    cfg = workloads.ChanConfig("ovl_test", N, 4, workloads.example_channels(), workloads.HANN, ovl=ovl)
+    nblocks = 37
+    x = workloads.tones_input(cfg, nblocks * cfg.hop, seed=8)
+    want, _ = fnp.channelize(x, cfg.N, cfg.R, cfg.params, cfg.windowtype, ovl=ovl, shifts=cfg.shifts())
+    d_in = torch.from_numpy(x.view(np.float32).copy()).cuda()
+    for path in ("device", "host"):
+        g = make_gpu_chain(FDC, cfg)
+        g.chunk_blocks = chunk
+        got = [[] for _ in range(cfg.nchan)]
+        pos = 0
+        for nb in (2, 1, 19, nblocks - 22):
+            if path == "device":
+                d_out = torch.empty(nb * cfg.out_per_block * 2, dtype=torch.float32, device="cuda")
+                g.work_device(d_in.data_ptr() + 8 * pos * cfg.hop, nb, d_out.data_ptr(), 0, torch.cuda.current_stream().cuda_stream)
+                torch.cuda.synchronize()
+                a = d_out.cpu().numpy().view(np.complex64)
+                outs = [a[off:off + ln] for off, ln in g.out_slices(nb)]
+            else:
+                outs, _ = g.work_host(x[pos * cfg.hop:(pos + nb) * cfg.hop])
+            for i in range(cfg.nchan):
+                got[i].append(np.array(outs[i]))
+            pos += nb
+        for i in range(cfg.nchan):
+            assert rel_l2(np.concatenate(got[i]), want[i]) < TOL, (path, i)
+
+
 def test_time_sharded_equals_single_stream(FDC):
     """SURVEY 8e on one GPU: the stream cut into per-rank runs (own halo, closed-form phase origin) gives bit-identical
     channel outputs to one context fed the whole stream"""
