@@ -1,8 +1,11 @@
 """Oracle (TEST INFRASTRUCTURE ONLY): restatement of the image arithmetic of the reference's waterfall consumer,
 python/WaterfallMsgTagging.py, as plain functions on a state dict, pixel by pixel where the reference uses array tricks.
 
-PARITY UNPINNED: the reference class needs PyQt4 and GNU Radio, neither of which can be imported in this container, and the
-reference ships no test or fixture for it.  What is restated, with the lines it follows:
+PARITY: the reference class needs PyQt4 and GNU Radio, neither of which can be imported in this container, and the reference
+ships no test or fixture for it.  Its ARITHMETIC is pinned: reduce_vectors and color_tables (and the colour mapping) are checked
+against tests/golden/waterfall.npz, which tests/golden/make_waterfall_golden.py makes by executing the reference's own lines
+(work :247-256, apply_colorscheme :261-262, cr_colorscheme :276-313).  The widget-side logic (resize, scrolling repaint, tag
+frames) is restated from the source and stays UNPINNED.  What is restated, with the lines it follows:
   reduce_vectors   work()              :272-279   mean over blocklen/1024 bins, or repetition when blocklen < 1024
   color_tables     cr_colorscheme()    :256-315
   resize           renew_pixmap()      :113-126

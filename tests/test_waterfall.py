@@ -1,6 +1,9 @@
 """The waterfall consumer: FDC.WaterfallMsgTagging (headless model of python/WaterfallMsgTagging.py) against
 the pixel-by-pixel restatement in oracle/waterfall_numpy.py, and the GPU reduction of spectrum rows to 1024 columns against
-NumPy.  The oracle for this piece is unpinned (the reference widget needs PyQt4 + GNU Radio), see its header."""
+NumPy.  The widget itself needs PyQt4 + GNU Radio and cannot run here; its ARITHMETIC (row reduction, colour tables, colour mapping:
+python/WaterfallMsgTagging.py:247-256, 261-262, 276-313) is pinned by tests/golden/waterfall.npz, made by executing those lines of the
+reference (tests/golden/make_waterfall_golden.py).  The scrolling / tag-frame drawing of the restatement stays unpinned."""
+import os
 import numpy as np
 import pytest
 
@@ -91,3 +94,54 @@ def test_gpu_reduction_of_spectrum_rows(blocklen, loginput):
         w.msg_handler({"blockstart": 2, "blockend": 6, "rel_cfreq": 0.34, "rel_bw": 0.06}); w.update()
     diff = np.count_nonzero(np.any(a.pixels.reshape(-1, 3) != b.pixels.reshape(-1, 3), axis=1))
     assert diff <= 2e-3 * a.pixels.size / 3
+
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "waterfall.npz")
+
+
+def test_arithmetic_against_the_reference_lines():
+    """row reduction, colour tables and colour mapping of the restatement AND of the FDC model against what the reference's own
+    lines return (golden file): rows to fp32 rounding, colour tables exactly, pixels equal except where a value sits within
+    rounding of a colour-bin edge"""
+    import FDC
+    from FDC import waterfall
+    from oracle import waterfall_numpy as wf_or
+    g = np.load(GOLD)
+    for key in [str(k) for k in g["names"]]:
+        blocklen, loginput, scheme, lo, hi = g[key + "_meta"]
+        blocklen, loginput, scheme = int(blocklen), bool(loginput), int(scheme)
+        x, rows, pix = g[key + "_x"], g[key + "_rows"], g[key + "_pixels"]
+        for cols, edges, frame in (wf_or.color_tables(scheme, lo, hi, loginput), waterfall.color_table(scheme, lo, hi, loginput)):
+            assert np.array_equal(cols, g[key + "_cols"]) and np.array_equal(frame, g[key + "_frame"])
+            assert np.allclose(edges, g[key + "_bins"], rtol=1e-14, atol=0)
+        mine = wf_or.reduce_vectors(x, blocklen)
+        assert mine.shape == rows.shape and np.allclose(mine, rows, rtol=2e-6, atol=1e-12)
+        model = FDC.WaterfallMsgTagging(blocklen, 1e6, 4, 1, loginput, lo, hi, scheme, 0, height=x.shape[0])
+        model.work([x]); model.update()
+        got = np.asarray(model._rows) if len(model._rows) else np.asarray(model.pixels)
+        assert model.pixels.shape == pix.shape
+        diff = np.count_nonzero(np.any(model.pixels.reshape(-1, 3) != pix.reshape(-1, 3), axis=1))
+        assert diff <= 2e-3 * pix.size / 3, (key, diff)
+
+
+@pytest.mark.gpu
+def test_gpu_rows_against_the_reference_lines():
+    """the device reduction (|X|^2, 10 log10, mean over blocklen / 1024 bins) fed with spectra whose powers are the golden inputs:
+    rows equal to the reference lines' rows to fp32 rounding"""
+    import FDC
+    import torch
+    g = np.load(GOLD)
+    for key in [str(k) for k in g["names"]]:
+        blocklen, loginput, scheme, lo, hi = g[key + "_meta"]
+        blocklen, loginput = int(blocklen), bool(loginput)
+        x, rows = g[key + "_x"], g[key + "_rows"]
+        power = 10.0 ** (x.astype(np.float64) / 10.0) if loginput else x.astype(np.float64)
+        spec = (np.sqrt(power) * np.exp(2j * np.pi * np.random.default_rng(3).random(power.shape))).astype(np.complex64)
+        c = FDC.WaterfallMsgTagging(blocklen, 1e6, 4, 1, loginput, lo, hi, int(scheme), 0, height=x.shape[0])
+        d = torch.from_numpy(spec.view(np.float32).copy()).cuda()
+        c.work_spectrum_device(x.shape[0], d.data_ptr())
+        got = np.asarray(c._rows)
+        if loginput:
+            assert np.max(np.abs(got - rows)) < 5e-4, key               # dB values (log per bin, then the mean, as in the reference)
+        else:
+            assert np.max(np.abs(got - rows) / np.maximum(np.abs(rows), 1e-30)) < 5e-6, key
