@@ -440,6 +440,9 @@ def main():
     claim_stdout()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and "FDC_COPY_THREADS" not in os.environ:
+        # one process per GPU shares the host cores: size each process's staging copy pool for its share (read when the library loads)
+        os.environ["FDC_COPY_THREADS"] = str(max(1, (os.cpu_count() or 1) // world - 1))
     if args.workload in ACTIVITY:
         global ACT
         ACT = ACTIVITY[args.workload]

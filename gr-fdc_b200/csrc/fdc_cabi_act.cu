@@ -65,8 +65,11 @@ struct ActEngine {
         size_t nblocks;
         Pending() : head(0), nowned(0), seg_head(0), nblocks(0) {}
         void push(const cfloat* p, size_t n) { segs.push_back(std::make_pair(p, n)); nblocks++; }
-        /* the first nb buffered blocks -> out (null: drop them) */
-        void take(size_t nb, size_t blocksamples, cfloat* out)
+        /* the first nb buffered blocks -> out (null: drop them).  With `later`, copies out of the current call's result buffer are
+         * only recorded there (destination, source, bytes) and done in one parallel batch at the end of the replay; blocks kept from
+         * earlier calls are copied at once (their buffer may be dropped by a later op) */
+        struct Deferred { std::vector<void*> dst; std::vector<const void*> src; std::vector<size_t> bytes; };
+        void take(size_t nb, size_t blocksamples, cfloat* out, Deferred* later = 0)
         {
             nblocks -= nb;
             const size_t from_owned = std::min(nb, nowned);
@@ -77,7 +80,11 @@ struct ActEngine {
                 if (nowned == 0) { data.clear(); head = 0; }
             }
             for (; nb > 0 && seg_head < segs.size(); nb--, seg_head++) {
-                if (out) { memcpy(out, segs[seg_head].first, sizeof(cfloat) * segs[seg_head].second); out += segs[seg_head].second; }
+                if (out) {
+                    if (later) { later->dst.push_back(out); later->src.push_back(segs[seg_head].first); later->bytes.push_back(sizeof(cfloat) * segs[seg_head].second); }
+                    else memcpy(out, segs[seg_head].first, sizeof(cfloat) * segs[seg_head].second);
+                    out += segs[seg_head].second;
+                }
             }
             if (seg_head == segs.size()) { segs.clear(); seg_head = 0; }
         }
@@ -217,6 +224,7 @@ struct ActEngine {
             }
             return;
         }
+        Pending::Deferred later;
         for (size_t i = 0; i < ops.size(); i++) {
             const ActOp& o = ops[i];
             if (o.kind == ActOp::PUSH) {
@@ -236,7 +244,8 @@ struct ActEngine {
                 else {
                     cfloat* dstp = (wanted && m.n) ? arena.alloc(m.n) : 0;
                     m.ptr = dstp;
-                    q.take(ntake, (size_t)o.blocksamples, dstp);
+                    /* a payload that also goes to a file is needed at once; the others are copied in one parallel batch below */
+                    q.take(ntake, (size_t)o.blocksamples, dstp, m.meta.filename.empty() ? &later : 0);
                 }
                 if (!m.meta.filename.empty()) {
                     FILE* fh = fopen(m.meta.filename.c_str(), "wb");
@@ -246,6 +255,11 @@ struct ActEngine {
                 if (!m.meta.logline.empty()) log_line(verbose, logfile, m.meta.logline);
                 if (m.meta.publish) msgs.push_back(std::move(m));
             }
+        }
+        if (!later.dst.empty()) {
+            /* tens of MB per call when the results are not channel-contiguous (time-sharded calls): the copy pool instead of one memcpy after the other */
+            copy_pool().submit_many(later.dst.data(), later.src.data(), later.bytes.data(), later.dst.size());
+            copy_pool().wait();
         }
         for (std::map<long, Pending>::iterator it = pending.begin(); it != pending.end(); ++it) it->second.keep();
     }
