@@ -621,6 +621,7 @@ def main():
             traffic_step = {k: tj[k]["dram_bytes_per_step"] * nb / tj["blocks_per_step"] for k in ("forward_fft", "channel_extract") if k in tj}
             traffic = traffic_step[dom] / max(1, kern[dom]["launches"] / PK)
     path_gbs = value * 1e6 / world * cfg.bytes_per_sample() / 1e9
+    l2if = (8.0 * cfg.N * (4 if cfg.N > 16384 else 2) + 0.6 * 8.0 * sum(p[1] for p in cfg.params) + 8.0 * cfg.out_per_block) / cfg.hop
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": ach / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": (out_bytes if dom == "channel_extract" else in_bytes) / max(1, kern[dom]["launches"]),
@@ -630,7 +631,12 @@ def main():
                 "path": {"bytes_per_sample": cfg.bytes_per_sample(), "achieved": path_gbs, "frac": path_gbs / peaks["hbm_gbs"],
                          "sustained_frac": (sustained["value"] * 1e6 / world * cfg.bytes_per_sample() / 1e9 / peaks["hbm_gbs"]) if sustained else None,
                          "frac_of_8TBps_nominal": path_gbs / 8000.0,
-                         "flop_per_sample": cfg.flops_per_sample(), "tflops_fp32": value * 1e6 / world * cfg.flops_per_sample() / 1e12}}
+                         "flop_per_sample": cfg.flops_per_sample(), "tflops_fp32": value * 1e6 / world * cfg.flops_per_sample() / 1e12},
+                # the resource that actually bounds the three-kernel structure: bytes the kernels move between the SMs and L2 per
+                # input sample (samples in, four-step intermediate out and in for N >= 32768, spectrum out, slices in at the measured 60 % of
+                # their nominal size thanks to L1 hits of overlapping slices, channel samples out) against the measured 29 B/clk/SM
+                "sm_l2_interface": {"bytes_per_sample": l2if, "peak": 8200.0, "unit": "GB/s", "peak_source": "measured: tools/lsubench.cu, tools/l2bw.cu (profiles/)",
+                                    "achieved": value * 1e6 / world * l2if / 1e9, "frac": value * 1e6 / world * l2if / 1e9 / 8200.0}}
 
     # ---- N > 1: the compute-only rate (outputs stay on the rank that made them) beside the gather-inclusive `value` ----
     compute_only = None

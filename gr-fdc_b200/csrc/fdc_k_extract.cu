@@ -5,6 +5,10 @@
  * between and behind them, and process_channel of the activity-gated blocks. */
 #include "fdc_kcommon.cuh"
 
+#ifndef FDC_EXT32_CTAS
+#define FDC_EXT32_CTAS 5
+#endif
+
 namespace fdc {
 
 template <int L, int B, bool PF>
@@ -44,7 +48,7 @@ k_extract8(const ExtractParams p, const float2* __restrict__ tw, long ntiles)
  * the L1/shared-memory pipe, so the exchange it does not do is the saving.  128 threads at 96 registers, 5 CTAs per SM (measured: 4 CTAs / 127 registers
  * 79.1 Gsample/s, 5 CTAs 80.4, 6 CTAs with the twiddles left in global memory to fit the shared memory 69). */
 template <int L, int B>
-__global__ void __launch_bounds__(128, 5)
+__global__ void __launch_bounds__(128, FDC_EXT32_CTAS)
 k_extract32(const ExtractParams p, const float2* __restrict__ tw, long ntiles)
 {
     tile_kernel_body<TileFFT<L, B, -1, false, false, 32>, false>(ExtractTiles<L, B>{p}, tw, ntiles);

@@ -72,8 +72,10 @@ static void host_pass_twiddles(int L, int E, std::vector<float2>& h)
     const int np = fft_npasses(L, E);
     for (int p = 1; p < np; p++) {
         const int R = fft_radix(L, p, E), NS = fft_ns(L, p, E), off = fft_twoff(L, p, E);
-        for (int t = 1; t < R; t++)
-            for (int k = 0; k < NS; k++) h[(size_t)(off + (t - 1) * NS + k)] = root((long)k * t, (long)NS * R);
+        for (int t = 1; t < R; t++) {
+            if (!fft_twstored(t, R)) continue;                /* FDC_TWGEN: the kernels generate the powers in between */
+            for (int k = 0; k < NS; k++) h[(size_t)(off + fft_twrow(t, R) * NS + k)] = root((long)k * t, (long)NS * R);
+        }
     }
 }
 const float2* twiddle_table(int L, int E)

@@ -13,7 +13,7 @@
  *      out  : y[(j-k)*R + k + t*Ns]
  * Every access of a butterfly is "base + t * compile-time stride": the functors and the shared-memory
  * exchange compute one address per butterfly and the 16 element accesses become immediate offsets.
- * The twiddles of pass p are stored as a [t-1][k] table (k fastest) so that lanes with consecutive k
+ * The twiddles of pass p are stored as a [row(t)][k] table (k fastest) so that lanes with consecutive k
  * read consecutive entries.
  *
  * The first exchange (Ns = 1, a thread writes 16 consecutive points) is stored with one pad slot per
@@ -76,11 +76,21 @@ constexpr int fft_ns(int L, int p, int E = 16)
     for (int q = 0; q < p; q++) ns *= fft_radix(L, q, E);
     return ns;
 }
+/* FDC_TWGEN: only the rows t = 1 and t = 8, 16, 24 of a pass's twiddle table exist (the powers in between are generated,
+ * twiddle_bfly); passes of radix < 8 keep all their rows.  fft_twrow(t, R) is the row of W^{k t}. */
+#if defined(FDC_TWGEN)
+constexpr bool fft_twgen(int R) { return R >= 8; }
+#else
+constexpr bool fft_twgen(int) { return false; }
+#endif
+constexpr int fft_twrows(int R) { return fft_twgen(R) ? 1 + (R - 1) / 8 : R - 1; }
+constexpr int fft_twrow(int t, int R) { return fft_twgen(R) ? (t == 1 ? 0 : t / 8) : t - 1; }
+constexpr bool fft_twstored(int t, int R) { return !fft_twgen(R) || t == 1 || t % 8 == 0; }
 /* offset of pass p's twiddles inside the per-length table, and the table's size (float2 units) */
 constexpr int fft_twoff(int L, int p, int E = 16)
 {
     int off = 0;
-    for (int q = 1; q < p; q++) off += (fft_radix(L, q, E) - 1) * fft_ns(L, q, E);
+    for (int q = 1; q < p; q++) off += fft_twrows(fft_radix(L, q, E)) * fft_ns(L, q, E);
     return off;
 }
 constexpr int fft_twsize(int L, int E = 16) { const int n = fft_twoff(L, fft_npasses(L, E), E); return n < 1 ? 1 : n; }
@@ -218,17 +228,12 @@ struct TileFFT {
             if (P > 0) {
                 int batch, j; PS::map(tid, u, batch, j);
                 const float2* twp = tw + PS::TWOFF + (j % PS::NS);
-#if defined(FDC_TWGEN)
-                constexpr bool GEN = PS::R >= 8;
-#else
-                constexpr bool GEN = false;
-#endif
                 float2 w1 = make_float2(1.f, 0.f), cur = w1;
 #pragma unroll
                 for (int t = 1; t < PS::R; t++) {
                     float2 w;
-                    if (!GEN || t == 1 || t % 8 == 0) {
-                        w = TWS ? twp[(t - 1) * PS::NS] : fdc_ldg(twp + (t - 1) * PS::NS);
+                    if (fft_twstored(t, PS::R)) {
+                        w = TWS ? twp[fft_twrow(t, PS::R) * PS::NS] : fdc_ldg(twp + fft_twrow(t, PS::R) * PS::NS);
                         if (t == 1) w1 = w;
                     } else w = cmul(cur, w1);
                     cur = w;

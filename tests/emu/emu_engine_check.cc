@@ -18,11 +18,13 @@ static std::vector<float2> pass_twiddles(int L, int E = 16)
     std::vector<float2> h((size_t)fft_twsize(L, E), make_float2(1.f, 0.f));
     for (int p = 1; p < fft_npasses(L, E); p++) {
         const int R = fft_radix(L, p, E), NS = fft_ns(L, p, E), off = fft_twoff(L, p, E);
-        for (int t = 1; t < R; t++)
+        for (int t = 1; t < R; t++) {
+            if (!fft_twstored(t, R)) continue;
             for (int k = 0; k < NS; k++) {
                 const double a = -2.0 * M_PI * (double)(((long)k * t) % ((long)NS * R)) / ((double)NS * R);
-                h[(size_t)(off + (t - 1) * NS + k)] = make_float2((float)cos(a), (float)sin(a));
+                h[(size_t)(off + fft_twrow(t, R) * NS + k)] = make_float2((float)cos(a), (float)sin(a));
             }
+        }
     }
     return h;
 }
