@@ -124,6 +124,7 @@ int fdc_psw_build_tables(int blocklen, int numphasestates, float passbw, float s
 struct fdc_chan {
     int dev, N, ovl, hop, nphase, nchan;
     bool big; int N1, N2;
+    bool fused_small;                  /* one kernel does K1 + K2 (fdc_k_chanfused.cu): N <= 16384, every channel of the same slice length */
     std::vector<ChanDev> chans;
     std::vector<int> l;
     std::vector<std::pair<int, std::pair<int, int> > > groups;    /* (l, (first index in d_chans, count)) */
@@ -187,10 +188,25 @@ static long pick_chunk_blocks(int N)
 /* enqueue K1 + K2 for nb blocks; block b reads d_in[b*hop - ovl, b*hop + hop) */
 static int chan_enqueue_chunk(fdc_chan* c, const float2* d_in, long nb, float2* d_spec, float2* d_mid,
                               float2* d_out, long call_blocks, long call_blk0, long glob_blk0, cudaStream_t s,
-                              const float2* d_hist = 0, long head_blocks = 0, const ExtractParams::Sink* sinks = 0, int nsinks = 0, long head_off = 0)
+                              const float2* d_hist = 0, long head_blocks = 0, const ExtractParams::Sink* sinks = 0, int nsinks = 0, long head_off = 0,
+                              bool need_spec = true)
 {
     cudaError_t e;
     if (c->prof) cudaEventRecord(c->ev(), s);
+    /* N <= 16384, one slice length, nobody wants the spectrum itself: K1 + K2 in one kernel, the spectrum stays in shared memory */
+    if (c->fused_small && !need_spec && (d_out || nsinks) && tuning().fuse_small) {
+        FwdParams p; p.in = d_in; p.spec = 0; p.nblocks = nb; p.hop = c->hop; p.ovl = c->ovl; p.N = c->N;
+        p.scale = 1.0f / (float)c->N; p.l2pf = tuning().l2pf ? 1 : 0; p.hist = d_hist; p.head_blocks = d_hist ? head_blocks : 0; p.head_off = head_off;
+        ExtractParams q; q.spec = 0; q.spec_stride = c->N; q.tables = (const float2*)c->d_tables.p;
+        q.chans = (const ChanDev*)c->d_chans.p; q.nsel = c->nchan; q.ny = 0; q.out = d_out; q.tma_ok = 0; q.l2pf = 0; q.bpt = 1; q.nsinks = nsinks;
+        for (int k = 0; k < nsinks; k++) q.sink[k] = sinks[k];
+        q.nb = nb; q.call_blocks = call_blocks; q.call_blk0 = call_blk0; q.glob_phase0 = (int)(glob_blk0 % c->nphase); q.nphase = c->nphase;
+        q.phase_mask = (c->nphase & (c->nphase - 1)) == 0 ? c->nphase - 1 : -1;
+        e = launch_chan_fused(p, q, c->groups[0].first, s);
+        if (e != cudaSuccess) return cuda_fail(e, "fused channelizer launch");
+        if (c->prof) { cudaEventRecord(c->ev(), s); cudaEventRecord(c->ev(), s); }
+        return 0;
+    }
     if (!c->big) {
         FwdParams p; p.in = d_in; p.spec = d_spec; p.nblocks = nb; p.hop = c->hop; p.ovl = c->ovl; p.N = c->N;
         p.scale = 1.0f / (float)c->N; p.l2pf = tuning().l2pf ? 1 : 0; p.hist = d_hist; p.head_blocks = d_hist ? head_blocks : 0; p.head_off = head_off;
@@ -287,6 +303,7 @@ fdc_chan* fdc_chan_create(int N, int ovl, int nphase, int nchan, const fdc_chan_
         std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return c->chans[a].f < c->chans[b].f; });
         sel.insert(sel.end(), order.begin(), order.end());
     }
+    c->fused_small = !c->big && c->groups.size() == 1 && chan_fused_supported(N, c->groups[0].first);
     c->chunk_blocks = pick_chunk_blocks(N);
     bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming) == cudaSuccess;
@@ -332,6 +349,7 @@ void fdc_chan_destroy(fdc_chan* c)
     delete c;
 }
 int fdc_chan_hop(const fdc_chan* c) { return c ? c->hop : -1; }
+int fdc_chan_is_fused(const fdc_chan* c) { return (c && c->fused_small && tuning().fuse_small) ? 1 : 0; }
 long fdc_chan_blockcount(const fdc_chan* c) { return c ? c->blockcount : -1; }
 int fdc_chan_reset(fdc_chan* c)
 {
@@ -505,7 +523,7 @@ static int chan_work_device(fdc_chan* c, const void* d_in_v, long nblocks, void*
         /* the staging slab of this worker is free once the copies of the chunk that used it last are done */
         if (staged && c->copies_pending[w] && (e = cudaStreamWaitEvent(wk[w], c->ev_c[w], 0)) != cudaSuccess) return cuda_fail(e, "stream wait");
         if (chan_enqueue_chunk(c, d_in + b0 * c->hop, nb, spec, ring_mid[w], d_out, slab_blocks, slab_first_block + b0, c->blockcount + b0, wk[w],
-                               (const float2*)c->d_hist.p, std::max(0L, nh - b0), sk, use_sinks ? c->nsinks : 0, b0 * c->hop)) return -1;
+                               (const float2*)c->d_hist.p, std::max(0L, nh - b0), sk, use_sinks ? c->nsinks : 0, b0 * c->hop, d_spectrum != 0)) return -1;
         if (staged) {
             if ((e = cudaEventRecord(c->ev_x[w], wk[w])) != cudaSuccess || (e = cudaStreamWaitEvent(c->cs[w], c->ev_x[w], 0)) != cudaSuccess)
                 return cuda_fail(e, "sink copy ordering");
@@ -789,7 +807,7 @@ int fdc_chan_work_host(fdc_chan* c, const void* in_v, long nblocks, void* const*
             if (e != cudaSuccess) return cuda_fail(e, "history copy");
         }
         if (chan_enqueue_chunk(c, d_in + c->ovl, nb, (float2*)c->h_spec[slot].p, (float2*)c->h_mid[slot].p, d_out, nb, 0,
-                               c->blockcount + b0, s, (b0 == 0) ? (const float2*)c->d_hist.p : 0, (b0 == 0) ? head : 0)) return -1;
+                               c->blockcount + b0, s, (b0 == 0) ? (const float2*)c->d_hist.p : 0, (b0 == 0) ? head : 0, 0, 0, 0, spectrum != 0)) return -1;
         if (d_out) {
             if (stage_out) {
                 e = cudaMemcpyAsync(c->p_out[slot].p, d_out, sizeof(float2) * (size_t)(nb * c->lout_total), cudaMemcpyDeviceToHost, s);

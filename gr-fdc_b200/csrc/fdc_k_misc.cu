@@ -23,7 +23,7 @@ static int env_int(const char* name, int dflt)
 }
 const Tuning& tuning()
 {
-    static const Tuning t = { env_int("FDC_PREFETCH", 1), env_int("FDC_CTAS_PER_SM", 0), env_int("FDC_STREAMS", 3), env_int("FDC_EXTRACT_E8", -1), env_int("FDC_CTAS_FWD", 0), env_int("FDC_CTAS_EXT", 0), env_int("FDC_PDL", 1), env_int("FDC_FWD_SPLIT", 32768), env_int("FDC_HOST_CHUNK_MB", 8), env_int("FDC_EXTRACT_E32", 1), env_int("FDC_FWD_E32", 1), env_int("FDC_L2PF", 1), env_int("FDC_PACK", 1), env_int("FDC_FUSED", 0), env_int("FDC_HOST_STAGING", 1), env_int("FDC_SINK_DMA", 0) };
+    static const Tuning t = { env_int("FDC_PREFETCH", 1), env_int("FDC_CTAS_PER_SM", 0), env_int("FDC_STREAMS", 3), env_int("FDC_EXTRACT_E8", -1), env_int("FDC_CTAS_FWD", 0), env_int("FDC_CTAS_EXT", 0), env_int("FDC_PDL", 1), env_int("FDC_FWD_SPLIT", 32768), env_int("FDC_HOST_CHUNK_MB", 8), env_int("FDC_EXTRACT_E32", 1), env_int("FDC_FWD_E32", 1), env_int("FDC_L2PF", 1), env_int("FDC_PACK", 1), env_int("FDC_FUSED", 0), env_int("FDC_HOST_STAGING", 1), env_int("FDC_SINK_DMA", 0), env_int("FDC_FUSE_SMALL", 0) };
     return t;
 }
 

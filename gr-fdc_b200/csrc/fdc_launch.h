@@ -10,8 +10,8 @@ namespace fdc {
 void count_launch(int n = 1);
 unsigned long long launch_count();
 
-/* run-time switches for measurements (environment: FDC_PREFETCH=bit 0 forward kernels | bit 1 extract kernels, FDC_CTAS_FWD / FDC_CTAS_EXT=n, FDC_CTAS_PER_SM=n, FDC_STREAMS=1..4, FDC_EXTRACT_E8=-1 (auto: slices <= 64) | 0 | 1, FDC_PDL=0|1, FDC_FWD_SPLIT=N, FDC_EXTRACT_E32=0|1, FDC_FWD_E32=0|1|2 (2: also 512/1024-point transforms), FDC_HOST_CHUNK_MB=n, FDC_L2PF=0|1 (bulk L2 prefetch of the extract's next tile; measured: +1 %, default on), FDC_PACK=0|1 (tiles spanning several blocks when a launch has few channels; default on), FDC_HOST_STAGING=0|1|2 (host path: never / for pageable caller memory (default) / always stage through the library's pinned slots), FDC_COPY_THREADS=n (threads of the staging copy pool), FDC_SINK_DMA=0|1 (channel-sharded sinks: 0 (default) the extract kernel stores into the owners' memory itself, 1 rows of remote owners go to a local staging slab and the copy engines forward them behind the kernels; measured on 2 GPUs: 111 against 97 Gsample/s), FDC_FUSED=0|1 (N >= 32768: forward transform inside a thread-block cluster, the four-step transpose over distributed shared memory, fdc_k_fused.cu)) */
-struct Tuning { int prefetch; int ctas_per_sm; int streams; int extract_e8; int ctas_fwd; int ctas_ext; int pdl; int fwd_split; int host_chunk_mb; int extract_e32; int fwd_e32; int l2pf; int pack; int fused; int host_staging; int sink_dma; };
+/* run-time switches for measurements (environment: FDC_PREFETCH=bit 0 forward kernels | bit 1 extract kernels, FDC_CTAS_FWD / FDC_CTAS_EXT=n, FDC_CTAS_PER_SM=n, FDC_STREAMS=1..4, FDC_EXTRACT_E8=-1 (auto: slices <= 64) | 0 | 1, FDC_PDL=0|1, FDC_FWD_SPLIT=N, FDC_EXTRACT_E32=0|1, FDC_FWD_E32=0|1|2 (2: also 512/1024-point transforms), FDC_HOST_CHUNK_MB=n, FDC_L2PF=0|1 (bulk L2 prefetch of the extract's next tile; measured: +1 %, default on), FDC_PACK=0|1 (tiles spanning several blocks when a launch has few channels; default on), FDC_HOST_STAGING=0|1|2 (host path: never / for pageable caller memory (default) / always stage through the library's pinned slots), FDC_COPY_THREADS=n (threads of the staging copy pool), FDC_SINK_DMA=0|1 (channel-sharded sinks: 0 (default) the extract kernel stores into the owners' memory itself, 1 rows of remote owners go to a local staging slab and the copy engines forward them behind the kernels; measured on 2 GPUs: 111 against 97 Gsample/s), FDC_FUSE_SMALL=0|1|2 (N <= 16384, one slice length: forward transform and all channels in ONE kernel, the spectrum stays in shared memory, fdc_k_chanfused.cu; 1: one thread group does both halves in turn, 2: two groups of one CTA, forward and extract, hand spectra over through named barriers; measured on cfg2 107 / 100 against 112 Gsample/s of the two kernels, cfg1 100 / 86 against 97, default 0), FDC_FUSED=0|1 (N >= 32768: forward transform inside a thread-block cluster, the four-step transpose over distributed shared memory, fdc_k_fused.cu)) */
+struct Tuning { int prefetch; int ctas_per_sm; int streams; int extract_e8; int ctas_fwd; int ctas_ext; int pdl; int fwd_split; int host_chunk_mb; int extract_e32; int fwd_e32; int l2pf; int pack; int fused; int host_staging; int sink_dma; int fuse_small; };
 const Tuning& tuning();
 
 /* per-pass Stockham twiddles of a length-L tile FFT (layout of fdc_tile_fft.cuh: pass p at fft_twoff(L, p), entry
@@ -31,6 +31,9 @@ cudaError_t launch_fwd_cluster(const BigParams& p, int N, cudaStream_t s);
 /* nsel channels sharing slice length l */
 cudaError_t launch_extract(const ExtractParams& p, int l, cudaStream_t s);
 cudaError_t launch_jobs(const JobParams& p, int l, cudaStream_t s);
+/* K1 + K2 in one kernel (N <= 16384, every channel of slice length l): the spectrum never leaves shared memory */
+bool chan_fused_supported(int N, int l);
+cudaError_t launch_chan_fused(const FwdParams& fp, const ExtractParams& xp, int l, cudaStream_t s);
 cudaError_t launch_plain_fft(const PlainParams& p, int L, int forward, cudaStream_t s);
 
 /* out row b (row_bytes) <- src[b*src_stride + src_off ...); source bytes before 0 come from hist

@@ -66,6 +66,7 @@ SIGNATURES = {
     "fdc_chan_get_profile": (_i, [_vp, _dp, _dp, C.POINTER(C.c_long)]),
     "fdc_chan_set_sinks": (_i, [_vp, _i, _vp, _vp, _i]),
     "fdc_chan_work_device_sinks": (_i, [_vp, _vp, _l, _l, _l, _vp]),
+    "fdc_chan_is_fused": (_i, [_vp]),
     "fdc_chan_chunk_blocks": (_i, [_vp]),
     "fdc_chan_set_chunk_blocks": (_i, [_vp, _i]),
     "fdc_overlap_save_create": (_vp, [_i, _i, _i]),

@@ -131,6 +131,9 @@ int fdc_chan_work_device_sinks(fdc_chan* c, const void* d_in, long nblocks, long
  * per-channel chains; overlap-save and the forward FFT are skipped.  d_spectrum (optional) receives the normalised
  * spectra for the activity-gated blocks / the debug port. */
 int fdc_chan_work_spectrum_device(fdc_chan* c, const void* d_spectra, long nblocks, void* d_out, void* d_spectrum, void* stream);
+/* 1 when calls that do not ask for the spectrum run overlap-save, forward FFT and all channels as ONE kernel (N <= 16384, every
+ * channel of the same slice length; the spectrum stays in shared memory) */
+int fdc_chan_is_fused(const fdc_chan* c);
 int fdc_chan_sync(fdc_chan* c);
 /* Measurement hooks.  Profiling records CUDA events around the forward-FFT and the channel-extract kernels of every
  * chunk; get_profile synchronises and returns the summed kernel times (ms) since the last call.  chunk_blocks is

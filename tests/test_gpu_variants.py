@@ -23,6 +23,8 @@ VARIANTS = {
     "four_step_from_4096": {"FDC_FWD_SPLIT": "4096"},
     "one_cta_per_sm": {"FDC_CTAS_PER_SM": "1"},
     "cluster_fused_forward": {"FDC_FUSED": "1"},
+    "one_kernel_for_short_transforms": {"FDC_FUSE_SMALL": "1"},
+    "one_kernel_two_thread_groups": {"FDC_FUSE_SMALL": "2"},
     "sinks_forwarded_by_the_copy_engines": {"FDC_SINK_DMA": "1"},
 }
 
