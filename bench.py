@@ -332,8 +332,8 @@ def cfg3_cpu_reference(nb, N, R, hop, x, segs, pac, pool, seconds=10.0):
     dtc = time.perf_counter() - t1
     ref.set_fft_mode(0)
     return {"value": reps * nb * hop / dtc / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "reference",
-            "sample": "%d x %d blocks, reference overlap_save + restated fft_vcc on all cores, then the unmodified SegmentDetection x2 and "
-                      "PowerActivationChannel x16 blocks, one thread per block as under GNU Radio's thread-per-block scheduler, %.1f s" % (reps, nb, dtc)}
+            "sample": "%d x %d blocks, reference overlap_save + restated fft_vcc on all cores, then the unmodified SegmentDetection x%d and "
+                      "PowerActivationChannel x%d blocks, one thread per block as under GNU Radio's thread-per-block scheduler, %.1f s" % (reps, nb, len(segs), len(pac), dtc)}
 
 
 def run_cfg3_reference(args):
@@ -448,7 +448,7 @@ def main():
         ACT = ACTIVITY[args.workload]
         if args.impl == "reference":
             return run_cfg3_reference(args) if rank == 0 else 0
-        if world > 1:
+        if world > 1 or os.environ.get("FDC_BENCH_FORCE_SHARDED") == "1":       # the latter: the time-sharded call sequence on one rank (measurement aid, under torchrun)
             return run_cfg3_sharded(args, rank, world, local)
         return run_cfg3(args, rank, world, local) if rank == 0 else 0
     cfg = WORKLOADS[args.workload]()

@@ -130,42 +130,50 @@ SegGeometry actdet_geometry(int blocklen, float v0, float v1, int D)
 }
 
 /* ---- SegmentState --------------------------------------------------------------------------------- */
-typedef std::pair<float, size_t> fipair;
-/* the reference's comparison (descending ratio) as an inlinable functor: std::sort's sequence of comparisons and moves depends
- * only on the comparison results, so the order among equal ratios stays the reference's */
-struct fipair_desc_t { bool operator()(const fipair& a, const fipair& b) const { return a.first > b.first; } };
+/* the reference's comparison (descending ratio, `fipair_sort`) as an inlinable functor: std::sort's sequence of comparisons and
+ * moves depends only on the comparison results and the length, so the order among equal ratios stays the reference's whatever
+ * the second member is (the reference carries the bin, this code the power-bin index) */
+struct ratio_desc_t { bool operator()(const std::pair<float, int>& a, const std::pair<float, int>& b) const { return a.first > b.first; } };
 
-void SegmentState::candidates(const EdgeBlock& e, std::deque<std::array<long, 2> >& poss) const
+void SegmentState::candidates(const EdgeBlock& e, CandList& poss) const
 {
     /* lib/SegmentDetection_impl.cc:195-244.  Same order of operations as the reference: rising edges sorted by ratio with
      * the same std::sort call (introsort makes the same comparisons and moves on any random-access range, so ties between
      * equal ratios resolve as in the reference's deque), then walked from the strongest down.  The scratch vectors live for
      * the thread's lifetime: no allocation per block. */
-    static thread_local std::vector<fipair> rise;
-    static thread_local std::vector<size_t> fall;
-    rise.clear(); fall.clear();
-    for (size_t n = 0; n < e.rise.size(); n++) rise.push_back(fipair(e.rise[n].first, (size_t)e.rise[n].second * (size_t)g.D + (size_t)g.start));
-    for (size_t n = 0; n < e.fall.size(); n++) fall.push_back(((size_t)e.fall[n] + 1) * (size_t)g.D + (size_t)g.start);
-    std::sort(rise.begin(), rise.end(), fipair_desc_t());
-    /* The reference tests a new candidate against every accepted one (quadratic in the number of carriers; a wideband
-     * segment has hundreds per block).  Candidates start and end on the detection raster (bin = start + D * p), so the
-     * accepted ones are recorded in an occupancy map over the raster points: candidate [a, b) owns the points a .. b-1.  The
-     * reference's test "s < b && e >= a" for some accepted [a, b) is "one of the points s .. e is owned" -- same decisions,
-     * a few loads per candidate.  match() uses the same map. */
+    static thread_local std::vector<std::pair<float, int> > rise;
+    rise.assign(e.rise.begin(), e.rise.end());
+    std::sort(rise.begin(), rise.end(), ratio_desc_t());
+    /* Everything below works on the detection raster (power-bin index p <-> bin start + D * p): a rising edge at power bin r
+     * starts a candidate at raster point r, a falling edge at power bin f ends one at raster point f + 1, and the reference's
+     * upper_bound over the falling BINS for the first one above the rising bin is the first f >= r.
+     * The reference tests a new candidate against every accepted one (quadratic in the number of carriers; a wideband
+     * segment has hundreds per block).  The accepted ones are recorded in an occupancy map over the raster points: candidate
+     * [a, b) owns the points a .. b-1.  The reference's test "s < b && e >= a" for some accepted [a, b) is "one of the points
+     * s .. e is owned" -- same decisions, asked of a bit set of the owned points (a noise edge far from the next falling edge
+     * would otherwise walk hundreds of map entries).  match() uses the map to find WHICH candidate owns a point. */
+    const std::vector<int>& fall = e.fall;
     std::vector<int>& own = owner_map();
     own.assign((size_t)g.M + 2, 0);
+    static thread_local std::vector<unsigned long long> busy;
+    busy.assign(((size_t)g.M + 2 + 63) / 64, 0ull);
     for (size_t r = 0; r < rise.size(); r++) {
-        const size_t poss_start = rise[r].second;
-        std::vector<size_t>::iterator next_end = std::upper_bound(fall.begin(), fall.end(), poss_start);
+        const int ps = rise[r].second;
+        std::vector<int>::const_iterator next_end = std::lower_bound(fall.begin(), fall.end(), ps);
         if (next_end == fall.end()) continue;
-        const long ps = ((long)poss_start - g.start) / g.D, pe = ((long)*next_end - g.start) / g.D;
-        bool overlapping = false;
-        for (long q = ps; q <= pe; q++)
-            if (own[(size_t)q]) { overlapping = true; break; }
+        const int pe = *next_end + 1;
+        const size_t w0 = (size_t)ps >> 6, w1 = (size_t)pe >> 6;
+        const unsigned long long m0 = ~0ull << (ps & 63), m1 = ~0ull >> (63 - (pe & 63));
+        bool overlapping;
+        if (w0 == w1) overlapping = (busy[w0] & m0 & m1) != 0;
+        else {
+            overlapping = (busy[w0] & m0) != 0 || (busy[w1] & m1) != 0;
+            for (size_t w = w0 + 1; w < w1 && !overlapping; w++) overlapping = busy[w] != 0;
+        }
         if (overlapping) continue;
-        const std::array<long, 2> a = {{(long)poss_start, (long)*next_end}};
+        const std::array<long, 2> a = {{(long)ps * g.D + g.start, (long)pe * g.D + g.start}};
         poss.push_back(a);
-        for (long q = ps; q < pe; q++) own[(size_t)q] = (int)poss.size();       /* 1 + position in poss */
+        for (int q = ps; q < pe; q++) { own[(size_t)q] = (int)poss.size(); busy[(size_t)q >> 6] |= 1ull << (q & 63); }       /* 1 + position in poss */
     }
 }
 
@@ -196,18 +204,25 @@ bool SegmentState::activate(long detect_start, long detect_end, long& uid_counte
     ActiveChannel c;
     c.ID = (int)chan_counter++;
     c.detect_start = (int)detect_start; c.detect_stop = (int)detect_end;
+    c.ras_lo = (int)std::max(0l, (detect_start - g.start) / g.D - 1); c.ras_hi = (int)std::min((long)g.M, (detect_end - g.start) / g.D - 1);
     c.extract_start = (int)extract_start; c.extract_stop = (int)extract_end; c.extract_width = (int)extract_width;
     c.extract_window = (int)log2((double)extract_width);
     c.ovlskip = (int)(extract_width / relinvovl);
     c.outputsamples = c.extract_width - c.ovlskip;
     c.count = 0; c.phase = 0; c.phaseincrement = (int)(extract_start % relinvovl); c.inactive = -1; c.part = 0;
-    c.msg_ID = current_time_string() + std::string(".DETECTED.") + std::to_string(seg_id) + std::string(".") + std::to_string(c.ID);
+    {   /* "<time>.DETECTED.<segID>.<chanID>", lib/SegmentDetection_impl.cc:674-678; one formatted write (a wideband segment activates
+         * hundreds of carriers per block) */
+        const std::string t = current_time_string();
+        char id[128];
+        const int n = snprintf(id, sizeof(id), "%s.DETECTED.%d.%d", t.c_str(), seg_id, c.ID);
+        c.msg_ID.assign(id, (size_t)(n < 0 ? 0 : std::min(n, (int)sizeof(id) - 1)));
+    }
     c.uid = uid_counter++; c.ndata = 0;
-    active.push_back(c);
+    active.push_back(std::move(c));
     return true;
 }
 
-void SegmentState::match(std::deque<std::array<long, 2> >& poss, long& uid_counter)
+void SegmentState::match(CandList& poss, long& uid_counter)
 {
     /* lib/SegmentDetection_impl.cc:246-288 */
     if (poss.empty()) {
@@ -225,10 +240,7 @@ void SegmentState::match(std::deque<std::array<long, 2> >& poss, long& uid_count
     for (size_t k = 0; k < active.size(); k++) {
         ActiveChannel& c = active[k];
         bool inactive = true;
-        long lo = ((long)c.detect_start - g.start) / g.D - 1, hi = ((long)c.detect_stop - g.start) / g.D - 1;
-        if (lo < 0) lo = 0;
-        if (hi > g.M) hi = g.M;
-        for (long q = lo; q <= hi; q++) {
+        for (int q = c.ras_lo; q <= c.ras_hi; q++) {
             const int id = own[(size_t)q];
             if (!id || dead[(size_t)id - 1]) continue;
             dead[(size_t)id - 1] = 1;
@@ -294,7 +306,8 @@ void SegmentState::emit_partial(ActiveChannel& c, long blockcount, std::vector<A
 
 void SegmentState::block(int row, const EdgeBlock& e, long blockcount, long& uid_counter, std::vector<ActJob>& jobs, std::vector<ActOp>& ops)
 {
-    std::deque<std::array<long, 2> > poss;
+    static thread_local CandList poss;          /* scratch: no allocation per block */
+    poss.clear();
     candidates(e, poss);
     match(poss, uid_counter);
     /* process_active_channels_single_thread, lib/SegmentDetection_impl.cc:346-365 */

@@ -66,6 +66,7 @@ struct ActiveChannel {
     std::string msg_ID;
     long uid;
     int ndata;                    /* number of buffered blocks (the reference's data.size()) */
+    int ras_lo, ras_hi;           /* raster points a candidate must own one of to count as this channel (match()) */
 };
 struct EdgeBlock {                /* detection result of one block, ascending bin order */
     std::vector<std::pair<float, int> > rise;    /* (ratio, power-bin index i) */
@@ -102,9 +103,10 @@ public:
     /* detection + bookkeeping of one block; `blockcount` is the reference's counter value during this block */
     void block(int row, const EdgeBlock& e, long blockcount, long& uid_counter, std::vector<ActJob>& jobs, std::vector<ActOp>& ops);
 private:
-    void candidates(const EdgeBlock& e, std::deque<std::array<long, 2> >& poss) const;
+    typedef std::vector<std::array<long, 2> > CandList;          /* accepted [start, end) candidates of a block, strongest first */
+    void candidates(const EdgeBlock& e, CandList& poss) const;
     static std::vector<int>& owner_map();
-    void match(std::deque<std::array<long, 2> >& poss, long& uid_counter);
+    void match(CandList& poss, long& uid_counter);
     bool activate(long detect_start, long detect_end, long& uid_counter);
     void job(ActiveChannel& c, int row, std::vector<ActJob>& jobs, std::vector<ActOp>& ops);
     void emit_final(ActiveChannel& c, long blockcount, std::vector<ActOp>& ops);

@@ -72,6 +72,7 @@ int fdc_host_unregister(void* p)
     const cudaError_t e = cudaHostUnregister(p);
     return e == cudaSuccess ? 0 : cuda_fail(e, "cudaHostUnregister");
 }
+void fdc_host_evict(const void* p, size_t bytes) { if (p) evict_lines(p, bytes); }
 unsigned long long fdc_launch_count(void) { return launch_count(); }
 void* fdc_dev_alloc(size_t bytes)
 {
@@ -714,10 +715,10 @@ static int host_drain_slot(fdc_chan* c, int slot, HostSlotJob& j, long nblocks, 
             if (!outs[i]) continue;
             const long lo = c->chans[i].lout;
             const size_t bytes = sizeof(float2) * (size_t)(j.nb * lo);
-            if (bytes >= (128u << 10)) copy_pool().submit((float2*)outs[i] + j.b0 * lo, src + j.nb * c->chans[i].lout_prefix, bytes);
+            if (bytes >= (128u << 10)) copy_pool().submit((float2*)outs[i] + j.b0 * lo, src + j.nb * c->chans[i].lout_prefix, bytes, true);
             else { vd.push_back((float2*)outs[i] + j.b0 * lo); vs.push_back(src + j.nb * c->chans[i].lout_prefix); vb.push_back(bytes); }
         }
-        if (!vd.empty()) copy_pool().submit_many(vd.data(), vs.data(), vb.data(), vd.size());
+        if (!vd.empty()) copy_pool().submit_many(vd.data(), vs.data(), vb.data(), vd.size(), true);
         copy_pool().wait();
     }
     j.busy = false;

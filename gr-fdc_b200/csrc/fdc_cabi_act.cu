@@ -15,6 +15,7 @@
 #include <cstring>
 #include <iostream>
 #include <map>
+#include <unordered_map>
 
 using namespace fdc;
 
@@ -64,7 +65,7 @@ struct ActEngine {
         std::vector<std::pair<const cfloat*, size_t> > segs; size_t seg_head;   /* blocks of this call, in order */
         size_t nblocks;
         Pending() : head(0), nowned(0), seg_head(0), nblocks(0) {}
-        void push(const cfloat* p, size_t n) { segs.push_back(std::make_pair(p, n)); nblocks++; }
+        void push(const cfloat* p, size_t n) { if (segs.capacity() == 0) segs.reserve(8); segs.push_back(std::make_pair(p, n)); nblocks++; }
         /* the first nb buffered blocks -> out (null: drop them).  With `later`, copies out of the current call's result buffer are
          * only recorded there (destination, source, bytes) and done in one parallel batch at the end of the replay; blocks kept from
          * earlier calls are copied at once (their buffer may be dropped by a later op) */
@@ -82,7 +83,7 @@ struct ActEngine {
             for (; nb > 0 && seg_head < segs.size(); nb--, seg_head++) {
                 if (out) {
                     if (later) { later->dst.push_back(out); later->src.push_back(segs[seg_head].first); later->bytes.push_back(sizeof(cfloat) * segs[seg_head].second); }
-                    else memcpy(out, segs[seg_head].first, sizeof(cfloat) * segs[seg_head].second);
+                    else copy_and_evict(out, segs[seg_head].first, sizeof(cfloat) * segs[seg_head].second);
                     out += segs[seg_head].second;
                 }
             }
@@ -100,7 +101,10 @@ struct ActEngine {
         {
             if (segs.empty()) return;
             if (head > (1u << 20)) { data.erase(data.begin(), data.begin() + head); head = 0; }
-            for (size_t k = seg_head; k < segs.size(); k++) { data.insert(data.end(), segs[k].first, segs[k].first + segs[k].second); nowned++; }
+            for (size_t k = seg_head; k < segs.size(); k++) {
+                data.insert(data.end(), segs[k].first, segs[k].first + segs[k].second); nowned++;
+                evict_lines(segs[k].first, sizeof(cfloat) * segs[k].second);         /* the result buffer is a D2H destination again next call */
+            }
             segs.clear(); seg_head = 0;
         }
     };
@@ -131,11 +135,12 @@ struct ActEngine {
             OutMsg& m = msgs[i];
             if (!m.ptr || !m.n || m.ptr < lo || m.ptr >= hi) continue;
             cfloat* keep = arena.alloc(m.n);
-            memcpy(keep, m.ptr, sizeof(cfloat) * m.n);
+            copy_and_evict(keep, m.ptr, sizeof(cfloat) * m.n);
             m.ptr = keep;
         }
     }
-    std::map<long, Pending> pending;
+    typedef std::unordered_map<long, Pending> PendingMap;          /* a busy segment replays ~10 ops per block: hashed, not ordered */
+    PendingMap pending;
     std::vector<OutMsg> msgs;
     long uid_counter;
     bool logic_only;               /* host-logic hooks: no device, messages carry metadata and sample counts only */
@@ -152,33 +157,54 @@ struct ActEngine {
         return d_tab.upload(tab.data(), sizeof(cfloat) * tab.size());
     }
 
-    /* run extraction jobs [j0, j1) of a call from the spectrum rows at d_rows (row `row0` of the call is d_rows[0]; the row before
-     * it is `d_prev`, the saved history block when that is null); results land in h_out, job j at dst[j] (job order) */
-    int extract(const float2* d_rows, const float2* d_prev, const std::vector<ActJob>& jobs, size_t j0, size_t j1, int row0,
-                std::vector<long>& dst, long* total_out, cudaStream_t st, float2* d_dst = 0, bool group_by_channel = false)
+    /* result offsets of jobs [j0, j1) laid out channel by channel (uid), blocks of a channel in order: a burst that is published in the
+     * call it was extracted in is then ONE contiguous run of the result buffer and the PDU can point at it (no copy into the arena).
+     * Returns the number of samples, -1 when the uids are too sparse for the counting pass (the caller keeps job order). */
+    static long channel_layout(const std::vector<ActJob>& jobs, size_t j0, size_t j1, std::vector<long>& dst)
     {
-        dst.assign(jobs.size(), 0);
+        if (j1 <= j0) return 0;
+        long lo = jobs[j0].uid, hi = jobs[j0].uid;
+        for (size_t i = j0; i < j1; i++) { lo = std::min(lo, jobs[i].uid); hi = std::max(hi, jobs[i].uid); }
+        if (hi - lo >= (long)(4 * (j1 - j0)) + 1024) return -1;
+        std::vector<long> run((size_t)(hi - lo + 2), 0);
+        for (size_t i = j0; i < j1; i++) run[(size_t)(jobs[i].uid - lo) + 1] += jobs[i].L - jobs[i].skip;
+        for (size_t k = 1; k < run.size(); k++) run[k] += run[k - 1];
+        for (size_t i = j0; i < j1; i++) { long& r = run[(size_t)(jobs[i].uid - lo)]; dst[i] = r; r += jobs[i].L - jobs[i].skip; }
+        return run[run.size() - 1];
+    }
+    /* run extraction jobs [j0, j1) of a call from the spectrum rows at d_rows (row `row0` of the call is d_rows[0]; the row before
+     * it is `d_prev`, the saved history block when that is null); results land in h_out, job j at dst[j] (job order, or by channel);
+     * `layout`: offsets of ALL jobs of the call decided beforehand (time-sharded calls, every rank stores into one common run) */
+    int extract(const float2* d_rows, const float2* d_prev, const std::vector<ActJob>& jobs, size_t j0, size_t j1, int row0,
+                std::vector<long>& dst, long* total_out, cudaStream_t st, float2* d_dst = 0, bool group_by_channel = false,
+                const std::vector<long>* layout = 0)
+    {
         long total = 0;
-        if (group_by_channel && j1 > j0) {
-            /* results laid out channel by channel (uid), blocks of a channel in order: a burst that is published in the call it was
-             * extracted in is then ONE contiguous run of the result buffer and the PDU can point at it (no copy into the arena) */
-            long lo = jobs[j0].uid, hi = jobs[j0].uid;
-            for (size_t i = j0; i < j1; i++) { lo = std::min(lo, jobs[i].uid); hi = std::max(hi, jobs[i].uid); }
-            if (hi - lo < (long)(4 * (j1 - j0)) + 1024) {
-                std::vector<long> run((size_t)(hi - lo + 2), 0);
-                for (size_t i = j0; i < j1; i++) run[(size_t)(jobs[i].uid - lo) + 1] += jobs[i].L - jobs[i].skip;
-                for (size_t k = 1; k < run.size(); k++) run[k] += run[k - 1];
-                for (size_t i = j0; i < j1; i++) { long& r = run[(size_t)(jobs[i].uid - lo)]; dst[i] = r; r += jobs[i].L - jobs[i].skip; }
-                total = run[run.size() - 1];
-            } else group_by_channel = false;
+        PhaseClock xc;
+        if (layout) {
+            dst = *layout;
+            for (size_t i = j0; i < j1; i++) total += jobs[i].L - jobs[i].skip;
+        } else {
+            dst.assign(jobs.size(), 0);
+            if (group_by_channel) {
+                total = channel_layout(jobs, j0, j1, dst);
+                if (total < 0) { group_by_channel = false; total = 0; }
+            }
+            if (!group_by_channel) for (size_t i = j0; i < j1; i++) { dst[i] = total; total += jobs[i].L - jobs[i].skip; }
         }
-        if (!group_by_channel) for (size_t i = j0; i < j1; i++) { dst[i] = total; total += jobs[i].L - jobs[i].skip; }
         *total_out = total;
         if (j1 <= j0 || logic_only) return 0;
         /* group by IFFT length */
         std::vector<int> order(j1 - j0);
-        for (size_t i = 0; i < order.size(); i++) order[i] = (int)(j0 + i);
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return jobs[a].L < jobs[b].L; });
+        {   /* stable counting sort by log2(L): one pass to count, one to place (a wideband segment has tens of thousands of jobs per call) */
+            size_t first[34]; for (int b = 0; b < 34; b++) first[b] = 0;
+            for (size_t i = j0; i < j1; i++) {
+                if (!tile_len_supported(jobs[i].L)) return fail("activity channel wider than 16384 bins is not supported by the extract kernel");
+                first[__builtin_ctz((unsigned)jobs[i].L) + 1]++;
+            }
+            for (int b = 1; b < 34; b++) first[b] += first[b - 1];
+            for (size_t i = j0; i < j1; i++) order[first[__builtin_ctz((unsigned)jobs[i].L)]++] = (int)i;
+        }
         std::vector<ExtractJob> ej(order.size());
         for (size_t k = 0; k < order.size(); k++) {
             const ActJob& j = jobs[order[k]];
@@ -187,10 +213,14 @@ struct ActEngine {
             if (ej[k].row < -1) return fail("activity extract: job refers to a row this shard does not hold");
         }
         if (!d_dst) rescue_views();
+        xc.lap();
         /* d_dst: the caller's device buffer (possibly peer memory of the sink rank), results stay on the device */
         if (!d_jobs.upload(ej.data(), sizeof(ExtractJob) * ej.size()) ||
             (!d_dst && (!d_out.reserve(sizeof(float2) * (size_t)total) || !h_out_buf().reserve(sizeof(float2) * (size_t)total))))
             return cuda_fail(cudaGetLastError(), "activity extract buffers");
+        xc.lap();
+        cudaEvent_t ev[3] = {0, 0, 0};
+        if (act_timing()) { for (int i = 0; i < 3; i++) cudaEventCreate(&ev[i]); cudaEventRecord(ev[0], st); }
         size_t k = 0;
         while (k < order.size()) {
             size_t e = k; const int L = jobs[order[k]].L;
@@ -201,9 +231,19 @@ struct ActEngine {
             if (ce != cudaSuccess) return cuda_fail(ce, "activity extract launch");
             k = e;
         }
+        xc.lap();
+        if (ev[1]) cudaEventRecord(ev[1], st);
         cudaError_t ce = d_dst ? cudaSuccess : cudaMemcpyAsync(h_out_buf().p, d_out.p, sizeof(float2) * (size_t)total, cudaMemcpyDeviceToHost, st);
+        if (ev[2]) cudaEventRecord(ev[2], st);
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
         if (ce != cudaSuccess) return cuda_fail(ce, "activity extract D2H");
+        xc.lap();
+        if (act_timing()) {
+            float tk = 0, tc = 0; cudaEventElapsedTime(&tk, ev[0], ev[1]); cudaEventElapsedTime(&tc, ev[1], ev[2]);
+            for (int i = 0; i < 3; i++) cudaEventDestroy(ev[i]);
+            fprintf(stderr, "  extract: layout + job list %.3f ms, upload + buffers %.3f ms, launches %.3f ms, wait for kernels + D2H %.3f ms (device: kernels %.3f ms, D2H %.3f ms)\n",
+                    xc.ms[0], xc.ms[1], xc.ms[2], xc.ms[3], tk, tc);
+        }
         return 0;
     }
     /* replay the ops of a call on the extracted blocks (res + dst[job]) -> PDUs / files in the reference's order */
@@ -235,7 +275,7 @@ struct ActEngine {
             } else {
                 Pending& q = pending[o.uid];
                 const size_t ntake = o.ntake < 0 ? q.nblocks : std::min((size_t)o.ntake, q.nblocks);
-                OutMsg m; m.meta = *o.meta;
+                OutMsg m; m.meta = std::move(*o.meta);          /* an op list is replayed once: its strings move into the message */
                 m.n = ntake * (size_t)o.blocksamples;
                 const bool wanted = m.meta.publish || !m.meta.filename.empty();
                 /* only results in the engine's own pinned buffer may be handed out as views (shard_assemble replays the caller's memory) */
@@ -250,7 +290,7 @@ struct ActEngine {
                 if (!m.meta.filename.empty()) {
                     FILE* fh = fopen(m.meta.filename.c_str(), "wb");
                     if (!fh) std::cerr << "Cannot write to file " << m.meta.filename << std::endl;
-                    else { if (m.n) fwrite(m.ptr, sizeof(cfloat), m.n, fh); fclose(fh); }
+                    else { if (m.n) { fwrite(m.ptr, sizeof(cfloat), m.n, fh); if (direct) evict_lines(m.ptr, sizeof(cfloat) * m.n); } fclose(fh); }
                 }
                 if (!m.meta.logline.empty()) log_line(verbose, logfile, m.meta.logline);
                 if (m.meta.publish) msgs.push_back(std::move(m));
@@ -258,10 +298,10 @@ struct ActEngine {
         }
         if (!later.dst.empty()) {
             /* tens of MB per call when the results are not channel-contiguous (time-sharded calls): the copy pool instead of one memcpy after the other */
-            copy_pool().submit_many(later.dst.data(), later.src.data(), later.bytes.data(), later.dst.size());
+            copy_pool().submit_many(later.dst.data(), later.src.data(), later.bytes.data(), later.dst.size(), true);
             copy_pool().wait();
         }
-        for (std::map<long, Pending>::iterator it = pending.begin(); it != pending.end(); ++it) it->second.keep();
+        for (PendingMap::iterator it = pending.begin(); it != pending.end(); ++it) it->second.keep();
     }
     /* run all extraction jobs of a call and replay the ops */
     int finish(const float2* d_rows, std::vector<ActJob>& jobs, const std::vector<ActOp>& ops, cudaStream_t st)
@@ -278,7 +318,8 @@ struct ActEngine {
      * results (`assemble`). */
     struct ShardCall {
         std::vector<char> blob; std::vector<ActJob> jobs; std::vector<ActOp> ops; std::vector<long> job_first; bool decided;
-        ShardCall() : decided(false) {}
+        bool by_channel; std::vector<long> layout;     /* shard_layout(1): offsets of all jobs of the call, channel by channel */
+        ShardCall() : decided(false), by_channel(false) {}
     } sh;
     template <class T> void blob_put(const T& v) { const char* c = (const char*)&v; sh.blob.insert(sh.blob.end(), c, c + sizeof(T)); }
     void blob_put_edges(const EdgeBlock& e)
@@ -301,7 +342,7 @@ struct ActEngine {
     }
     void shard_begin(int nblocks_total)
     {
-        sh.jobs.clear(); sh.ops.clear(); sh.job_first.assign(1, 0); sh.decided = false;
+        sh.jobs.clear(); sh.ops.clear(); sh.job_first.assign(1, 0); sh.decided = false; sh.by_channel = false; sh.layout.clear();
         sh.jobs.reserve((size_t)nblocks_total * 16 + 16); sh.ops.reserve((size_t)nblocks_total * 18 + 16);
     }
     bool shard_rows_ok(int first_row, int nrows) const
@@ -313,6 +354,19 @@ struct ActEngine {
         for (long j = sh.job_first[(size_t)first_row]; j < sh.job_first[(size_t)(first_row + nrows)]; j++) t += sh.jobs[(size_t)j].L - sh.jobs[(size_t)j].skip;
         return t;
     }
+    /* by_channel: the device form of the call keeps ONE run per block instance for all ranks, laid out channel by channel; d_dst of
+     * shard_extract_device and d_results of shard_assemble_device are then the start of that run, and bursts that begin and end
+     * inside the call become views of the assembled buffer.  Every rank derives the same offsets from the same job list.
+     * Returns the samples of the whole call. */
+    long shard_layout(int by_channel)
+    {
+        if (!sh.decided) return fail("shard call: nothing decided");
+        sh.layout.assign(sh.jobs.size(), 0);
+        long total = by_channel ? channel_layout(sh.jobs, 0, sh.jobs.size(), sh.layout) : -1;
+        sh.by_channel = total >= 0;
+        if (!sh.by_channel) { total = 0; for (size_t i = 0; i < sh.jobs.size(); i++) { sh.layout[i] = total; total += sh.jobs[i].L - sh.jobs[i].skip; } }
+        return total;
+    }
     long shard_extract(int first_row, int nrows, const void* d_rows, const void* d_prev, void* stream, void* out_host)
     {
         if (!shard_rows_ok(first_row, nrows)) return fail("shard call: rows out of range or no decided call");
@@ -321,7 +375,7 @@ struct ActEngine {
         std::vector<long> dst; long total = 0;
         if (extract((const float2*)d_rows, (const float2*)d_prev, sh.jobs, (size_t)sh.job_first[(size_t)first_row],
                     (size_t)sh.job_first[(size_t)(first_row + nrows)], first_row, dst, &total, st)) return -1;
-        if (!logic_only && total > 0 && out_host) memcpy(out_host, h_out_buf().p, sizeof(float2) * (size_t)total);
+        if (!logic_only && total > 0 && out_host) { copy_pool().submit(out_host, h_out_buf().p, sizeof(float2) * (size_t)total, true); copy_pool().wait(); }
         return total;
     }
     long shard_extract_device(int first_row, int nrows, const void* d_rows, const void* d_prev, void* stream, void* d_dst)
@@ -330,7 +384,8 @@ struct ActEngine {
         OnDevice on_dev(dev);
         std::vector<long> dst; long total = 0;
         if (extract((const float2*)d_rows, (const float2*)d_prev, sh.jobs, (size_t)sh.job_first[(size_t)first_row],
-                    (size_t)sh.job_first[(size_t)(first_row + nrows)], first_row, dst, &total, stream ? (cudaStream_t)stream : s, (float2*)d_dst)) return -1;
+                    (size_t)sh.job_first[(size_t)(first_row + nrows)], first_row, dst, &total, stream ? (cudaStream_t)stream : s, (float2*)d_dst, false,
+                    sh.layout.size() == sh.jobs.size() && !sh.jobs.empty() ? &sh.layout : 0)) return -1;
         return total;
     }
     int shard_assemble_device(const void* d_results, long nsamples, void* stream)
@@ -338,6 +393,7 @@ struct ActEngine {
         if (!sh.decided || logic_only) return fail("shard call: nothing decided");
         OnDevice on_dev(dev);
         cudaStream_t st = stream ? (cudaStream_t)stream : s;
+        PhaseClock pc;
         if (nsamples > 0) {
             rescue_views();
             if (!h_out_buf().reserve(sizeof(float2) * (size_t)nsamples)) return cuda_fail(cudaGetLastError(), "assemble buffer");
@@ -345,19 +401,25 @@ struct ActEngine {
             if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
             if (ce != cudaSuccess) return cuda_fail(ce, "assemble D2H");
         }
+        pc.lap();
         static const float2 none = {0.0f, 0.0f};           /* a null result pointer means "drop the call" to shard_assemble */
-        return shard_assemble(h_out_buf().p ? h_out_buf().p : (const void*)&none, nsamples);
+        const size_t nops = sh.ops.size();
+        const int rc = shard_assemble(h_out_buf().p ? h_out_buf().p : (const void*)&none, nsamples, true);
+        pc.lap();
+        if (act_timing()) fprintf(stderr, "shard_assemble_device: D2H of %ld samples %.3f ms, replay of %zu ops %.3f ms (%zu msgs)\n", nsamples, pc.ms[0], nops, pc.ms[1], msgs.size());
+        return rc;
     }
-    int shard_assemble(const void* results, long nsamples)
+    int shard_assemble(const void* results, long nsamples, bool laid_out = false)
     {
         if (!sh.decided) return fail("shard call: nothing decided");
         if (results || logic_only) {
             std::vector<long> dst(sh.jobs.size(), 0); long total = 0;
-            for (size_t i = 0; i < sh.jobs.size(); i++) { dst[i] = total; total += sh.jobs[i].L - sh.jobs[i].skip; }
+            const bool use_layout = laid_out && sh.layout.size() == sh.jobs.size();
+            for (size_t i = 0; i < sh.jobs.size(); i++) { dst[i] = use_layout ? sh.layout[i] : total; total += sh.jobs[i].L - sh.jobs[i].skip; }
             if (!logic_only && total != nsamples) return fail("shard assemble: result size does not match the job list");
             replay((const cfloat*)results, dst, sh.jobs, sh.ops);
         }
-        sh.jobs.clear(); sh.ops.clear(); sh.decided = false;
+        sh.jobs.clear(); sh.ops.clear(); sh.layout.clear(); sh.decided = false; sh.by_channel = false;
         return 0;
     }
     int save_hist(const float2* d_rows, int n, cudaStream_t st)
@@ -381,18 +443,27 @@ struct ActEngine {
     }
     long msg_copy_data(float* out) const
     {
-        long total = 0; size_t big = 0;
+        /* tens of MB per call on a busy segment (a few large bursts or thousands of short ones): the copy pool's streaming copies
+         * instead of one thread's memcpy; payloads that are views of the pinned result buffer are evicted from the CPU caches as
+         * they are read (the buffer is the next call's D2H destination, see fdc_host.cc) */
+        const cfloat* lo = (const cfloat*)h_res.p; const cfloat* hi = lo ? lo + h_res.cap / sizeof(cfloat) : lo;
+        std::vector<void*> vd[2]; std::vector<const void*> vs[2]; std::vector<size_t> vb[2];
+        long total = 0;
         for (size_t i = 0; i < msgs.size(); i++) {
             const OutMsg& m = msgs[i];
             if (m.logic_samples >= 0 || m.n == 0) continue;
             if (out) {
-                /* tens of MB per call on a busy segment: the copy pool's streaming copies instead of one thread's memcpy */
-                if (m.n >= 2048) { copy_pool().submit(out + 2 * total, m.ptr, sizeof(cfloat) * m.n); big++; }
-                else memcpy(out + 2 * total, m.ptr, sizeof(cfloat) * m.n);
+                const int view = (m.ptr >= lo && m.ptr < hi) ? 1 : 0;
+                if (m.n >= (32u << 10)) copy_pool().submit(out + 2 * total, m.ptr, sizeof(cfloat) * m.n, view != 0);
+                else { vd[view].push_back(out + 2 * total); vs[view].push_back(m.ptr); vb[view].push_back(sizeof(cfloat) * m.n); }
             }
             total += (long)m.n;
         }
-        if (big) copy_pool().wait();
+        if (out) {
+            for (int view = 0; view < 2; view++)
+                if (!vd[view].empty()) copy_pool().submit_many(vd[view].data(), vs[view].data(), vb[view].data(), vd[view].size(), view != 0);
+            copy_pool().wait();
+        }
         return total;
     }
     int msg_get(int i, fdc_msg* out) const
@@ -972,6 +1043,8 @@ long fdc_actdet_shard_decide(fdc_actdet* b, int n, const void* blob, long bytes)
     }                                                                                                                              \
     long fdc_##X##_shard_samples(const fdc_##X* b, int first_row, int nrows)                                                      \
     { return b ? b->e.shard_samples(first_row, nrows) : fail("null block"); }                                                     \
+    long fdc_##X##_shard_layout(fdc_##X* b, int by_channel)                                                                       \
+    { return b ? b->e.shard_layout(by_channel) : fail("null block"); }                                                            \
     long fdc_##X##_shard_extract(fdc_##X* b, int first_row, int nrows, const void* d_rows, const void* d_prev, void* stream, void* out_host) \
     { return b ? b->e.shard_extract(first_row, nrows, d_rows, d_prev, stream, out_host) : fail("null block"); }                   \
     int fdc_##X##_shard_assemble(fdc_##X* b, const void* results, long nsamples)                                                  \

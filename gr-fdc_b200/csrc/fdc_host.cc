@@ -102,8 +102,28 @@ float db_to_ratio(float db) { return (float)std::pow(10.0, (double)db / 10.0); }
  * buffer, never something this thread reads back, and a plain memcpy of such a buffer first reads the destination lines it
  * is about to overwrite (measured on the GPU box, tools/hostbw.cc: 6.2 GB/s per thread with memcpy, 12.5 GB/s with
  * non-temporal stores; 45 against 72 GB/s on all 16 cores). */
+/* ---- copies out of a pinned buffer the GPU writes into (D2H destination) ------------------------------------------------
+ * A DMA write into lines that several CPU cores hold in their caches is slow: measured on the GPU box (Xeon, 16 cores, one
+ * socket) a 10 MB D2H copy takes 0.185 ms into a buffer nobody has read and 1.1-2.0 ms after 12 threads have read it
+ * (tools/d2hcache.cu, profiles/r2_d2h_after_cpu_reads.txt).  Flushing the lines after they have been read (clflushopt: they
+ * are clean, nothing is written back) restores 0.185 ms at no measurable cost to the copy.  Every copy the library makes
+ * out of its own D2H destinations therefore evicts what it has read. */
 #if defined(__x86_64__)
 #include <immintrin.h>
+#include <cpuid.h>
+static bool have_clflushopt()
+{
+    static const bool have = [] { unsigned a, b, c, d; return __get_cpuid_count(7, 0, &a, &b, &c, &d) && (b & (1u << 23)); }();
+    return have;
+}
+void evict_lines(const void* p, size_t bytes)
+{
+    if (!bytes) return;
+    const uintptr_t a = (uintptr_t)p & ~(uintptr_t)63, e = (uintptr_t)p + bytes;
+    if (have_clflushopt()) for (uintptr_t q = a; q < e; q += 64) __asm__ volatile("clflushopt %0" : "+m"(*(volatile char*)q));
+    else for (uintptr_t q = a; q < e; q += 64) _mm_clflush((const void*)q);
+    _mm_sfence();
+}
 __attribute__((target("avx2"))) static void stream_copy_avx2(char* dp, const char* sp, size_t n)
 {
     while (n && ((uintptr_t)dp & 31)) { *dp++ = *sp++; n--; }
@@ -112,18 +132,21 @@ __attribute__((target("avx2"))) static void stream_copy_avx2(char* dp, const cha
     _mm_sfence();
     memcpy(dp + v * 32, sp + v * 32, n - v * 32);
 }
-static void stream_copy(void* d, const void* s, size_t n)
+static void stream_copy(void* d, const void* s, size_t n, bool evict_src)
 {
     static const bool avx2 = __builtin_cpu_supports("avx2");
     if (avx2 && n >= 4096) stream_copy_avx2((char*)d, (const char*)s, n); else memcpy(d, s, n);
+    if (evict_src) evict_lines(s, n);
 }
 #else
-static void stream_copy(void* d, const void* s, size_t n) { memcpy(d, s, n); }
+void evict_lines(const void*, size_t) {}
+static void stream_copy(void* d, const void* s, size_t n, bool) { memcpy(d, s, n); }
 #endif
+void copy_and_evict(void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); evict_lines(src, bytes); }
 
 struct CopyPool::Impl {
     /* one contiguous copy, or (many != 0) a run of small copies described by arrays the submitter keeps alive until wait() */
-    struct Piece { char* d; const char* s; size_t n; void* const* md; const void* const* ms; const size_t* mb; size_t many; };
+    struct Piece { char* d; const char* s; size_t n; void* const* md; const void* const* ms; const size_t* mb; size_t many; bool evict; };
     std::vector<std::thread> th;
     std::mutex m; std::condition_variable cv, idle;
     std::deque<Piece> q; size_t inflight; bool stop;
@@ -133,8 +156,8 @@ struct CopyPool::Impl {
         if (q.empty()) return false;
         const Piece p = q.front(); q.pop_front();
         lk.unlock();
-        if (p.many) for (size_t i = 0; i < p.many; i++) stream_copy(p.md[i], p.ms[i], p.mb[i]);
-        else stream_copy(p.d, p.s, p.n);
+        if (p.many) for (size_t i = 0; i < p.many; i++) stream_copy(p.md[i], p.ms[i], p.mb[i], p.evict);
+        else stream_copy(p.d, p.s, p.n, p.evict);
         lk.lock();
         if (--inflight == 0) idle.notify_all();
         return true;
@@ -162,18 +185,18 @@ CopyPool::~CopyPool()
 }
 int CopyPool::threads() const { return (int)d->th.size(); }
 /* queues the copy in pieces; nothing runs before wait() (one wake-up per batch, not per copy) */
-void CopyPool::submit(void* dst, const void* src, size_t bytes)
+void CopyPool::submit(void* dst, const void* src, size_t bytes, bool evict_src)
 {
     if (!bytes) return;
     const size_t piece = 256u << 10;
     std::lock_guard<std::mutex> g(d->m);
     for (size_t off = 0; off < bytes; off += piece) {
         Impl::Piece p; p.d = (char*)dst + off; p.s = (const char*)src + off; p.n = std::min(piece, bytes - off);
-        p.md = 0; p.ms = 0; p.mb = 0; p.many = 0;
+        p.md = 0; p.ms = 0; p.mb = 0; p.many = 0; p.evict = evict_src;
         d->q.push_back(p); d->inflight++;
     }
 }
-void CopyPool::submit_many(void* const* dst, const void* const* src, const size_t* bytes, size_t n)
+void CopyPool::submit_many(void* const* dst, const void* const* src, const size_t* bytes, size_t n, bool evict_src)
 {
     const size_t target = 256u << 10;
     std::lock_guard<std::mutex> g(d->m);
@@ -181,7 +204,7 @@ void CopyPool::submit_many(void* const* dst, const void* const* src, const size_
     while (i < n) {
         size_t j = i, acc = 0;
         while (j < n && (acc < target || j == i)) acc += bytes[j++];
-        Impl::Piece p; p.d = 0; p.s = 0; p.n = 0; p.md = dst + i; p.ms = src + i; p.mb = bytes + i; p.many = j - i;
+        Impl::Piece p; p.d = 0; p.s = 0; p.n = 0; p.md = dst + i; p.ms = src + i; p.mb = bytes + i; p.many = j - i; p.evict = evict_src;
         d->q.push_back(p); d->inflight++;
         i = j;
     }

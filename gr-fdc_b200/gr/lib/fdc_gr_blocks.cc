@@ -44,7 +44,9 @@ pmt::pmt_t to_pdu(const fdc_msg& m)
         d = pmt::dict_add(d, pmt::intern("vectorstart"), pmt::from_long(m.vectorstart));
         d = pmt::dict_add(d, pmt::intern("vectorend"), pmt::from_long(m.vectorend));
     }
-    return pmt::cons(d, pmt::init_c32vector((size_t)m.nsamples, reinterpret_cast<const std::complex<float>*>(m.data)));
+    pmt::pmt_t v = pmt::init_c32vector((size_t)m.nsamples, reinterpret_cast<const std::complex<float>*>(m.data));
+    fdc_host_evict(m.data, sizeof(float) * 2 * (size_t)m.nsamples);     /* the payload may be a view of the next call's D2H destination (fdc_cabi.h) */
+    return pmt::cons(d, v);
 }
 
 /* ---- copy / multiply blocks ------------------------------------------------------------------------------ */

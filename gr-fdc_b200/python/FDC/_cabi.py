@@ -39,6 +39,7 @@ SIGNATURES = {
     "fdc_copy_threads": (_i, []),
     "fdc_host_register": (_i, [_vp, C.c_size_t]),
     "fdc_host_unregister": (_i, [_vp]),
+    "fdc_host_evict": (None, [_vp, C.c_size_t]),
     "fdc_launch_count": (C.c_ulonglong, []),
     "fdc_dev_alloc": (_vp, [C.c_size_t]),
     "fdc_dev_free": (None, [_vp]),
@@ -134,6 +135,7 @@ SIGNATURES = {
     "fdc_pac_shard_blob": (_i, [_vp, _vp]),
     "fdc_pac_shard_decide": (_l, [_vp, _i, _vp, _l]),
     "fdc_pac_shard_samples": (_l, [_vp, _i, _i]),
+    "fdc_pac_shard_layout": (_l, [_vp, _i]),
     "fdc_pac_shard_extract": (_l, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
     "fdc_pac_shard_assemble": (_i, [_vp, _vp, _l]),
     "fdc_pac_shard_extract_device": (_l, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
@@ -143,6 +145,7 @@ SIGNATURES = {
     "fdc_segdet_shard_blob": (_i, [_vp, _vp]),
     "fdc_segdet_shard_decide": (_l, [_vp, _i, _vp, _l]),
     "fdc_segdet_shard_samples": (_l, [_vp, _i, _i]),
+    "fdc_segdet_shard_layout": (_l, [_vp, _i]),
     "fdc_segdet_shard_extract": (_l, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
     "fdc_segdet_shard_assemble": (_i, [_vp, _vp, _l]),
     "fdc_segdet_shard_extract_device": (_l, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
@@ -152,6 +155,7 @@ SIGNATURES = {
     "fdc_actdet_shard_blob": (_i, [_vp, _vp]),
     "fdc_actdet_shard_decide": (_l, [_vp, _i, _vp, _l]),
     "fdc_actdet_shard_samples": (_l, [_vp, _i, _i]),
+    "fdc_actdet_shard_layout": (_l, [_vp, _i]),
     "fdc_actdet_shard_extract": (_l, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
     "fdc_actdet_shard_assemble": (_i, [_vp, _vp, _l]),
     "fdc_actdet_shard_extract_device": (_l, [_vp, _i, _i, _vp, _vp, _vp, _vp]),

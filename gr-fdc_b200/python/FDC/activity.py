@@ -80,6 +80,11 @@ class _MsgBlock(_SyncBlock):
     def shard_samples(self, first_row, nrows):
         return int(check(self._fn("shard_samples")(self._h, int(first_row), int(nrows)), self._name))
 
+    def shard_layout(self, by_channel=True):
+        """device form of the call: one run per block instance for all ranks, channel by channel (fdc_*_shard_layout);
+        returns the samples of the whole call"""
+        return int(check(self._fn("shard_layout")(self._h, 1 if by_channel else 0), self._name))
+
     def shard_extract(self, first_row, nrows, d_rows=0, d_prev=0, stream=0):
         """Step 4: samples of the jobs this rank's rows emitted, in job order (complex64)."""
         out = np.empty(self.shard_samples(first_row, nrows), dtype=np.complex64)

@@ -297,12 +297,16 @@ class ShardedActivityGroup(object):
         own_of = [i % self.world for i in idx]
         per_owner = [sum(total[i] for i in idx if own_of[i] == r) for r in range(self.world)]
         if self.owners is not None and 8 * max(per_owner + [0]) <= self.owners.nbytes:
-            # instance-major layout in each owner's buffer, an instance's ranks in rank order: what shard_assemble wants
+            # instance-major layout in each owner's buffer; inside an instance's run the samples of ALL ranks lie channel by channel
+            # (shard_layout: every rank derives the same offsets), so that the owner can publish whole bursts as views
             base, run = [], [0] * self.world
             for i in idx:
                 base.append(run[own_of[i]]); run[own_of[i]] += total[i]
-            list(self._map(lambda i: self.blocks[i].shard_extract_device(first[me], count[me], d_rows, d_prev,
-                                                                         self.owners.ptrs[own_of[i]] + 8 * (base[i] + sum(sizes[i][:me])), stream), idx))
+
+            def extract_to_owner(i):
+                self.blocks[i].shard_layout(True)
+                return self.blocks[i].shard_extract_device(first[me], count[me], d_rows, d_prev, self.owners.ptrs[own_of[i]] + 8 * base[i], stream)
+            list(self._map(extract_to_owner, idx))
             t.append(time.perf_counter())
             dist.barrier(group=self.group)                                          # every rank's stores have landed
             t.append(time.perf_counter())
@@ -316,10 +320,13 @@ class ShardedActivityGroup(object):
                 return b.messages_arrays(reuse=True) if self.arrays else b.messages()
             out = list(self._map(assemble_own, idx))
         elif self.sink is not None and 8 * sum(total) <= self.sink.nbytes:
-            # block-major layout in the sink's buffer, a block's ranks in rank order: what shard_assemble wants
+            # instance-major layout in the sink's buffer, all ranks' samples of an instance channel by channel (shard_layout)
             base = np.concatenate([[0], np.cumsum(total)]).tolist()
-            list(self._map(lambda i: self.blocks[i].shard_extract_device(first[me], count[me], d_rows, d_prev,
-                                                                         self.sink.ptr + 8 * (base[i] + sum(sizes[i][:me])), stream), idx))
+
+            def extract_to_sink(i):
+                self.blocks[i].shard_layout(True)
+                return self.blocks[i].shard_extract_device(first[me], count[me], d_rows, d_prev, self.sink.ptr + 8 * base[i], stream)
+            list(self._map(extract_to_sink, idx))
             t.append(time.perf_counter())
             dist.barrier(group=self.group)                                          # every rank's stores have landed
             t.append(time.perf_counter())

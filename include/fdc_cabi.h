@@ -48,6 +48,12 @@ int fdc_copy_threads(void);                        /* worker threads of the stag
  * caller must unregister before freeing or remapping the range. */
 int fdc_host_register(void* p, size_t bytes);
 int fdc_host_unregister(void* p);
+/* A consumer that reads a PDU payload IN PLACE (fdc_msg.data may point into the block's pinned result buffer, which the GPU
+ * writes again at the next work() call) should call this on the range when it is done: it drops the lines from the CPU caches
+ * (clflushopt).  A DMA write into lines that several cores still hold is up to 10x slower than into lines nobody caches
+ * (measured: 10 MB in 1.1-2.0 ms against 0.185 ms, profiles/r2_d2h_after_cpu_reads.txt).  The library's own copies
+ * (*_msg_copy_data, the staging slots of the *_work_host calls) do it themselves.  Never required for correctness. */
+void fdc_host_evict(const void* p, size_t bytes);
 /* plain device memory + blocking copies, so that a host language without a CUDA binding can keep a call's
  * spectrum on the GPU between fdc_chan_work_device and the activity-gated blocks' *_work_device */
 void* fdc_dev_alloc(size_t bytes);
@@ -299,6 +305,10 @@ int fdc_actdet_logic_work(fdc_actdet* b, int nblocks, const float* power_rows);
  * Device form of steps 4 and 5 (the gather fused into the extract kernel): *_shard_extract_device stores the samples at d_dst,
  * which may be the sink rank's buffer mapped over CUDA IPC (fdc_ipc_open) -- the kernel's stores then cross NVLink -- and returns
  * after its stream has drained; after a barrier the sink calls *_shard_assemble_device on its buffer.
+ * *_shard_layout(b, 1) between steps 3 and 4 switches the device form to ONE run per block instance for all ranks, laid out
+ * channel by channel (every rank derives the same offsets from the same job list): d_dst / d_results are then the start of that
+ * run on the sink, and bursts that begin and end inside the call are published as views of the assembled buffer instead of
+ * being copied block by block.  Returns the samples of the whole call.
  * All ranks must make the same sequence of calls on contexts built with the same arguments.  *_shard_measure_logic is the
  * host-logic form of step 1 (contexts from *_create_logic; input as for *_logic_work), for CPU tests of the plumbing. */
 long fdc_pac_shard_measure(fdc_pac* b, int nrows, const void* d_rows, void* stream);
@@ -306,6 +316,7 @@ long fdc_pac_shard_measure_logic(fdc_pac* b, int nrows, const float* power);
 int fdc_pac_shard_blob(const fdc_pac* b, void* out);
 long fdc_pac_shard_decide(fdc_pac* b, int nblocks_total, const void* records, long bytes);
 long fdc_pac_shard_samples(const fdc_pac* b, int first_row, int nrows);
+long fdc_pac_shard_layout(fdc_pac* b, int by_channel);
 long fdc_pac_shard_extract(fdc_pac* b, int first_row, int nrows, const void* d_rows, const void* d_prev, void* stream, void* out_host);
 int fdc_pac_shard_assemble(fdc_pac* b, const void* results, long nsamples);
 long fdc_pac_shard_extract_device(fdc_pac* b, int first_row, int nrows, const void* d_rows, const void* d_prev, void* stream, void* d_dst);
@@ -315,6 +326,7 @@ long fdc_segdet_shard_measure_logic(fdc_segdet* b, int nrows, const float* power
 int fdc_segdet_shard_blob(const fdc_segdet* b, void* out);
 long fdc_segdet_shard_decide(fdc_segdet* b, int nblocks_total, const void* records, long bytes);
 long fdc_segdet_shard_samples(const fdc_segdet* b, int first_row, int nrows);
+long fdc_segdet_shard_layout(fdc_segdet* b, int by_channel);
 long fdc_segdet_shard_extract(fdc_segdet* b, int first_row, int nrows, const void* d_rows, const void* d_prev, void* stream, void* out_host);
 int fdc_segdet_shard_assemble(fdc_segdet* b, const void* results, long nsamples);
 long fdc_segdet_shard_extract_device(fdc_segdet* b, int first_row, int nrows, const void* d_rows, const void* d_prev, void* stream, void* d_dst);
@@ -324,6 +336,7 @@ long fdc_actdet_shard_measure_logic(fdc_actdet* b, int nrows, const float* power
 int fdc_actdet_shard_blob(const fdc_actdet* b, void* out);
 long fdc_actdet_shard_decide(fdc_actdet* b, int nblocks_total, const void* records, long bytes);
 long fdc_actdet_shard_samples(const fdc_actdet* b, int first_row, int nrows);
+long fdc_actdet_shard_layout(fdc_actdet* b, int by_channel);
 long fdc_actdet_shard_extract(fdc_actdet* b, int first_row, int nrows, const void* d_rows, const void* d_prev, void* stream, void* out_host);
 int fdc_actdet_shard_assemble(fdc_actdet* b, const void* results, long nsamples);
 long fdc_actdet_shard_extract_device(fdc_actdet* b, int first_row, int nrows, const void* d_rows, const void* d_prev, void* stream, void* d_dst);

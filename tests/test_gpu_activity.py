@@ -287,8 +287,10 @@ def _virtual_ranks_run(mk, x, N, calls, world, device_form=False):
             sizes = [ranks[0].shard_samples(first[r], count[r]) for r in range(world)]
             sink = torch.zeros(2 * max(sum(sizes), 1), dtype=torch.float32, device="cuda")
             for r in range(world):
+                if device_form == "by_channel":     # one run for all ranks, channel by channel: every rank stores at the run's start + its offsets
+                    assert ranks[r].shard_layout(True) == sum(sizes)
                 got = ranks[r].shard_extract_device(first[r], count[r], dev[r].data_ptr(), prev[r].data_ptr() if prev[r] is not None else 0,
-                                                    sink.data_ptr() + 8 * sum(sizes[:r]))
+                                                    sink.data_ptr() + (0 if device_form == "by_channel" else 8 * sum(sizes[:r])))
                 assert got == sizes[r]
             for r in range(1, world):
                 ranks[r].shard_assemble(None)
@@ -320,10 +322,11 @@ def test_sharded_segdet_equals_single_stream(FDC, ref, world):
     for u, v in zip(mb, ms):
         assert np.array_equal(u["data"].view(np.uint32), v["data"].view(np.uint32))
     assert all(r.active_channels() == b.active_channels() for r in ranks)
-    md, _ = _virtual_ranks_run(lambda: FDC.SegmentDetection(*args), x, N, (37, 1, 62), world, device_form=True)
-    assert [sc.meta_tuple(m) for m in mb] == [sc.meta_tuple(m) for m in md]
-    for u, v in zip(mb, md):
-        assert np.array_equal(u["data"].view(np.uint32), v["data"].view(np.uint32))
+    for form in (True, "by_channel"):
+        md, _ = _virtual_ranks_run(lambda: FDC.SegmentDetection(*args), x, N, (37, 1, 62), world, device_form=form)
+        assert [sc.meta_tuple(m) for m in mb] == [sc.meta_tuple(m) for m in md]
+        for u, v in zip(mb, md):
+            assert np.array_equal(u["data"].view(np.uint32), v["data"].view(np.uint32))
 
 
 def test_sharded_pac_and_actdet_equal_single_stream(FDC, ref):
@@ -357,7 +360,7 @@ def test_segdet_cfg5_geometry(FDC, ref):
     compare_messages(ma, mb)
     assert a.active_channels() == b.active_channels()
     assert np.array_equal(a.power().view(np.uint32), b.power().view(np.uint32))
-    ms, _ = _virtual_ranks_run(lambda: FDC.SegmentDetection(*args), x, N, (nblocks,), 4, device_form=True)
+    ms, _ = _virtual_ranks_run(lambda: FDC.SegmentDetection(*args), x, N, (nblocks,), 4, device_form="by_channel")
     assert [sc.meta_tuple(m) for m in mb] == [sc.meta_tuple(m) for m in ms]
     for u, v in zip(mb, ms):
         assert np.array_equal(u["data"].view(np.uint32), v["data"].view(np.uint32))
