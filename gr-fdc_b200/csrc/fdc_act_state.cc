@@ -2,6 +2,7 @@
  * integer for integer with the reference, and its float/double mix follows the reference expression by expression. */
 #include "fdc_act_state.h"
 #include <cstdio>
+#include <cstring>
 #include <algorithm>
 #include <cmath>
 #include <ctime>
@@ -13,13 +14,12 @@ namespace fdc {
 
 template <class T> static std::string num2str(T v) { std::ostringstream ss; ss << v; return ss.str(); }
 
-std::string current_time_string()
+const std::string& time_string(time_t raw)
 {
     /* lib/SegmentDetection_impl.cc:680-694; the text only changes once a second, so it is formatted once a second
      * (a wideband segment activates hundreds of carriers per block) */
     static thread_local time_t cached_at = (time_t)-1;
     static thread_local std::string cached;
-    time_t raw; time(&raw);
     if (raw != cached_at) {
         struct tm ti; localtime_r(&raw, &ti);
         char p[80];
@@ -28,6 +28,7 @@ std::string current_time_string()
     }
     return cached;
 }
+std::string current_time_string() { time_t raw; time(&raw); return time_string(raw); }
 
 /* fmod(fmod(x, y) + 1, y) -- lib/SegmentDetection_impl.cc:700-703 */
 static float mod_f(float x, float y) { return (float)fmod(fmod((double)x, (double)y) + 1.0, (double)y); }
@@ -132,55 +133,104 @@ SegGeometry actdet_geometry(int blocklen, float v0, float v1, int D)
 /* ---- SegmentState --------------------------------------------------------------------------------- */
 /* the reference's comparison (descending ratio, `fipair_sort`) as an inlinable functor: std::sort's sequence of comparisons and
  * moves depends only on the comparison results and the length, so the order among equal ratios stays the reference's whatever
- * the second member is (the reference carries the bin, this code the power-bin index) */
+ * the second member is (the reference carries the bin, this code the position in the block's rising-edge list) */
 struct ratio_desc_t { bool operator()(const std::pair<float, int>& a, const std::pair<float, int>& b) const { return a.first > b.first; } };
+
+/* rising edges by descending ratio.  Few edges: the reference's std::sort call.  Many (a wideband segment has hundreds per block):
+ * an LSD radix sort on the float bits -- the ratios are positive (r > T > 0), so their bit patterns order like the values; when
+ * all ratios differ the sorted order is unique and equals std::sort's, and when two are equal (the only case in which the
+ * reference's order depends on the algorithm) the list is sorted again from its original order with std::sort itself. */
+static void sort_by_ratio(std::vector<std::pair<float, int> >& v)
+{
+    const size_t n = v.size();
+    if (n < 96) { std::sort(v.begin(), v.end(), ratio_desc_t()); return; }
+    static thread_local std::vector<std::pair<float, int> > tmp, orig;
+    orig = v; tmp.resize(n);
+    std::pair<float, int>* a = v.data(); std::pair<float, int>* b = tmp.data();
+    bool ok = true;
+    for (size_t i = 0; i < n && ok; i++) { unsigned u; memcpy(&u, &a[i].first, 4); ok = (u >> 31) == 0 && a[i].first == a[i].first; }   /* positive, not NaN */
+    for (int pass = 0; pass < 4 && ok; pass++) {
+        size_t cnt[257]; for (int k = 0; k < 257; k++) cnt[k] = 0;
+        const int sh = 8 * pass;
+        for (size_t i = 0; i < n; i++) { unsigned u; memcpy(&u, &a[i].first, 4); cnt[255 - ((u >> sh) & 255u) + 1]++; }      /* descending */
+        for (int k = 1; k < 257; k++) cnt[k] += cnt[k - 1];
+        for (size_t i = 0; i < n; i++) { unsigned u; memcpy(&u, &a[i].first, 4); b[cnt[255 - ((u >> sh) & 255u)]++] = a[i]; }
+        std::swap(a, b);
+    }
+    /* four passes: the result is back in v */
+    for (size_t i = 1; i < n && ok; i++) ok = v[i - 1].first > v[i].first;
+    if (!ok) { v = orig; std::sort(v.begin(), v.end(), ratio_desc_t()); }
+}
+
+/* Occupancy of the detection raster by the accepted candidates of the current block: own[p] = 1 + position in the candidate
+ * list of the candidate that owns raster point p (0: free), busy = the same as a bit set.  Only the points written for one
+ * block are cleared for the next (a wideband segment has tens of thousands of raster points and a few hundred owned ones). */
+struct SegmentState::OwnerMap {
+    std::vector<int> own; std::vector<unsigned long long> busy; std::vector<std::pair<int, int> > written;
+    void begin(size_t points)
+    {
+        if (own.size() != points) { own.assign(points, 0); busy.assign((points + 63) / 64, 0ull); written.clear(); return; }
+        for (size_t k = 0; k < written.size(); k++)
+            for (int q = written[k].first; q < written[k].second; q++) { own[(size_t)q] = 0; busy[(size_t)q >> 6] = 0ull; }
+        written.clear();
+    }
+    bool any(int ps, int pe) const               /* one of the points ps .. pe owned? */
+    {
+        const size_t w0 = (size_t)ps >> 6, w1 = (size_t)pe >> 6;
+        const unsigned long long m0 = ~0ull << (ps & 63), m1 = ~0ull >> (63 - (pe & 63));
+        if (w0 == w1) return (busy[w0] & m0 & m1) != 0;
+        if ((busy[w0] & m0) != 0 || (busy[w1] & m1) != 0) return true;
+        for (size_t w = w0 + 1; w < w1; w++) if (busy[w] != 0) return true;
+        return false;
+    }
+    void take(int ps, int pe, int id)
+    {
+        for (int q = ps; q < pe; q++) { own[(size_t)q] = id; busy[(size_t)q >> 6] |= 1ull << (q & 63); }
+        written.push_back(std::make_pair(ps, pe));
+    }
+};
+SegmentState::OwnerMap& SegmentState::owner_map()
+{
+    static thread_local OwnerMap m;
+    return m;
+}
 
 void SegmentState::candidates(const EdgeBlock& e, CandList& poss) const
 {
-    /* lib/SegmentDetection_impl.cc:195-244.  Same order of operations as the reference: rising edges sorted by ratio with
-     * the same std::sort call (introsort makes the same comparisons and moves on any random-access range, so ties between
-     * equal ratios resolve as in the reference's deque), then walked from the strongest down.  The scratch vectors live for
-     * the thread's lifetime: no allocation per block. */
-    static thread_local std::vector<std::pair<float, int> > rise;
-    rise.assign(e.rise.begin(), e.rise.end());
-    std::sort(rise.begin(), rise.end(), ratio_desc_t());
-    /* Everything below works on the detection raster (power-bin index p <-> bin start + D * p): a rising edge at power bin r
-     * starts a candidate at raster point r, a falling edge at power bin f ends one at raster point f + 1, and the reference's
-     * upper_bound over the falling BINS for the first one above the rising bin is the first f >= r.
-     * The reference tests a new candidate against every accepted one (quadratic in the number of carriers; a wideband
-     * segment has hundreds per block).  The accepted ones are recorded in an occupancy map over the raster points: candidate
-     * [a, b) owns the points a .. b-1.  The reference's test "s < b && e >= a" for some accepted [a, b) is "one of the points
-     * s .. e is owned" -- same decisions, asked of a bit set of the owned points (a noise edge far from the next falling edge
-     * would otherwise walk hundreds of map entries).  match() uses the map to find WHICH candidate owns a point. */
-    const std::vector<int>& fall = e.fall;
-    std::vector<int>& own = owner_map();
-    own.assign((size_t)g.M + 2, 0);
-    static thread_local std::vector<unsigned long long> busy;
-    busy.assign(((size_t)g.M + 2 + 63) / 64, 0ull);
-    for (size_t r = 0; r < rise.size(); r++) {
-        const int ps = rise[r].second;
-        std::vector<int>::const_iterator next_end = std::lower_bound(fall.begin(), fall.end(), ps);
-        if (next_end == fall.end()) continue;
-        const int pe = *next_end + 1;
-        const size_t w0 = (size_t)ps >> 6, w1 = (size_t)pe >> 6;
-        const unsigned long long m0 = ~0ull << (ps & 63), m1 = ~0ull >> (63 - (pe & 63));
-        bool overlapping;
-        if (w0 == w1) overlapping = (busy[w0] & m0 & m1) != 0;
-        else {
-            overlapping = (busy[w0] & m0) != 0 || (busy[w1] & m1) != 0;
-            for (size_t w = w0 + 1; w < w1 && !overlapping; w++) overlapping = busy[w] != 0;
-        }
-        if (overlapping) continue;
+    /* lib/SegmentDetection_impl.cc:195-244.  Same order of operations as the reference: rising edges sorted by ratio (ties
+     * resolved as the reference's std::sort call resolves them, sort_by_ratio), then walked from the strongest down.  The
+     * scratch vectors live for the thread's lifetime: no allocation per block.
+     * Everything works on the detection raster (power-bin index p <-> bin start + D * p): a rising edge at power bin r starts a
+     * candidate at raster point r, a falling edge at power bin f ends one at raster point f + 1, and the reference's upper_bound
+     * over the falling BINS for the first one above the rising bin is the first f >= r -- found for all rising edges at once by
+     * one merge of the two lists (both are in ascending bin order) instead of a binary search each.
+     * The reference tests a new candidate against every accepted one (quadratic in the number of carriers; a wideband segment
+     * has hundreds per block).  The accepted ones are recorded in an occupancy map over the raster points: candidate [a, b) owns
+     * the points a .. b-1.  The reference's test "s < b && e >= a" for some accepted [a, b) is "one of the points s .. e is owned"
+     * -- same decisions, asked of a bit set of the owned points.  match() uses the map to find WHICH candidate owns a point. */
+    static thread_local std::vector<std::pair<float, int> > rise;         /* (ratio, position in e.rise) */
+    static thread_local std::vector<int> end_of;                           /* raster end of the candidate rising edge k would start, -1: none */
+    const size_t nr = e.rise.size(), nf = e.fall.size();
+    rise.resize(nr); end_of.resize(nr);
+    bool ascending = true;
+    for (size_t k = 1; k < nr && ascending; k++) ascending = e.rise[k - 1].second <= e.rise[k].second;
+    for (size_t k = 0, f = 0; k < nr; k++) {
+        rise[k] = std::make_pair(e.rise[k].first, (int)k);
+        if (ascending) { while (f < nf && e.fall[f] < e.rise[k].second) f++; end_of[k] = f < nf ? e.fall[f] + 1 : -1; }
+        else { std::vector<int>::const_iterator it = std::lower_bound(e.fall.begin(), e.fall.end(), e.rise[k].second); end_of[k] = it == e.fall.end() ? -1 : *it + 1; }
+    }
+    sort_by_ratio(rise);
+    OwnerMap& map = owner_map();
+    map.begin((size_t)g.M + 2);
+    for (size_t r = 0; r < nr; r++) {
+        const int pe = end_of[(size_t)rise[r].second];
+        if (pe < 0) continue;
+        const int ps = e.rise[(size_t)rise[r].second].second;
+        if (map.any(ps, pe)) continue;
         const std::array<long, 2> a = {{(long)ps * g.D + g.start, (long)pe * g.D + g.start}};
         poss.push_back(a);
-        for (int q = ps; q < pe; q++) { own[(size_t)q] = (int)poss.size(); busy[(size_t)q >> 6] |= 1ull << (q & 63); }       /* 1 + position in poss */
+        map.take(ps, pe, (int)poss.size());       /* 1 + position in poss */
     }
-}
-
-std::vector<int>& SegmentState::owner_map()
-{
-    static thread_local std::vector<int> own;       /* scratch shared by candidates() and match() of one block() call */
-    return own;
 }
 
 bool SegmentState::activate(long detect_start, long detect_end, long& uid_counter)
@@ -210,15 +260,9 @@ bool SegmentState::activate(long detect_start, long detect_end, long& uid_counte
     c.ovlskip = (int)(extract_width / relinvovl);
     c.outputsamples = c.extract_width - c.ovlskip;
     c.count = 0; c.phase = 0; c.phaseincrement = (int)(extract_start % relinvovl); c.inactive = -1; c.part = 0;
-    {   /* "<time>.DETECTED.<segID>.<chanID>", lib/SegmentDetection_impl.cc:674-678; one formatted write (a wideband segment activates
-         * hundreds of carriers per block) */
-        const std::string t = current_time_string();
-        char id[128];
-        const int n = snprintf(id, sizeof(id), "%s.DETECTED.%d.%d", t.c_str(), seg_id, c.ID);
-        c.msg_ID.assign(id, (size_t)(n < 0 ? 0 : std::min(n, (int)sizeof(id) - 1)));
-    }
+    time(&c.act_time);                                   /* the id text is built when a PDU is (channel_id) */
     c.uid = uid_counter++; c.ndata = 0;
-    active.push_back(std::move(c));
+    active.push_back(c);
     return true;
 }
 
@@ -234,7 +278,7 @@ void SegmentState::match(CandList& poss, long& uid_counter)
      * With the occupancy map of candidates(): candidate [a, b) touches the channel iff it owns one of the raster points
      * detect_start - 1 .. detect_stop - 1 (in raster units); "erased" is a flag.  Same result, no quadratic walk. */
     const size_t n = poss.size();
-    const std::vector<int>& own = owner_map();
+    const std::vector<int>& own = owner_map().own;
     static thread_local std::vector<char> dead;
     dead.assign(n, 0);
     for (size_t k = 0; k < active.size(); k++) {
@@ -252,59 +296,79 @@ void SegmentState::match(CandList& poss, long& uid_counter)
         if (!dead[i]) activate(poss[i][0], poss[i][1], uid_counter);
 }
 
-void SegmentState::job(ActiveChannel& c, int row, std::vector<ActJob>& jobs, std::vector<ActOp>& ops)
+void SegmentState::job(ActiveChannel& c, int row, std::vector<ActJob>& jobs, ActOps& ops)
 {
     /* process_channel, lib/SegmentDetection_impl.cc:399-429 */
     ActJob j; j.L = c.extract_width; j.row = row; j.start = c.extract_start;
     j.tab_off = (*win_offsets)[c.extract_window] + (long)c.phase * c.extract_width;
     j.skip = c.ovlskip; j.uid = c.uid;
-    ActOp o; o.kind = ActOp::PUSH; o.uid = c.uid; o.job = (int)jobs.size(); o.ntake = 0; o.blocksamples = c.outputsamples;
+    ActOp o; o.kind = ActOp::PUSH; o.uid = c.uid; o.job = (int)jobs.size(); o.ntake = 0; o.blocksamples = c.outputsamples; o.meta = -1;
     jobs.push_back(j); ops.push_back(o);
     c.ndata++; c.count++;
     c.phase = (c.phase + c.phaseincrement) % relinvovl;
 }
 
-MsgMeta SegmentState::meta(const ActiveChannel& c, long blockcount, bool fin) const
+static void append_int(std::string& s, long v)
 {
-    MsgMeta m;
-    m.id = c.msg_ID; m.finalized = fin; m.publish = msg_output;
+    char d[24]; int n = 0;
+    unsigned long u = v < 0 ? 0ul - (unsigned long)v : (unsigned long)v;
+    do { d[n++] = (char)('0' + u % 10); u /= 10; } while (u);
+    if (v < 0) s.push_back('-');
+    while (n) s.push_back(d[--n]);
+}
+std::string SegmentState::channel_id(const ActiveChannel& c) const
+{
+    /* "<time of activation>.DETECTED.<segID>.<chanID>", lib/SegmentDetection_impl.cc:674-678 (hundreds per block on a wideband
+     * segment: appended by hand, no stream or printf formatting) */
+    std::string id;
+    id.reserve(48);
+    id = time_string(c.act_time);
+    id.append(".DETECTED.", 10);
+    append_int(id, seg_id);
+    id.push_back('.');
+    append_int(id, c.ID);
+    return id;
+}
+
+void SegmentState::meta(MsgMeta& m, const ActiveChannel& c, long blockcount, bool fin) const
+{
+    m.id = channel_id(c); m.finalized = fin; m.publish = msg_output;
     m.part = fin ? (c.part > 0 ? c.part : -1) : c.part;
     m.rel_bw = (double)c.extract_width / (double)blocklen;
     m.rel_cfreq = (double)(c.extract_start + c.extract_stop) / 2.0 / (double)blocklen;
     m.blockstart = blockcount - c.count; m.blockend = blockcount;
     m.vectorstart = c.extract_start; m.vectorend = c.extract_stop;
-    if (fileoutput) m.filename = path + std::string("/") + c.msg_ID + (fin ? std::string(".fin") : std::string(".parted.") + std::to_string(c.part));
+    if (fileoutput) m.filename = path + std::string("/") + m.id + (fin ? std::string(".fin") : std::string(".parted.") + std::to_string(c.part));
     if (verbose) {
-        m.logline = c.msg_ID + (fin ? std::string(".fin: ") : std::string(".part: ")) + std::string("start=") + num2str(c.extract_start) +
+        m.logline = m.id + (fin ? std::string(".fin: ") : std::string(".part: ")) + std::string("start=") + num2str(c.extract_start) +
                     std::string(", stop=") + num2str(c.extract_stop) + (fin ? std::string("") : std::string(", part=") + num2str(c.part + 1)) +
                     std::string(", blockstart=") + num2str(blockcount - c.count) + std::string(", blockend=") + num2str(blockcount);
     }
-    return m;
 }
 
-void SegmentState::emit_final(ActiveChannel& c, long blockcount, std::vector<ActOp>& ops)
+void SegmentState::emit_final(ActiveChannel& c, long blockcount, ActOps& ops)
 {
     /* emit_channel, lib/SegmentDetection_impl.cc:437-482: everything buffered, even nothing */
     ActOp o; o.kind = ActOp::EMIT; o.uid = c.uid; o.job = -1; o.ntake = -1; o.blocksamples = c.outputsamples;
-    o.meta = std::make_shared<MsgMeta>(meta(c, blockcount, true));
+    meta(ops.new_meta(o), c, blockcount, true);
     ops.push_back(o);
     c.ndata = 0;
 }
 
-void SegmentState::emit_partial(ActiveChannel& c, long blockcount, std::vector<ActOp>& ops)
+void SegmentState::emit_partial(ActiveChannel& c, long blockcount, ActOps& ops)
 {
     /* emit_unfinished_channel, lib/SegmentDetection_impl.cc:484-539 */
     if (maxblocks < 0 || c.ndata < maxblocks) return;
     const int ntx = maxblocks == 0 ? c.ndata : maxblocks;
     if (ntx <= 0) return;
     ActOp o; o.kind = ActOp::EMIT; o.uid = c.uid; o.job = -1; o.ntake = ntx; o.blocksamples = c.outputsamples;
-    o.meta = std::make_shared<MsgMeta>(meta(c, blockcount, false));
+    meta(ops.new_meta(o), c, blockcount, false);
     ops.push_back(o);
     c.ndata -= ntx;
     c.part++;
 }
 
-void SegmentState::block(int row, const EdgeBlock& e, long blockcount, long& uid_counter, std::vector<ActJob>& jobs, std::vector<ActOp>& ops)
+void SegmentState::block(int row, const EdgeBlock& e, long blockcount, long& uid_counter, std::vector<ActJob>& jobs, ActOps& ops)
 {
     static thread_local CandList poss;          /* scratch: no allocation per block */
     poss.clear();
@@ -325,7 +389,7 @@ void SegmentState::block(int row, const EdgeBlock& e, long blockcount, long& uid
     size_t keep = 0;
     for (size_t i = 0; i < active.size(); i++) {          /* same survivors in the same order, one pass instead of an erase each */
         if (active[i].inactive > delay) {
-            ActOp o; o.kind = ActOp::DROP; o.uid = active[i].uid; o.job = -1; o.ntake = 0; o.blocksamples = 0;
+            ActOp o; o.kind = ActOp::DROP; o.uid = active[i].uid; o.job = -1; o.ntake = 0; o.blocksamples = 0; o.meta = -1;
             ops.push_back(o);
         } else {
             if (keep != i) active[keep] = std::move(active[i]);
@@ -382,22 +446,21 @@ void PacState::init(int v_blocklen, float cfreq, float bw, int v_relinvovl, floa
     finished_channels = 0; count = 0; part = 0; uid = -1; ndata = 0;
 }
 
-void PacState::job(int row, std::vector<ActJob>& jobs, std::vector<ActOp>& ops)
+void PacState::job(int row, std::vector<ActJob>& jobs, ActOps& ops)
 {
     /* process_channel, lib/PowerActivationChannel_impl.cc:260-284 */
     ActJob j; j.L = extract_width; j.row = row; j.start = extract_start; j.tab_off = (long)phase * blocklen; j.skip = output_ovl_offset; j.uid = uid;
-    ActOp o; o.kind = ActOp::PUSH; o.uid = uid; o.job = (int)jobs.size(); o.ntake = 0; o.blocksamples = output_len;
+    ActOp o; o.kind = ActOp::PUSH; o.uid = uid; o.job = (int)jobs.size(); o.ntake = 0; o.blocksamples = output_len; o.meta = -1;
     jobs.push_back(j); ops.push_back(o);
     ndata++; count++;
     phase = (phase + deltaphase) % relinvovl;
 }
 
-void PacState::emit(bool fin, std::vector<ActOp>& ops)
+void PacState::emit(bool fin, ActOps& ops)
 {
     /* emit_data, lib/PowerActivationChannel_impl.cc:212-258 */
     ActOp o; o.kind = ActOp::EMIT; o.uid = uid; o.job = -1; o.ntake = -1; o.blocksamples = output_len;
-    o.meta = std::make_shared<MsgMeta>();
-    MsgMeta& m = *o.meta;
+    MsgMeta& m = ops.new_meta(o);
     m.id = msgID + (fin ? std::string(".fin") : std::string(".part"));
     m.finalized = fin; m.part = part;
     m.rel_cfreq = (double)(extract_start + extract_stop) / 2.0 / (double)blocklen;
@@ -414,7 +477,7 @@ void PacState::emit(bool fin, std::vector<ActOp>& ops)
     part++;
 }
 
-void PacState::block(int row, float pwr, long& uid_counter, std::vector<ActJob>& jobs, std::vector<ActOp>& ops)
+void PacState::block(int row, float pwr, long& uid_counter, std::vector<ActJob>& jobs, ActOps& ops)
 {
     /* work + measure_power decision, lib/PowerActivationChannel_impl.cc:137-177, 286-306 */
     if (pwr == 0.0f) pwr = std::numeric_limits<float>::min();
@@ -426,7 +489,7 @@ void PacState::block(int row, float pwr, long& uid_counter, std::vector<ActJob>&
         if (!active) {
             /* activate: previous and current block, :198-210 */
             part = 0; count = 0; active = true; phase = 0; ndata = 0;
-            if (uid >= 0) { ActOp d; d.kind = ActOp::DROP; d.uid = uid; d.job = -1; d.ntake = 0; d.blocksamples = 0; ops.push_back(d); }
+            if (uid >= 0) { ActOp d; d.kind = ActOp::DROP; d.uid = uid; d.job = -1; d.ntake = 0; d.blocksamples = 0; d.meta = -1; ops.push_back(d); }
             uid = uid_counter++;
             msgID = current_time_string() + std::string(".PowActChan.") + std::to_string(ID) + std::string(".") + std::to_string(finished_channels);
             job(row - 1, jobs, ops);

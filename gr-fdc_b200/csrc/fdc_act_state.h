@@ -13,6 +13,7 @@
 #define FDC_ACT_STATE_H
 #include <array>
 #include <complex>
+#include <ctime>
 #include <deque>
 #include <memory>
 #include <string>
@@ -46,10 +47,21 @@ struct ActOp {
     int job;                      /* PUSH: index into the call's job list */
     int ntake;                    /* EMIT: number of buffered blocks to publish, -1 = all */
     int blocksamples;             /* EMIT: samples per buffered block */
-    std::shared_ptr<MsgMeta> meta;  /* EMIT only: PUSH / DROP ops (one per extracted block) stay small and string free */
+    int meta;                     /* EMIT: index into the op list's `metas`, -1 otherwise (ops are one per extracted block: small, trivially copyable) */
+};
+/* the ordered ops of a call and the metadata of the PDUs they publish */
+struct ActOps {
+    std::vector<ActOp> v; std::vector<MsgMeta> metas;
+    void reserve(size_t n) { v.reserve(n); }
+    void clear() { v.clear(); metas.clear(); }
+    size_t size() const { return v.size(); }
+    const ActOp& operator[](size_t i) const { return v[i]; }
+    void push_back(const ActOp& o) { v.push_back(o); }
+    MsgMeta& new_meta(ActOp& o) { o.meta = (int)metas.size(); metas.emplace_back(); return metas.back(); }
 };
 
 std::string current_time_string();            /* "%Y-%m-%d-%H-%M-%S" */
+const std::string& time_string(time_t t);      /* the same for a given time (cached per thread: the text changes once a second) */
 
 /* ---- windows ---------------------------------------------------------------------------------- */
 /* lib/SegmentDetection_impl.cc:551-583 == lib/activity_detection_channelizer_vcm_impl.cc:199-228:
@@ -63,7 +75,8 @@ void build_pac_windows(int blocklen, int relinvovl, int rampsamps, std::vector<c
 struct ActiveChannel {
     int ID, detect_start, detect_stop, extract_start, extract_stop, extract_width, extract_window, ovlskip, outputsamples;
     int count, phase, phaseincrement, inactive, part;
-    std::string msg_ID;
+    time_t act_time;              /* wall clock of the activation: the "<time>" of the channel's message id, formatted when a PDU is built
+                                   * (no string in here: the list of a wideband segment is compacted every block) */
     long uid;
     int ndata;                    /* number of buffered blocks (the reference's data.size()) */
     int ras_lo, ras_hi;           /* raster points a candidate must own one of to count as this channel (match()) */
@@ -87,7 +100,7 @@ public:
     double flank;
     SegGeometry g;
     bool emit_inside_loop;        /* activity_detection single-thread order (…vcm_impl.cc:306-337) vs SegmentDetection order */
-    std::deque<ActiveChannel> active;
+    std::vector<ActiveChannel> active;        /* in the reference's list order; plain data, compacted in place every block */
     long chan_counter;
     const std::vector<long>* win_offsets;
     std::string path; bool fileoutput; bool verbose; bool msg_output;
@@ -101,17 +114,19 @@ public:
                      chan_counter(0), win_offsets(0), fileoutput(false), verbose(false), msg_output(true),
                      max_extract_width(16384), warned_wide(false) {}
     /* detection + bookkeeping of one block; `blockcount` is the reference's counter value during this block */
-    void block(int row, const EdgeBlock& e, long blockcount, long& uid_counter, std::vector<ActJob>& jobs, std::vector<ActOp>& ops);
+    void block(int row, const EdgeBlock& e, long blockcount, long& uid_counter, std::vector<ActJob>& jobs, ActOps& ops);
 private:
     typedef std::vector<std::array<long, 2> > CandList;          /* accepted [start, end) candidates of a block, strongest first */
     void candidates(const EdgeBlock& e, CandList& poss) const;
-    static std::vector<int>& owner_map();
+    struct OwnerMap;                                            /* per-thread scratch shared by candidates() and match() */
+    static OwnerMap& owner_map();
+    std::string channel_id(const ActiveChannel& c) const;
     void match(CandList& poss, long& uid_counter);
     bool activate(long detect_start, long detect_end, long& uid_counter);
-    void job(ActiveChannel& c, int row, std::vector<ActJob>& jobs, std::vector<ActOp>& ops);
-    void emit_final(ActiveChannel& c, long blockcount, std::vector<ActOp>& ops);
-    void emit_partial(ActiveChannel& c, long blockcount, std::vector<ActOp>& ops);
-    MsgMeta meta(const ActiveChannel& c, long blockcount, bool fin) const;
+    void job(ActiveChannel& c, int row, std::vector<ActJob>& jobs, ActOps& ops);
+    void emit_final(ActiveChannel& c, long blockcount, ActOps& ops);
+    void emit_partial(ActiveChannel& c, long blockcount, ActOps& ops);
+    void meta(MsgMeta& m, const ActiveChannel& c, long blockcount, bool fin) const;
 };
 
 /* ---- PowerActivationChannel --------------------------------------------------------------------- */
@@ -127,10 +142,10 @@ public:
 
     /* constructor arguments of lib/PowerActivationChannel_impl.cc:42; throws std::invalid_argument like the reference */
     void init(int v_blocklen, float cfreq, float bw, int v_relinvovl, float v_thresh, int v_maxblocks, int v_delay, int v_ID);
-    void block(int row, float pwr, long& uid_counter, std::vector<ActJob>& jobs, std::vector<ActOp>& ops);
+    void block(int row, float pwr, long& uid_counter, std::vector<ActJob>& jobs, ActOps& ops);
 private:
-    void job(int row, std::vector<ActJob>& jobs, std::vector<ActOp>& ops);
-    void emit(bool fin, std::vector<ActOp>& ops);
+    void job(int row, std::vector<ActJob>& jobs, ActOps& ops);
+    void emit(bool fin, ActOps& ops);
 };
 
 }  // namespace fdc

@@ -141,6 +141,23 @@ struct ActEngine {
     }
     typedef std::unordered_map<long, Pending> PendingMap;          /* a busy segment replays ~10 ops per block: hashed, not ordered */
     PendingMap pending;
+    /* direct-mapped front of the map (uids are consecutive integers, a few hundred are live at a time): the replay looks a uid up
+     * once per extracted block; map nodes never move, so the cached pointers stay valid until the uid is erased */
+    enum { PCACHE = 4096 };
+    struct PendingRef { long uid; Pending* p; PendingRef() : uid(-1), p(0) {} };
+    std::vector<PendingRef> pcache;
+    Pending& pending_of(long uid)
+    {
+        if (pcache.empty()) pcache.resize(PCACHE);
+        PendingRef& r = pcache[(size_t)uid & (PCACHE - 1)];
+        if (r.uid != uid) { r.p = &pending[uid]; r.uid = uid; }
+        return *r.p;
+    }
+    void pending_erase(long uid)
+    {
+        if (!pcache.empty()) { PendingRef& r = pcache[(size_t)uid & (PCACHE - 1)]; if (r.uid == uid) { r.uid = -1; r.p = 0; } }
+        pending.erase(uid);
+    }
     std::vector<OutMsg> msgs;
     long uid_counter;
     bool logic_only;               /* host-logic hooks: no device, messages carry metadata and sample counts only */
@@ -247,17 +264,17 @@ struct ActEngine {
         return 0;
     }
     /* replay the ops of a call on the extracted blocks (res + dst[job]) -> PDUs / files in the reference's order */
-    void replay(const cfloat* res, const std::vector<long>& dst, const std::vector<ActJob>& jobs, const std::vector<ActOp>& ops)
+    void replay(const cfloat* res, const std::vector<long>& dst, const std::vector<ActJob>& jobs, ActOps& ops)
     {
         if (logic_only) {
             for (size_t i = 0; i < ops.size(); i++) {
                 const ActOp& o = ops[i];
-                if (o.kind == ActOp::PUSH) pending[o.uid].nblocks++;
-                else if (o.kind == ActOp::DROP) pending.erase(o.uid);
+                if (o.kind == ActOp::PUSH) pending_of(o.uid).nblocks++;
+                else if (o.kind == ActOp::DROP) pending_erase(o.uid);
                 else {
-                    Pending& q = pending[o.uid];
+                    Pending& q = pending_of(o.uid);
                     const size_t ntake = o.ntake < 0 ? q.nblocks : std::min((size_t)o.ntake, q.nblocks);
-                    OutMsg m; m.meta = *o.meta; m.logic_samples = (long)(ntake * (size_t)o.blocksamples);
+                    OutMsg m; m.meta = ops.metas[(size_t)o.meta]; m.logic_samples = (long)(ntake * (size_t)o.blocksamples);
                     q.nblocks -= ntake;
                     if (m.meta.publish) msgs.push_back(std::move(m));
                 }
@@ -269,13 +286,13 @@ struct ActEngine {
             const ActOp& o = ops[i];
             if (o.kind == ActOp::PUSH) {
                 const ActJob& j = jobs[o.job];
-                pending[o.uid].push(res + dst[o.job], (size_t)(j.L - j.skip));
+                pending_of(o.uid).push(res + dst[o.job], (size_t)(j.L - j.skip));
             } else if (o.kind == ActOp::DROP) {
-                pending.erase(o.uid);
+                pending_erase(o.uid);
             } else {
-                Pending& q = pending[o.uid];
+                Pending& q = pending_of(o.uid);
                 const size_t ntake = o.ntake < 0 ? q.nblocks : std::min((size_t)o.ntake, q.nblocks);
-                OutMsg m; m.meta = std::move(*o.meta);          /* an op list is replayed once: its strings move into the message */
+                OutMsg m; m.meta = std::move(ops.metas[(size_t)o.meta]);          /* an op list is replayed once: its strings move into the message */
                 m.n = ntake * (size_t)o.blocksamples;
                 const bool wanted = m.meta.publish || !m.meta.filename.empty();
                 /* only results in the engine's own pinned buffer may be handed out as views (shard_assemble replays the caller's memory) */
@@ -304,7 +321,7 @@ struct ActEngine {
         for (PendingMap::iterator it = pending.begin(); it != pending.end(); ++it) it->second.keep();
     }
     /* run all extraction jobs of a call and replay the ops */
-    int finish(const float2* d_rows, std::vector<ActJob>& jobs, const std::vector<ActOp>& ops, cudaStream_t st)
+    int finish(const float2* d_rows, std::vector<ActJob>& jobs, ActOps& ops, cudaStream_t st)
     {
         std::vector<long> dst; long total = 0;
         if (extract(d_rows, 0, jobs, 0, jobs.size(), 0, dst, &total, st, 0, true)) return -1;
@@ -317,7 +334,7 @@ struct ActEngine {
      * jobs emitted by its own blocks (a contiguous range of the job list), and the sink rank replays the ops on the concatenated
      * results (`assemble`). */
     struct ShardCall {
-        std::vector<char> blob; std::vector<ActJob> jobs; std::vector<ActOp> ops; std::vector<long> job_first; bool decided;
+        std::vector<char> blob; std::vector<ActJob> jobs; ActOps ops; std::vector<long> job_first; bool decided;
         bool by_channel; std::vector<long> layout;     /* shard_layout(1): offsets of all jobs of the call, channel by channel */
         ShardCall() : decided(false), by_channel(false) {}
     } sh;
@@ -585,7 +602,7 @@ fdc_pac* fdc_pac_create_logic(int blocklen, float cfreq, float bw, int relinvovl
 int fdc_pac_logic_work(fdc_pac* b, int n, const float* pwr)
 {
     if (!b || !b->e.logic_only || n < 0) return fail("fdc_pac_logic_work: needs a context from fdc_pac_create_logic");
-    std::vector<ActJob> jobs; std::vector<ActOp> ops;
+    std::vector<ActJob> jobs; ActOps ops;
     jobs.reserve((size_t)n * 16 + 16); ops.reserve((size_t)n * 18 + 16);     /* no reallocation (and op copies) while the blocks are walked */
     for (int i = 0; i < n; i++) b->st.block(i, pwr[i], b->e.uid_counter, jobs, ops);
     return b->e.finish(0, jobs, ops, 0) ? -1 : n;
@@ -603,7 +620,7 @@ int fdc_pac_work_device(fdc_pac* b, int n, const void* d_in, void* stream)
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
     if (ce != cudaSuccess) return cuda_fail(ce, "band power");
     const float* pw = (const float*)b->e.h_misc.p;
-    std::vector<ActJob> jobs; std::vector<ActOp> ops;
+    std::vector<ActJob> jobs; ActOps ops;
     jobs.reserve((size_t)n * 16 + 16); ops.reserve((size_t)n * 18 + 16);     /* no reallocation (and op copies) while the blocks are walked */
     for (int i = 0; i < n; i++) b->st.block(i, pw[i], b->e.uid_counter, jobs, ops);
     if (b->e.finish(rows, jobs, ops, st)) return -1;
@@ -704,7 +721,7 @@ int fdc_segdet_logic_work(fdc_segdet* b, int n, const float* P)
     if (!b || !b->e.logic_only || n < 0) return fail("fdc_segdet_logic_work: needs a context from fdc_segdet_create_logic");
     std::vector<EdgeBlock> edges;
     classify_rows(P, n, (int)b->st.g.M, b->thresh, 0, edges);
-    std::vector<ActJob> jobs; std::vector<ActOp> ops;
+    std::vector<ActJob> jobs; ActOps ops;
     jobs.reserve((size_t)n * 16 + 16); ops.reserve((size_t)n * 18 + 16);     /* no reallocation (and op copies) while the blocks are walked */
     for (int i = 0; i < n; i++) { b->st.block(i, edges[(size_t)i], b->blockcount, b->e.uid_counter, jobs, ops); b->blockcount++; }
     if (n > 0) b->det.last_power.assign(P + (size_t)(n - 1) * b->st.g.M, P + (size_t)n * b->st.g.M);
@@ -721,7 +738,7 @@ int fdc_segdet_work_device(fdc_segdet* b, int n, const void* d_in, void* stream)
     PhaseClock pc;
     if (b->det.run(b->e, rows, n, b->st.g, b->thresh, 0, 0, edges, st)) return -1;
     pc.lap();
-    std::vector<ActJob> jobs; std::vector<ActOp> ops;
+    std::vector<ActJob> jobs; ActOps ops;
     jobs.reserve((size_t)n * 16 + 16); ops.reserve((size_t)n * 18 + 16);     /* no reallocation (and op copies) while the blocks are walked */
     for (int i = 0; i < n; i++) { b->st.block(i, edges[(size_t)i], b->blockcount, b->e.uid_counter, jobs, ops); b->blockcount++; }
     pc.lap();
@@ -839,7 +856,7 @@ int fdc_actdet_logic_work(fdc_actdet* b, int n, const float* P)
     if (!b || !b->e.logic_only || n < 0) return fail("fdc_actdet_logic_work: needs a context from fdc_actdet_create_logic");
     long rowlen = 0;
     for (size_t s = 0; s < b->segs.size(); s++) rowlen += b->segs[s].g.M;
-    std::vector<ActJob> jobs; std::vector<ActOp> ops;
+    std::vector<ActJob> jobs; ActOps ops;
     jobs.reserve((size_t)n * 16 + 16); ops.reserve((size_t)n * 18 + 16);     /* no reallocation (and op copies) while the blocks are walked */
     std::vector<EdgeBlock> eb;
     for (int i = 0; i < n; i++) {
@@ -865,7 +882,7 @@ int fdc_actdet_work_device(fdc_actdet* b, int n, const void* d_in, void* stream)
     std::vector<std::vector<EdgeBlock> > edges(b->segs.size());
     for (size_t s = 0; s < b->segs.size(); s++)
         if (b->det[s].run(b->e, rows, n, b->segs[s].g, b->thresh, 1, 1, edges[s], st)) return -1;
-    std::vector<ActJob> jobs; std::vector<ActOp> ops;
+    std::vector<ActJob> jobs; ActOps ops;
     jobs.reserve((size_t)n * 16 + 16); ops.reserve((size_t)n * 18 + 16);     /* no reallocation (and op copies) while the blocks are walked */
     for (int i = 0; i < n; i++) {
         /* detection in every segment first, then extraction segment by segment (work(), …vcm_impl.cc:553-566); both orders coincide

@@ -251,7 +251,7 @@ def test_segdet_state_machine_vs_oracle(FDC, ref, maxblocks, delay):
     assert np.array_equal(a.power(), b.power())
 
 
-@pytest.mark.parametrize("kind", ["noise", "crowded"])
+@pytest.mark.parametrize("kind", ["noise", "crowded", "ties"])
 def test_segdet_dense_scenes_vs_oracle(FDC, ref, kind):
     """hundreds of candidates per block: the candidate overlap test and the candidate/channel matching are done with binary
     searches here and with nested walks in the reference -- decisions, order of activation and PDUs must not differ"""
@@ -261,6 +261,18 @@ def test_segdet_dense_scenes_vs_oracle(FDC, ref, kind):
         x = (rng.standard_normal((14, N)) + 1j * rng.standard_normal((14, N))).astype(np.complex64)
         args = (0, N, 4, 0.02, 0.999, 3.0, 0.0001, 0.1, 2, 0, True, False, "", False, 0)
         chunks_a, chunks_b = (14,), (5, 9)
+    elif kind == "ties":             # hundreds of rising edges with EXACTLY equal ratios per block: the order among them is whatever the
+        N = 4096                     # reference's std::sort call leaves, and it decides channel ids and which overlapping candidate wins
+        rng = np.random.default_rng(21)
+        amp = np.ones((20, N), dtype=np.float32)
+        for b_ in range(20):
+            on = rng.random(N // 8) < 0.55          # 8-bin cells: 3 bins at amplitude 3 (power 9, ratio exactly 9) when the cell is on
+            for c_ in np.nonzero(on)[0]:
+                w_ = int(rng.integers(2, 5))
+                amp[b_, 8 * c_ + 2:8 * c_ + 2 + w_] = 3.0
+        x = amp.astype(np.complex64)
+        args = (1, N, 4, 0.02, 0.98, 6.0, 0.0001, 0.1, 3, 1, True, False, "", False, 0)
+        chunks_a, chunks_b = (20,), (7, 13)
     else:                            # several hundred narrow carriers switching on and off
         N = 32768
         x, _ = sc.bursty_spectra(N, 40, 400, seed=77, raster=64, widths=(24, 40), mean_on=3, mean_off=9, lo=0.05, hi=0.95)
