@@ -32,7 +32,9 @@ std::string current_time_string() { time_t raw; time(&raw); return time_string(r
 
 /* fmod(fmod(x, y) + 1, y) -- lib/SegmentDetection_impl.cc:700-703 */
 static float mod_f(float x, float y) { return (float)fmod(fmod((double)x, (double)y) + 1.0, (double)y); }
-static int nextpow2_shift(double v) { return 1 << (int)ceil(log2(v)); }   /* lib/SegmentDetection_impl.cc:705-708 */
+/* lib/SegmentDetection_impl.cc:705-708: 1 << (int)ceil(log2(v)) for the integer v >= 1 the caller passes: the smallest power of two
+ * >= v (log2 of a power of two is exact, and one more than a power of two already rounds up), computed on the bits */
+static long nextpow2_shift(long v) { return v <= 1 ? 1 : 1l << (64 - __builtin_clzl((unsigned long)(v - 1))); }
 
 /* ---- windows ------------------------------------------------------------------------------------ */
 void build_flank_windows(int blocklen, int relinvovl, double flank_puffer, std::vector<cfloat>& tab, std::vector<long>& offsets)
@@ -238,7 +240,7 @@ bool SegmentState::activate(long detect_start, long detect_end, long& uid_counte
     /* lib/SegmentDetection_impl.cc:290-344 */
     const long detect_width = detect_end - detect_start;
     const long extract_mid = detect_start + detect_width / 2;
-    const long extract_width = nextpow2_shift((double)(long)ceil((double)detect_width * (1.0 + 2.0 * flank)));
+    const long extract_width = nextpow2_shift((long)ceil((double)detect_width * (1.0 + 2.0 * flank)));
     if (extract_width > blocklen) return false;         /* the reference logs to cerr and skips the carrier */
     if (extract_width > max_extract_width) {
         if (!warned_wide) {
@@ -256,7 +258,7 @@ bool SegmentState::activate(long detect_start, long detect_end, long& uid_counte
     c.detect_start = (int)detect_start; c.detect_stop = (int)detect_end;
     c.ras_lo = (int)std::max(0l, (detect_start - g.start) / g.D - 1); c.ras_hi = (int)std::min((long)g.M, (detect_end - g.start) / g.D - 1);
     c.extract_start = (int)extract_start; c.extract_stop = (int)extract_end; c.extract_width = (int)extract_width;
-    c.extract_window = (int)log2((double)extract_width);
+    c.extract_window = __builtin_ctzl((unsigned long)extract_width);          /* (int)log2(extract_width), a power of two */
     c.ovlskip = (int)(extract_width / relinvovl);
     c.outputsamples = c.extract_width - c.ovlskip;
     c.count = 0; c.phase = 0; c.phaseincrement = (int)(extract_start % relinvovl); c.inactive = -1; c.part = 0;
