@@ -44,6 +44,14 @@ static void init_logfile(int verbose, const std::string& logfile)
 
 /* FDC_ACT_TIMING=1: wall-clock share of the phases of a work() call on stderr (measurement aid) */
 static bool act_timing() { static const bool on = getenv("FDC_ACT_TIMING") && atoi(getenv("FDC_ACT_TIMING")) > 0; return on; }
+/* FDC_ACT_TIMING=1: device-side split of a call's extraction (kernels / D2H), events destroyed on every exit path */
+struct ExtractEvents {
+    cudaEvent_t ev[3]; bool on;
+    explicit ExtractEvents(bool enable) : on(enable) { for (int i = 0; i < 3; i++) { ev[i] = 0; if (on && cudaEventCreate(&ev[i]) != cudaSuccess) on = false; } }
+    ~ExtractEvents() { for (int i = 0; i < 3; i++) if (ev[i]) cudaEventDestroy(ev[i]); }
+    void mark(int i, cudaStream_t st) { if (on) cudaEventRecord(ev[i], st); }
+    float ms(int a, int b) const { float t = 0; if (on) cudaEventElapsedTime(&t, ev[a], ev[b]); return t; }
+};
 struct PhaseClock {
     std::chrono::steady_clock::time_point t0; double ms[4]; int k;
     PhaseClock() : t0(std::chrono::steady_clock::now()), k(0) { ms[0] = ms[1] = ms[2] = ms[3] = 0; }
@@ -236,8 +244,8 @@ struct ActEngine {
             (!d_dst && (!d_out.reserve(sizeof(float2) * (size_t)total) || !h_out_buf().reserve(sizeof(float2) * (size_t)total))))
             return cuda_fail(cudaGetLastError(), "activity extract buffers");
         xc.lap();
-        cudaEvent_t ev[3] = {0, 0, 0};
-        if (act_timing()) { for (int i = 0; i < 3; i++) cudaEventCreate(&ev[i]); cudaEventRecord(ev[0], st); }
+        ExtractEvents ev(act_timing());
+        ev.mark(0, st);
         size_t k = 0;
         while (k < order.size()) {
             size_t e = k; const int L = jobs[order[k]].L;
@@ -249,18 +257,15 @@ struct ActEngine {
             k = e;
         }
         xc.lap();
-        if (ev[1]) cudaEventRecord(ev[1], st);
+        ev.mark(1, st);
         cudaError_t ce = d_dst ? cudaSuccess : cudaMemcpyAsync(h_out_buf().p, d_out.p, sizeof(float2) * (size_t)total, cudaMemcpyDeviceToHost, st);
-        if (ev[2]) cudaEventRecord(ev[2], st);
+        ev.mark(2, st);
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
         if (ce != cudaSuccess) return cuda_fail(ce, "activity extract D2H");
         xc.lap();
-        if (act_timing()) {
-            float tk = 0, tc = 0; cudaEventElapsedTime(&tk, ev[0], ev[1]); cudaEventElapsedTime(&tc, ev[1], ev[2]);
-            for (int i = 0; i < 3; i++) cudaEventDestroy(ev[i]);
+        if (ev.on)
             fprintf(stderr, "  extract: layout + job list %.3f ms, upload + buffers %.3f ms, launches %.3f ms, wait for kernels + D2H %.3f ms (device: kernels %.3f ms, D2H %.3f ms)\n",
-                    xc.ms[0], xc.ms[1], xc.ms[2], xc.ms[3], tk, tc);
-        }
+                    xc.ms[0], xc.ms[1], xc.ms[2], xc.ms[3], ev.ms(0, 1), ev.ms(1, 2));
         return 0;
     }
     /* replay the ops of a call on the extracted blocks (res + dst[job]) -> PDUs / files in the reference's order */

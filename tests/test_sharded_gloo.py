@@ -188,6 +188,32 @@ def test_sharded_activity_bookkeeping(world):
         assert got["group_" + name] == want, name
 
 
+def test_shard_layout_is_the_same_on_every_rank_and_covers_the_call():
+    """fdc_*_shard_layout (device form of the time-sharded call): every rank derives the offsets of ALL jobs of the call from
+    the replicated job list; the run holds exactly the samples of all ranks, by channel or in job order"""
+    for p in (ROOT, os.path.join(ROOT, "gr-fdc_b200", "python"), os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import FDC
+    from FDC import sharded
+    for name, mk in (("segdet", 0), ("actdet", 1), ("pac", 2)):
+        ranks = [_activity_blocks(FDC, 1024)[mk] for _ in range(3)]                # three "ranks": the same block built three times
+        P = ranks[0][2]
+        n = P.shape[0]
+        first, count = sharded.partition(n, 3)
+        recs = b"".join(ranks[r][1].shard_measure(count[r], power=P[first[r]:first[r] + count[r]]) for r in range(3))
+        with pytest.raises(RuntimeError):
+            ranks[0][1].shard_layout(True)                                          # nothing decided yet
+        njobs = [ranks[r][1].shard_decide(n, recs) for r in range(3)]
+        assert len(set(njobs)) == 1 and njobs[0] > 0, name
+        sizes = [ranks[0][1].shard_samples(first[r], count[r]) for r in range(3)]
+        for by_channel in (True, False):
+            totals = [ranks[r][1].shard_layout(by_channel) for r in range(3)]
+            assert totals == [sum(sizes)] * 3, (name, by_channel)
+        for r in range(3):
+            ranks[r][1].shard_assemble(None)
+
+
 def test_channel_owners_partition():
     """FDC.sharded.channel_owners: contiguous runs, every channel owned, volumes balanced to within one channel"""
     from FDC import sharded
