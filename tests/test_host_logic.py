@@ -34,6 +34,21 @@ def test_cabi_exports_every_declared_symbol(FDC):
     assert L.fdc_api_version() == 1
 
 
+def test_host_evict_keeps_the_data(FDC):
+    """fdc_host_evict only drops cache lines (clflushopt): any range, aligned or not, keeps its contents; needs no GPU"""
+    L = FDC._cabi.lib()
+    rng = np.random.default_rng(5)
+    a = rng.integers(0, 255, size=1 << 20, dtype=np.uint8)
+    want = a.copy()
+    for off, n in ((0, a.size), (1, 63), (64, 64), (4097, 100000), (a.size - 5, 5), (17, 0)):
+        L.fdc_host_evict(a.ctypes.data + off, n)
+    L.fdc_host_evict(None, 128)
+    assert np.array_equal(a, want)
+    a[100:200] = 7                                   # dirty lines are written back, not lost
+    L.fdc_host_evict(a.ctypes.data, a.size)
+    assert np.all(a[100:200] == 7) and np.array_equal(a[200:], want[200:])
+
+
 def test_no_cpu_fallback(FDC):
     if FDC._cabi.lib().fdc_device_count() > 0:
         pytest.skip("a CUDA device is present")
